@@ -1,0 +1,175 @@
+/*
+ * matchtigs_b200.h -- C ABI of the B200-native greedy-matchtig hot path.
+ *
+ * Two groups of entry points:
+ *
+ *  (1) `matchtigs_*`: the reference's own C API, names and signatures unchanged
+ *      (reference: src/clib.rs:90, :97, :135-141, :180-183, :280-290).  A program linked against
+ *      the Rust `libmatchtigs` dylib can link against this library instead.  Only
+ *      tig_algorithm 1 (unitigs) and 5 (greedy matchtigs -- see the id quirk at src/clib.rs:367-389)
+ *      are served; 2/3/4 (pathtigs, eulertigs, Blossom-V matchtigs) stay reference-only and
+ *      make the call fail loudly.
+ *
+ *  (2) `mtg_*`: the step API the (Rust) host calls underneath `TigAlgorithm::compute_tigs`
+ *      (reference seam: src/implementation/mod.rs:50-59, greedy impl src/implementation/greedytigs/mod.rs:75-90).
+ *      One entry per north-star step; each cites the reference region it replaces.
+ *
+ * Conventions: plain C types only; every `mtg_*` function returns 0 on success or a negative
+ * `mtg_status`, never throws or aborts, and leaves a message retrievable with mtg_last_error().
+ * A context is bound to one CUDA device and is not re-entrant.  There is no CPU fallback:
+ * without a usable CUDA device mtg_ctx_create fails with MTG_ERR_CUDA.
+ */
+#ifndef MATCHTIGS_B200_H
+#define MATCHTIGS_B200_H
+
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum mtg_status {
+    MTG_OK = 0,
+    MTG_ERR_INVALID = -1,  /* bad argument / call order */
+    MTG_ERR_CUDA = -2,     /* CUDA runtime error or no device */
+    MTG_ERR_INPUT = -3,    /* malformed input data (non-ACGT, sequence shorter than k, inconsistent links) */
+    MTG_ERR_INTERNAL = -4, /* invariant violated (the reference would panic) */
+    MTG_ERR_UNSUPPORTED = -5
+} mtg_status;
+
+typedef struct mtg_ctx mtg_ctx;
+
+/* Sizes of the resident graph. */
+typedef struct mtg_graph_info {
+    uint64_t unitigs;       /* U */
+    uint64_t nodes;         /* N: (k-1)-mer nodes incl. mirrors */
+    uint64_t edges;         /* 2U */
+    uint64_t short_edges;   /* directed edges with weight <= k-1 (all the Dijkstra can traverse) */
+    uint64_t sources;       /* S: out-imbalanced nodes (+ odd self-mirrors), ascending node id */
+    uint64_t targets;       /* in-imbalanced nodes (+ odd self-mirrors) */
+    uint64_t self_mirrors_unbalanced;
+    uint32_t k;
+} mtg_graph_info;
+
+/* Counters of the last mtg_dijkstra_candidates / mtg_greedy_match calls. */
+typedef struct mtg_search_stats {
+    uint64_t sources_searched;  /* sources that had at least one short out-edge */
+    uint64_t settled_nodes;     /* nodes popped with a final label (numerator of settled nodes/s) */
+    uint64_t relaxed_edges;     /* short out-edges inspected */
+    uint64_t candidates;        /* (dst, dist) records emitted */
+    uint64_t truncated_sources; /* lists cut at `cap` */
+    uint64_t overflow_sources;  /* sources that outgrew the shared-memory table and used the global-memory tier */
+    uint64_t match_rounds;      /* reservation rounds of the matching kernel */
+    uint64_t requery_phases;    /* extra search phases for sources whose capped list ran dry */
+    uint64_t matched;           /* triples produced */
+    float dijkstra_ms;          /* device time of the search kernels (CUDA events) */
+    float match_ms;             /* device time of the matching kernels */
+} mtg_search_stats;
+
+/* ---- lifecycle ---- */
+int mtg_ctx_create(mtg_ctx** out, int device);
+void mtg_ctx_destroy(mtg_ctx* ctx);
+const char* mtg_last_error(const mtg_ctx* ctx);
+/* The CUDA stream (cudaStream_t) every kernel of this context is launched on; for event timing by the caller. */
+void* mtg_ctx_stream(mtg_ctx* ctx);
+/* Number of kernels this context has launched since creation (the caller's gpu_launches claim). */
+uint64_t mtg_ctx_kernel_launches(const mtg_ctx* ctx);
+
+/* ---- step 1: bidirected unitig overlap graph ----
+ * Replaces read_bigraph_from_fasta_as_edge_centric (call site src/bin.rs:896-899) + compute_edge_weights
+ * (src/bin.rs:359-379) + the imbalance scan (src/implementation/greedytigs/mod.rs:222-245).
+ * `seq_ascii`: the U unitig sequences concatenated (ACGT only), `offsets[U+1]`: start of each unitig.
+ * Unitigs are packed to 2 bit, the canonical (k-1)-mer keys of both ends are extracted, radix-sorted and
+ * joined into node ids that equal the reference reader's first-seen numbering; CSR, mirror table,
+ * imbalances, sources and the target bitmap stay resident on the device.
+ * `seq_on_device` != 0: both pointers are device pointers (inputs already resident in HBM). */
+int mtg_build_graph_from_sequences(mtg_ctx* ctx, const char* seq_ascii, const uint64_t* offsets, uint64_t unitigs,
+                                   uint32_t k, int seq_on_device);
+
+/* Replaces matchtigs_merge_nodes + matchtigs_build_graph (src/clib.rs:135-170, :180-259) and, for --bcalm-in,
+ * read_bigraph_from_bcalm2_as_edge_centric (call site src/bin.rs:907-910).  Links are (a, strand_a, b, strand_b)
+ * in call order; `weights[U]` = k-mers per unitig.  Optional sequences (may be NULL) are only packed for output. */
+int mtg_build_graph_from_links(mtg_ctx* ctx, uint64_t unitigs, const uint64_t* weights, uint64_t n_links,
+                               const uint64_t* link_a, const uint8_t* strand_a, const uint64_t* link_b,
+                               const uint8_t* strand_b, uint32_t k, const char* seq_ascii, const uint64_t* offsets);
+
+int mtg_graph_get_info(mtg_ctx* ctx, mtg_graph_info* info);
+/* Copies the graph to host arrays (any pointer may be NULL): edge_from/edge_to [2U] (edge 2u = unitig u forward,
+ * 2u+1 = its mirror), mirror [N], imbalance [N], sources [S]. */
+int mtg_graph_export(mtg_ctx* ctx, uint32_t* edge_from, uint32_t* edge_to, uint32_t* mirror, int32_t* imbalance,
+                     uint32_t* sources);
+
+/* ---- step 2: many-source bounded Dijkstra ----
+ * Replaces the Dijkstra::shortest_path_lens calls and their work distribution
+ * (src/implementation/greedytigs/mod.rs:301-335, :557-627).  For every source with index i, i % shard_count ==
+ * shard_rank, computes the first `cap` initially-open in-nodes within distance k-1 in settle order
+ * (dist, node id) plus a `truncated` flag.  Results stay on the device. */
+int mtg_dijkstra_candidates(mtg_ctx* ctx, uint32_t cap, uint32_t shard_rank, uint32_t shard_count);
+/* Device pointers of this rank's candidate slice for the NVLink exchange: records are uint64
+ * (node | dist << 32), `cap` per source; meta is uint32 per source (count | truncated << 31).
+ * Local source l corresponds to global source l * shard_count + shard_rank. */
+int mtg_candidates_local(mtg_ctx* ctx, void** d_records, void** d_meta, uint64_t* sources_local, uint32_t* cap);
+/* Copies local candidate lists to the host (tests): nodes/dists [sources_local * cap], meta [sources_local]. */
+int mtg_candidates_export(mtg_ctx* ctx, uint32_t* nodes, uint32_t* dists, uint32_t* meta);
+
+/* ---- step 3: source-ordered greedy matching ----
+ * Replaces the matching body of compute_dijkstras (src/implementation/greedytigs/mod.rs:350-502) under the
+ * --threads 1 semantics.  `d_records_all` / `d_meta_all`: gathered candidate slices of all ranks, laid out
+ * [shard][local source] (pass NULL, NULL, 1 to use this context's own full-range result).
+ * Output: triples (out_node, in_node, dist) in the order of the reference's `results` vector. */
+int mtg_greedy_match(mtg_ctx* ctx, const void* d_records_all, const void* d_meta_all, uint32_t shard_count,
+                     uint64_t* n_triples);
+int mtg_triples_export(mtg_ctx* ctx, uint32_t* triples /* 3 * n_triples */);
+
+/* ---- host-sequential tail kept for byte parity (runs on the host inside the library) ----
+ * Dummy-edge insertion (greedytigs/mod.rs:678-689), make_graph_eulerian_with_breaking_edges
+ * (src/implementation/mod.rs:392-649), Euler decomposition (greedytigs/mod.rs:722) and cycle breaking
+ * (greedytigs/mod.rs:726-789).  Produces walks over edge ids: original edge e < 2U, dummy edges >= 2U. */
+int mtg_finish_walks(mtg_ctx* ctx, uint64_t* n_walks, uint64_t* n_walk_edges);
+/* walk_edges [n_walk_edges], walk_limits [n_walks] (end offsets), per-edge weight of dummies via mtg_edge_weight. */
+int mtg_walks_export(mtg_ctx* ctx, uint32_t* walk_edges, uint64_t* walk_limits);
+/* C-API encoding of the walks (src/clib.rs:393-407). */
+int mtg_walks_export_capi(mtg_ctx* ctx, ptrdiff_t* tigs_edge_out, size_t* tigs_insert_out, size_t* tigs_out_limits);
+
+/* ---- step 3b: outputs ----
+ * Duplicate-k-mer bitvector (src/implementation/mod.rs:671-702) and tig strings
+ * (write_walks_gfa src/bin.rs:667-818, write_walks_fasta :466-606), assembled on the device from the
+ * 2-bit store.  Call with out == NULL to obtain the required size. */
+int mtg_dup_bitvector(mtg_ctx* ctx, char* out, uint64_t cap, uint64_t* out_len);
+typedef enum mtg_text_format { MTG_FORMAT_GFA = 0, MTG_FORMAT_FASTA = 1 } mtg_text_format;
+int mtg_assemble_tigs(mtg_ctx* ctx, int format, char* out, uint64_t cap, uint64_t* out_len);
+
+/* Everything above in order (single GPU): build -> search -> match -> walks. */
+int mtg_compute_greedytigs_from_sequences(mtg_ctx* ctx, const char* seq_ascii, const uint64_t* offsets,
+                                          uint64_t unitigs, uint32_t k, uint32_t cap);
+int mtg_get_search_stats(mtg_ctx* ctx, mtg_search_stats* stats);
+
+/* ---- host-side record reader ----
+ * Splits FASTA / bcalm2 text into the arrays the step API takes; stands where genome-graph's readers stand
+ * (call sites src/bin.rs:896-899, 907-910).  `bcalm` != 0: record ids must equal their position and
+ * `L:<+/->:<id>:<+/->` header fields are returned as links in file order.  Character validation
+ * (ACGT only) happens on the device while packing. */
+typedef struct mtg_unitigs mtg_unitigs;
+int mtg_unitigs_parse(const char* text, size_t len, int bcalm, mtg_unitigs** out, char* errbuf, size_t errcap);
+void mtg_unitigs_free(mtg_unitigs* u);
+int mtg_unitigs_view(const mtg_unitigs* u, const char** seq, const uint64_t** offsets, uint64_t* unitigs,
+                     const uint64_t** link_a, const uint8_t** strand_a, const uint64_t** link_b,
+                     const uint8_t** strand_b, uint64_t* n_links);
+
+/* ---- the reference's C API (src/clib.rs) ---- */
+typedef struct MatchtigsData MatchtigsData;
+void matchtigs_initialise(void);                                          /* src/clib.rs:90 */
+MatchtigsData* matchtigs_initialise_graph(size_t unitig_amount);          /* src/clib.rs:97 */
+void matchtigs_merge_nodes(MatchtigsData* matchtigs_data, size_t unitig_a, bool strand_a, size_t unitig_b,
+                           bool strand_b);                                /* src/clib.rs:135-141 */
+void matchtigs_build_graph(MatchtigsData* matchtigs_data, const size_t* unitig_weights); /* src/clib.rs:180-183 */
+size_t matchtigs_compute_tigs(MatchtigsData* matchtigs_data, size_t tig_algorithm, size_t threads, size_t k,
+                              const char* matching_file_prefix, const char* matcher_path, ptrdiff_t* tigs_edge_out,
+                              size_t* tigs_insert_out, size_t* tigs_out_limits); /* src/clib.rs:280-290 */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MATCHTIGS_B200_H */

@@ -1,0 +1,365 @@
+// api.cpp -- the C ABI declared in include/matchtigs_b200.h: exception firewall around the
+// step functions plus the reference's own C API (src/clib.rs) on top of them.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include <algorithm>
+#include <memory>
+
+#include "mtg_internal.cuh"
+
+using namespace mtg;
+
+namespace {
+
+template <class F>
+int guarded(mtg_ctx* ctx, F&& f) {
+    if (!ctx) return MTG_ERR_INVALID;
+    try {
+        cudaError_t e = cudaSetDevice(ctx->device);
+        if (e != cudaSuccess) throw Error{MTG_ERR_CUDA, std::string("cudaSetDevice failed: ") + cudaGetErrorString(e)};
+        f();
+        ctx->err.clear();
+        return MTG_OK;
+    } catch (const Error& e) {
+        ctx->err = e.msg;
+        // leave the device in a defined state for the next call
+        cudaStreamSynchronize(ctx->stream);
+        cudaGetLastError();
+        return e.code;
+    } catch (const std::bad_alloc&) {
+        ctx->err = "out of host memory";
+        return MTG_ERR_INTERNAL;
+    } catch (const std::exception& e) {
+        ctx->err = e.what();
+        return MTG_ERR_INTERNAL;
+    } catch (...) {
+        ctx->err = "unknown error";
+        return MTG_ERR_INTERNAL;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int mtg_ctx_create(mtg_ctx** out, int device) {
+    if (!out) return MTG_ERR_INVALID;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) {
+        cudaGetLastError();
+        return MTG_ERR_CUDA;  // no CPU fallback: without a CUDA device there is no context
+    }
+    mtg_ctx* ctx = new (std::nothrow) mtg_ctx();
+    if (!ctx) return MTG_ERR_INTERNAL;
+    ctx->device = device;
+    int rc = guarded(ctx, [&] {
+        MTG_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        MTG_CUDA(cudaEventCreate(&ctx->ev0));
+        MTG_CUDA(cudaEventCreate(&ctx->ev1));
+        cudaDeviceProp prop{};
+        MTG_CUDA(cudaGetDeviceProperties(&prop, device));
+        ctx->num_sms = prop.multiProcessorCount;
+        MTG_REQUIRE(prop.cooperativeLaunch, MTG_ERR_CUDA, "device lacks cooperative launch");
+        cudaMemPool_t pool;
+        MTG_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+        unsigned long long keep = ~0ull;  // keep freed blocks cached: repeated runs reuse them
+        MTG_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    });
+    if (rc != MTG_OK) {
+        fprintf(stderr, "matchtigs_b200: context creation failed: %s\n", ctx->err.c_str());
+        delete ctx;
+        return rc;
+    }
+    *out = ctx;
+    return MTG_OK;
+}
+
+void mtg_ctx_destroy(mtg_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStream_t s = ctx->stream;
+    ctx->seq_words.release(s);
+    ctx->seq_off.release(s);
+    ctx->unitig_w.release(s);
+    ctx->edge_from.release(s);
+    ctx->edge_to.release(s);
+    ctx->mirror.release(s);
+    ctx->out_deg.release(s);
+    ctx->imbalance.release(s);
+    ctx->target_bits.release(s);
+    ctx->sources.release(s);
+    ctx->row_s.release(s);
+    ctx->col_s.release(s);
+    ctx->w_s.release(s);
+    ctx->cand.release(s);
+    ctx->cand_meta.release(s);
+    ctx->dstats.release(s);
+    ctx->triples.release(s);
+    ctx->d_walk_edges.release(s);
+    ctx->d_walk_limits.release(s);
+    ctx->d_dummy_w.release(s);
+    ctx->scratch_a.release(s);
+    ctx->scratch_b.release(s);
+    if (s) {
+        cudaStreamSynchronize(s);
+        cudaStreamDestroy(s);
+    }
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    delete ctx;
+}
+
+const char* mtg_last_error(const mtg_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+void* mtg_ctx_stream(mtg_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+uint64_t mtg_ctx_kernel_launches(const mtg_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int mtg_build_graph_from_sequences(mtg_ctx* ctx, const char* seq_ascii, const uint64_t* offsets, uint64_t unitigs, uint32_t k,
+                                   int seq_on_device) {
+    return guarded(ctx, [&] { build_graph_from_sequences(ctx, seq_ascii, offsets, unitigs, k, seq_on_device != 0); });
+}
+
+int mtg_build_graph_from_links(mtg_ctx* ctx, uint64_t unitigs, const uint64_t* weights, uint64_t n_links, const uint64_t* link_a,
+                               const uint8_t* strand_a, const uint64_t* link_b, const uint8_t* strand_b, uint32_t k,
+                               const char* seq_ascii, const uint64_t* offsets) {
+    return guarded(ctx, [&] {
+        build_graph_from_links(ctx, unitigs, weights, n_links, link_a, strand_a, link_b, strand_b, k, seq_ascii, offsets);
+    });
+}
+
+int mtg_graph_get_info(mtg_ctx* ctx, mtg_graph_info* info) {
+    return guarded(ctx, [&] {
+        MTG_REQUIRE(info && ctx->have_graph, MTG_ERR_INVALID, "no graph resident");
+        info->unitigs = ctx->U;
+        info->nodes = ctx->N;
+        info->edges = ctx->E;
+        info->short_edges = ctx->Es;
+        info->sources = ctx->S;
+        info->targets = ctx->T;
+        info->self_mirrors_unbalanced = ctx->self_mirror_unbalanced;
+        info->k = ctx->k;
+    });
+}
+
+int mtg_graph_export(mtg_ctx* ctx, uint32_t* edge_from, uint32_t* edge_to, uint32_t* mirror, int32_t* imbalance, uint32_t* sources) {
+    return guarded(ctx, [&] {
+        MTG_REQUIRE(ctx->have_graph, MTG_ERR_INVALID, "no graph resident");
+        cudaStream_t s = ctx->stream;
+        if (edge_from) ctx->edge_from.download(edge_from, s);
+        if (edge_to) ctx->edge_to.download(edge_to, s);
+        if (mirror) ctx->mirror.download(mirror, s);
+        if (imbalance) ctx->imbalance.download(imbalance, s);
+        if (sources) ctx->sources.download(sources, s);
+        MTG_CUDA(cudaStreamSynchronize(s));
+    });
+}
+
+int mtg_dijkstra_candidates(mtg_ctx* ctx, uint32_t cap, uint32_t shard_rank, uint32_t shard_count) {
+    return guarded(ctx, [&] { dijkstra_candidates(ctx, cap, shard_rank, shard_count); });
+}
+
+int mtg_candidates_local(mtg_ctx* ctx, void** d_records, void** d_meta, uint64_t* sources_local, uint32_t* cap) {
+    return guarded(ctx, [&] {
+        MTG_REQUIRE(ctx->have_cand, MTG_ERR_INVALID, "mtg_dijkstra_candidates has not run");
+        if (d_records) *d_records = ctx->cand.p;
+        if (d_meta) *d_meta = ctx->cand_meta.p;
+        if (sources_local) *sources_local = ctx->S_local;
+        if (cap) *cap = ctx->cap;
+    });
+}
+
+int mtg_candidates_export(mtg_ctx* ctx, uint32_t* nodes, uint32_t* dists, uint32_t* meta) {
+    return guarded(ctx, [&] {
+        MTG_REQUIRE(ctx->have_cand, MTG_ERR_INVALID, "mtg_dijkstra_candidates has not run");
+        cudaStream_t s = ctx->stream;
+        const size_t n = (size_t)ctx->S_local * ctx->cap;
+        std::vector<u64> rec(n);
+        if (n) MTG_CUDA(cudaMemcpyAsync(rec.data(), ctx->cand.p, n * sizeof(u64), cudaMemcpyDeviceToHost, s));
+        if (meta && ctx->S_local)
+            MTG_CUDA(cudaMemcpyAsync(meta, ctx->cand_meta.p, ctx->S_local * sizeof(u32), cudaMemcpyDeviceToHost, s));
+        MTG_CUDA(cudaStreamSynchronize(s));
+        for (size_t i = 0; i < n; i++) {
+            if (nodes) nodes[i] = (u32)rec[i];
+            if (dists) dists[i] = (u32)(rec[i] >> 32);
+        }
+    });
+}
+
+int mtg_greedy_match(mtg_ctx* ctx, const void* d_records_all, const void* d_meta_all, uint32_t shard_count, uint64_t* n_triples) {
+    return guarded(ctx, [&] {
+        greedy_match(ctx, (const u64*)d_records_all, (const u32*)d_meta_all, shard_count);
+        if (n_triples) *n_triples = ctx->n_triples;
+    });
+}
+
+int mtg_triples_export(mtg_ctx* ctx, uint32_t* triples) {
+    return guarded(ctx, [&] {
+        MTG_REQUIRE(ctx->have_triples, MTG_ERR_INVALID, "mtg_greedy_match has not run");
+        if (triples && ctx->n_triples) memcpy(triples, ctx->h_triples.data(), ctx->h_triples.size() * sizeof(u32));
+    });
+}
+
+int mtg_finish_walks(mtg_ctx* ctx, uint64_t* n_walks, uint64_t* n_walk_edges) {
+    return guarded(ctx, [&] {
+        finish_walks(ctx);
+        if (n_walks) *n_walks = ctx->walk_limits.size();
+        if (n_walk_edges) *n_walk_edges = ctx->walk_edges.size();
+    });
+}
+
+int mtg_walks_export(mtg_ctx* ctx, uint32_t* walk_edges, uint64_t* walk_limits) {
+    return guarded(ctx, [&] {
+        MTG_REQUIRE(ctx->have_walks, MTG_ERR_INVALID, "mtg_finish_walks has not run");
+        if (walk_edges && !ctx->walk_edges.empty()) memcpy(walk_edges, ctx->walk_edges.data(), ctx->walk_edges.size() * sizeof(u32));
+        if (walk_limits && !ctx->walk_limits.empty())
+            memcpy(walk_limits, ctx->walk_limits.data(), ctx->walk_limits.size() * sizeof(u64));
+    });
+}
+
+int mtg_walks_export_capi(mtg_ctx* ctx, ptrdiff_t* tigs_edge_out, size_t* tigs_insert_out, size_t* tigs_out_limits) {
+    return guarded(ctx, [&] {
+        MTG_REQUIRE(ctx->have_walks, MTG_ERR_INVALID, "mtg_finish_walks has not run");
+        MTG_REQUIRE(tigs_edge_out && tigs_insert_out && tigs_out_limits, MTG_ERR_INVALID, "null output array");
+        const HostGraph& g = ctx->hg;
+        // src/clib.rs:393-407: +-unitig id (dummies carry the default handle 0), dummy weight or 0, end offsets
+        for (size_t j = 0; j < ctx->walk_edges.size(); j++) {
+            u32 e = ctx->walk_edges[j];
+            bool fwd = !(e & 1);
+            if (g.dummy[e]) {
+                tigs_edge_out[j] = 0;
+                tigs_insert_out[j] = g.weight[e];
+            } else {
+                tigs_edge_out[j] = (ptrdiff_t)(e >> 1) * (fwd ? 1 : -1);
+                tigs_insert_out[j] = 0;
+            }
+        }
+        for (size_t i = 0; i < ctx->walk_limits.size(); i++) tigs_out_limits[i] = (size_t)ctx->walk_limits[i];
+    });
+}
+
+int mtg_dup_bitvector(mtg_ctx* ctx, char* out, uint64_t cap, uint64_t* out_len) {
+    return guarded(ctx, [&] {
+        u64 n = dup_bitvector(ctx, out, cap);
+        if (out_len) *out_len = n;
+    });
+}
+
+int mtg_assemble_tigs(mtg_ctx* ctx, int format, char* out, uint64_t cap, uint64_t* out_len) {
+    return guarded(ctx, [&] {
+        u64 n = assemble_tigs(ctx, format, out, cap);
+        if (out_len) *out_len = n;
+    });
+}
+
+int mtg_compute_greedytigs_from_sequences(mtg_ctx* ctx, const char* seq_ascii, const uint64_t* offsets, uint64_t unitigs, uint32_t k,
+                                          uint32_t cap) {
+    return guarded(ctx, [&] {
+        build_graph_from_sequences(ctx, seq_ascii, offsets, unitigs, k, false);
+        dijkstra_candidates(ctx, cap, 0, 1);
+        greedy_match(ctx, nullptr, nullptr, 1);
+        finish_walks(ctx);
+    });
+}
+
+int mtg_get_search_stats(mtg_ctx* ctx, mtg_search_stats* stats) {
+    return guarded(ctx, [&] {
+        MTG_REQUIRE(stats, MTG_ERR_INVALID, "null stats");
+        *stats = ctx->stats;
+    });
+}
+
+// =====================================================================================
+// The reference's C API (src/clib.rs).  Same names, argument meaning and error behaviour:
+// the reference has no error channel and panics, so failures print a message and abort().
+// =====================================================================================
+struct MatchtigsData {
+    size_t unitig_amount = 0;
+    std::vector<u64> a, b;
+    std::vector<u8> sa, sb;
+    std::vector<u64> weights;
+    bool built = false;
+};
+
+static bool g_initialised = false;
+
+[[noreturn]] static void clib_panic(const char* what) {
+    fprintf(stderr, "matchtigs (b200): %s\n", what);
+    abort();
+}
+
+void matchtigs_initialise(void) {
+    // src/clib.rs:90 -> initialise_logging(...).unwrap(): a second call panics (src/implementation/mod.rs:38-44)
+    if (g_initialised) clib_panic("matchtigs_initialise called twice");
+    g_initialised = true;
+}
+
+MatchtigsData* matchtigs_initialise_graph(size_t unitig_amount) {
+    MatchtigsData* d = new MatchtigsData();
+    d->unitig_amount = unitig_amount;
+    return d;
+}
+
+void matchtigs_merge_nodes(MatchtigsData* d, size_t unitig_a, bool strand_a, size_t unitig_b, bool strand_b) {
+    if (!d) clib_panic("matchtigs_merge_nodes: null handle");
+    if (unitig_a >= d->unitig_amount || unitig_b >= d->unitig_amount) clib_panic("matchtigs_merge_nodes: unitig id out of range");
+    d->a.push_back(unitig_a);
+    d->sa.push_back(strand_a ? 1 : 0);
+    d->b.push_back(unitig_b);
+    d->sb.push_back(strand_b ? 1 : 0);
+}
+
+void matchtigs_build_graph(MatchtigsData* d, const size_t* unitig_weights) {
+    if (!d) clib_panic("matchtigs_build_graph: null handle");
+    if (!unitig_weights) clib_panic("matchtigs_build_graph: unitig_weights is null");  // assert! src/clib.rs:188
+    d->weights.assign(unitig_weights, unitig_weights + d->unitig_amount);
+    d->built = true;  // the device graph is built by matchtigs_compute_tigs, which knows k
+}
+
+size_t matchtigs_compute_tigs(MatchtigsData* d, size_t tig_algorithm, size_t threads, size_t k, const char* matching_file_prefix,
+                              const char* matcher_path, ptrdiff_t* tigs_edge_out, size_t* tigs_insert_out, size_t* tigs_out_limits) {
+    (void)threads;
+    if (!d) clib_panic("matchtigs_compute_tigs: null handle");
+    std::unique_ptr<MatchtigsData> owned(d);  // the handle is consumed, like Box::from_raw (src/clib.rs:291)
+    if (!d->built) clib_panic("matchtigs_compute_tigs: matchtigs_build_graph was not called");
+    if (!matching_file_prefix) clib_panic("matching_file_prefix is null");  // assert! src/clib.rs:300
+    if (!matcher_path) clib_panic("matcher_path is null");                  // assert! src/clib.rs:316
+    if (!tigs_edge_out || !tigs_insert_out || !tigs_out_limits) clib_panic("output array is null");  // :333-345
+    const size_t U = d->unitig_amount;
+    if (tig_algorithm == 1) {  // unitigs: every forward edge on its own (src/clib.rs:351-361)
+        for (size_t u = 0; u < U; u++) {
+            tigs_edge_out[u] = (ptrdiff_t)u;
+            tigs_insert_out[u] = 0;
+            tigs_out_limits[u] = u + 1;
+        }
+        return U;
+    }
+    if (tig_algorithm != 5) {
+        if (tig_algorithm >= 2 && tig_algorithm <= 4)
+            clib_panic("tig algorithms 2 (pathtigs), 3 (eulertigs) and 4 (matchtigs) are reference-only; this library serves 1 and 5");
+        clib_panic("Unknown tigs algorithm identifier");  // src/clib.rs:390
+    }
+    mtg_ctx* ctx = nullptr;
+    int dev = 0;
+    if (const char* e = getenv("MTG_DEVICE")) dev = atoi(e);
+    if (mtg_ctx_create(&ctx, dev) != MTG_OK) clib_panic("no usable CUDA device (there is no CPU fallback)");
+    auto check = [&](int rc) {
+        if (rc != MTG_OK) {
+            fprintf(stderr, "matchtigs (b200): %s\n", mtg_last_error(ctx));
+            abort();
+        }
+    };
+    check(mtg_build_graph_from_links(ctx, U, d->weights.data(), d->a.size(), d->a.data(), d->sa.data(), d->b.data(), d->sb.data(),
+                                     (uint32_t)k, nullptr, nullptr));
+    check(mtg_dijkstra_candidates(ctx, 8, 0, 1));
+    uint64_t nt = 0, nw = 0, nwe = 0;
+    check(mtg_greedy_match(ctx, nullptr, nullptr, 1, &nt));
+    check(mtg_finish_walks(ctx, &nw, &nwe));
+    check(mtg_walks_export_capi(ctx, tigs_edge_out, tigs_insert_out, tigs_out_limits));
+    mtg_ctx_destroy(ctx);
+    return (size_t)nw;
+}
+
+}  // extern "C"

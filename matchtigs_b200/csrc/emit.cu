@@ -1,0 +1,221 @@
+// emit.cu -- step 3b: duplicate-k-mer bitvector (K6) and tig string assembly from the 2-bit store.
+//
+//   bitvector: write_duplication_bitvector, src/implementation/mod.rs:671-702
+//   strings:   write_walks_gfa src/bin.rs:667-818, write_walks_fasta src/bin.rs:466-606
+//
+// Both are prefix-sum + fill: every walk edge becomes a segment of the output text, an exclusive
+// scan of segment lengths gives its byte offset, and each thread then produces 16 consecutive
+// output bytes (one 128-bit store) after locating its first segment by binary search.
+#include <algorithm>
+#include <memory>
+
+#include "mtg_internal.cuh"
+
+namespace mtg {
+
+namespace {
+
+constexpr int TB = 256;
+constexpr int CHUNK = 16;
+
+__device__ __forceinline__ u32 dec_digits(u64 v) {
+    u32 d = 1;
+    while (v >= 10) {
+        v /= 10;
+        d++;
+    }
+    return d;
+}
+
+struct WalkView {
+    const u32* edges;     // [W]
+    const u64* limits;    // [T] end offsets
+    const u32* dummy_w;   // weights of dummy edges
+    const u32* unitig_w;  // [U]
+    const u64* seq_off;   // [U+1]
+    u64 W, T, E;          // E = 2U: ids >= E are dummies
+    u32 k;
+};
+
+__device__ __forceinline__ u64 tig_of(const WalkView& w, u64 j) {  // first t with limits[t] > j
+    u64 lo = 0, hi = w.T;
+    while (lo < hi) {
+        u64 mid = (lo + hi) >> 1;
+        if (w.limits[mid] > j) hi = mid;
+        else lo = mid + 1;
+    }
+    return lo;
+}
+
+// mode 0: bitvector, 1: GFA, 2: FASTA.  seg_len[j] = bytes walk edge j contributes (incl. header / newline).
+__global__ void __launch_bounds__(TB) segment_lengths(WalkView w, int mode, u32* __restrict__ seg_len, u32* __restrict__ seg_tig) {
+    u64 j = (u64)blockIdx.x * TB + threadIdx.x;
+    if (j >= w.W) return;
+    const u64 t = tig_of(w, j);
+    const u64 start = t ? w.limits[t - 1] : 0, end = w.limits[t];
+    const u32 e = w.edges[j];
+    const bool dummy = e >= w.E;
+    u32 len;
+    if (mode == 0) {
+        len = dummy ? w.dummy_w[e - w.E] : w.unitig_w[e >> 1];
+    } else if (dummy) {
+        len = 0;
+    } else {
+        const u32 full = w.unitig_w[e >> 1] + w.k - 1;
+        if (j == start) {
+            len = full + (mode == 1 ? 3 : 2) + dec_digits(t + 1);  // "S\t<i>\t" / "><i>\n"
+        } else {
+            const u32 pe = w.edges[j - 1];
+            const u32 skip = pe >= w.E ? w.k - 1 - w.dummy_w[pe - w.E] : w.k - 1;  // src/bin.rs:745-749
+            len = full - skip;
+        }
+    }
+    if (j + 1 == end) len += 1;  // '\n'
+    seg_len[j] = len;
+    seg_tig[j] = (u32)t;
+}
+
+__device__ __forceinline__ u64 segment_of(const u64* __restrict__ seg_off, u64 W, u64 q) {  // last j with seg_off[j] <= q
+    u64 lo = 0, hi = W;
+    while (lo < hi) {
+        u64 mid = (lo + hi) >> 1;
+        if (seg_off[mid] <= q) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo - 1;
+}
+
+__device__ __forceinline__ char decode_base(const u64* __restrict__ words, u64 pos, bool complement) {
+    u32 c = (u32)(words[pos >> 5] >> ((pos & 31) * 2)) & 3u;
+    if (complement) c ^= 2u;
+    return (char)((0x47544341u >> (8 * c)) & 0xFFu);  // "ACTG"
+}
+
+__global__ void __launch_bounds__(TB)
+    fill_text(WalkView w, int mode, const u64* __restrict__ seg_off, const u32* __restrict__ seg_len, const u32* __restrict__ seg_tig,
+              const u64* __restrict__ words, u64 total, char* __restrict__ out) {
+    const u64 q0 = ((u64)blockIdx.x * TB + threadIdx.x) * CHUNK;
+    if (q0 >= total) return;
+    u64 j = segment_of(seg_off, w.W, q0);
+    alignas(16) char buf[CHUNK];
+    u64 q = q0;
+    const u64 qend = min(q0 + (u64)CHUNK, total);
+    while (q < qend) {
+        while (seg_off[j] + seg_len[j] <= q) j++;  // skips empty segments
+        const u64 s0 = seg_off[j];
+        const u32 len = seg_len[j];
+        const u32 e = w.edges[j];
+        const bool dummy = e >= w.E;
+        const u64 t = seg_tig[j];
+        const u64 tstart = t ? w.limits[t - 1] : 0;
+        const bool last = (j + 1 == w.limits[t]);
+        u32 hdr = 0, skip = 0;
+        if (mode != 0 && !dummy) {
+            if (j == tstart) hdr = (mode == 1 ? 3 : 2) + dec_digits(t + 1);
+            else {
+                const u32 pe = w.edges[j - 1];
+                skip = pe >= w.E ? w.k - 1 - w.dummy_w[pe - w.E] : w.k - 1;
+            }
+        }
+        const u64 u = e >> 1;
+        const u64 sbeg = dummy ? 0 : w.seq_off[u], send = dummy ? 0 : w.seq_off[u + 1];
+        const bool fwd = !(e & 1);
+        const u64 seg_end = s0 + len;
+        for (; q < qend && q < seg_end; q++) {
+            const u32 c = (u32)(q - s0);
+            char ch;
+            if (last && c == len - 1) {
+                ch = '\n';
+            } else if (mode == 0) {
+                ch = dummy ? '0' : '1';
+            } else if (c < hdr) {
+                if (mode == 1) {
+                    if (c == 0) ch = 'S';
+                    else if (c == 1 || c == hdr - 1) ch = '\t';
+                    else {
+                        u64 v = t + 1;
+                        for (u32 r = hdr - 2 - c; r > 0; r--) v /= 10;
+                        ch = (char)('0' + v % 10);
+                    }
+                } else {
+                    if (c == 0) ch = '>';
+                    else if (c == hdr - 1) ch = '\n';
+                    else {
+                        u64 v = t + 1;
+                        for (u32 r = hdr - 2 - c; r > 0; r--) v /= 10;
+                        ch = (char)('0' + v % 10);
+                    }
+                }
+            } else {
+                const u64 b = (u64)(c - hdr) + skip;  // index into the oriented unitig string
+                ch = fwd ? decode_base(words, sbeg + b, false) : decode_base(words, send - 1 - b, true);
+            }
+            buf[q - q0] = ch;
+        }
+    }
+    if (qend - q0 == CHUNK) {
+        *reinterpret_cast<uint4*>(out + q0) = *reinterpret_cast<const uint4*>(buf);
+    } else {
+        for (u64 i = 0; i < qend - q0; i++) out[q0 + i] = buf[i];
+    }
+}
+
+u64 emit(mtg_ctx* ctx, int mode, const char* prefix, size_t prefix_len, char* out, u64 cap) {
+    MTG_REQUIRE(ctx->have_walks, MTG_ERR_INVALID, "no walks: call mtg_finish_walks first");
+    MTG_REQUIRE(mode == 0 || ctx->have_seqs, MTG_ERR_INVALID, "sequences were not supplied: tig strings cannot be assembled");
+    cudaStream_t s = ctx->stream;
+    WalkView w{};
+    w.edges = ctx->d_walk_edges.p;
+    w.limits = ctx->d_walk_limits.p;
+    w.dummy_w = ctx->d_dummy_w.p;
+    w.unitig_w = ctx->unitig_w.p;
+    w.seq_off = ctx->seq_off.p;
+    w.W = ctx->walk_edges.size();
+    w.T = ctx->walk_limits.size();
+    w.E = ctx->E;
+    w.k = ctx->k;
+    if (w.W == 0) {
+        if (out && cap >= prefix_len && prefix_len) memcpy(out, prefix, prefix_len);
+        return prefix_len;
+    }
+    DBuf<u32> seg_len, seg_tig;
+    DBuf<u64> seg_off;
+    seg_len.resize(w.W, s);
+    seg_tig.resize(w.W, s);
+    seg_off.resize(w.W + 1, s);
+    MTG_LAUNCH(ctx, segment_lengths, grid_for(w.W, TB), TB, 0, w, mode, seg_len.p, seg_tig.p);
+    exclusive_sum_u32_to_u64(ctx, seg_len.p, seg_off.p, w.W, seg_off.p + w.W);
+    u64 total = 0;
+    MTG_CUDA(cudaMemcpyAsync(&total, seg_off.p + w.W, sizeof(u64), cudaMemcpyDeviceToHost, s));
+    MTG_CUDA(cudaStreamSynchronize(s));
+    if (out) {
+        MTG_REQUIRE(cap >= total + prefix_len, MTG_ERR_INVALID, "output buffer too small");
+        char* d_out = nullptr;
+        MTG_CUDA(cudaMallocAsync((void**)&d_out, total + CHUNK, s));
+        u64 chunks = (total + CHUNK - 1) / CHUNK;
+        MTG_LAUNCH(ctx, fill_text, grid_for(chunks, TB), TB, 0, w, mode, seg_off.p, seg_len.p, seg_tig.p, ctx->seq_words.p, total, d_out);
+        if (prefix_len) memcpy(out, prefix, prefix_len);
+        MTG_CUDA(cudaMemcpyAsync(out + prefix_len, d_out, total, cudaMemcpyDeviceToHost, s));
+        MTG_CUDA(cudaStreamSynchronize(s));
+        MTG_CUDA(cudaFreeAsync(d_out, s));
+    }
+    seg_len.release(s);
+    seg_tig.release(s);
+    seg_off.release(s);
+    return total + prefix_len;
+}
+
+}  // namespace
+
+u64 dup_bitvector(mtg_ctx* ctx, char* out, u64 cap) { return emit(ctx, 0, nullptr, 0, out, cap); }
+
+u64 assemble_tigs(mtg_ctx* ctx, int format, char* out, u64 cap) {
+    MTG_REQUIRE(format == MTG_FORMAT_GFA || format == MTG_FORMAT_FASTA, MTG_ERR_INVALID, "unknown text format");
+    if (format == MTG_FORMAT_GFA) {
+        std::string header = "H\tKL:Z:" + std::to_string(ctx->k) + "\n";  // src/bin.rs:688-693
+        return emit(ctx, 1, header.data(), header.size(), out, cap);
+    }
+    return emit(ctx, 2, nullptr, 0, out, cap);
+}
+
+}  // namespace mtg

@@ -1,0 +1,194 @@
+// mtg_internal.cuh -- context, device buffers and launch helpers shared by the kernels.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "matchtigs_b200.h"
+
+namespace mtg {
+
+using u8 = uint8_t;
+using u16 = uint16_t;
+using u32 = uint32_t;
+using u64 = uint64_t;
+using i8 = int8_t;
+using i32 = int32_t;
+using i64 = int64_t;
+
+constexpr u32 NONE32 = 0xFFFFFFFFu;
+constexpr int NUM_SMS_B200 = 148;
+
+struct Error {
+    int code;
+    std::string msg;
+};
+
+#define MTG_CUDA(expr)                                                                                         \
+    do {                                                                                                       \
+        cudaError_t _e = (expr);                                                                               \
+        if (_e != cudaSuccess)                                                                                 \
+            throw ::mtg::Error{MTG_ERR_CUDA, std::string(#expr) + " failed: " + cudaGetErrorString(_e)};       \
+    } while (0)
+
+#define MTG_REQUIRE(cond, code, text)                   \
+    do {                                                \
+        if (!(cond)) throw ::mtg::Error{(code), (text)}; \
+    } while (0)
+
+// Stream-ordered device array that only ever grows; memory comes from the device's default
+// pool (cudaMallocAsync) whose release threshold the context raises, so repeated runs reuse it.
+template <class T>
+struct DBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    size_t n = 0;
+    void resize(size_t count, cudaStream_t s) {
+        if (count > cap) {
+            if (p) MTG_CUDA(cudaFreeAsync(p, s));
+            p = nullptr;
+            size_t want = count + count / 16 + 64;
+            MTG_CUDA(cudaMallocAsync((void**)&p, want * sizeof(T), s));
+            cap = want;
+        }
+        n = count;
+    }
+    void zero(cudaStream_t s) {
+        if (n) MTG_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s));
+    }
+    void fill_ff(cudaStream_t s) {
+        if (n) MTG_CUDA(cudaMemsetAsync(p, 0xFF, n * sizeof(T), s));
+    }
+    void release(cudaStream_t s) {
+        if (p) cudaFreeAsync(p, s);
+        p = nullptr;
+        cap = n = 0;
+    }
+    void upload(const T* h, size_t count, cudaStream_t s) {
+        resize(count, s);
+        if (count) MTG_CUDA(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s));
+    }
+    void download(T* h, cudaStream_t s) const {
+        if (n) MTG_CUDA(cudaMemcpyAsync(h, p, n * sizeof(T), cudaMemcpyDeviceToHost, s));
+    }
+};
+
+// Device-side counters of the search / matching kernels.
+struct DevStats {
+    unsigned long long sources_searched;
+    unsigned long long settled;
+    unsigned long long relaxed;
+    unsigned long long candidates;
+    unsigned long long truncated;
+    unsigned long long overflow;
+};
+
+// Host-side graph used by the sequential tail (host_tail.cpp).
+struct HostGraph {
+    u32 n_nodes = 0, n_orig_edges = 0;
+    std::vector<u32> from, to, mirror;   // all edges incl. dummies
+    std::vector<u32> weight;             // per edge (k-mers)
+    std::vector<u8> dummy;               // 1 = dummy edge
+    std::vector<u32> head_out, next_out; // newest-first out-adjacency
+    std::vector<u32> out_deg, in_deg;
+};
+
+}  // namespace mtg
+
+struct mtg_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+    int num_sms = mtg::NUM_SMS_B200;
+
+    // ---- resident graph (step 1) ----
+    uint32_t k = 0;
+    uint64_t U = 0, N = 0, E = 0, Es = 0, S = 0, T = 0, self_mirror_unbalanced = 0;
+    bool have_graph = false, have_seqs = false;
+    mtg::DBuf<mtg::u64> seq_words;    // 2-bit store: base i at bits [2(i%32), 2(i%32)+1] of word i/32; A0 C1 T2 G3
+    mtg::DBuf<mtg::u64> seq_off;      // [U+1] base offsets
+    uint64_t total_bases = 0;
+    mtg::DBuf<mtg::u32> unitig_w;     // [U] k-mers per unitig
+    mtg::DBuf<mtg::u32> edge_from, edge_to;  // [2U]
+    mtg::DBuf<mtg::u32> mirror;       // [N]
+    mtg::DBuf<mtg::u32> out_deg;      // [N]
+    mtg::DBuf<mtg::i32> imbalance;    // [N] initial node_multiplicities
+    mtg::DBuf<mtg::u32> target_bits;  // [(N+31)/32] initial in_node_map
+    mtg::DBuf<mtg::u32> sources;      // [S] ascending
+    mtg::DBuf<mtg::u32> row_s;        // [N+1] short-edge CSR
+    mtg::DBuf<mtg::u32> col_s;        // [Es]
+    mtg::DBuf<mtg::u8> w_s;           // [Es]
+
+    // ---- candidates (step 2) ----
+    uint32_t cap = 0, shard_rank = 0, shard_count = 1;
+    uint64_t S_local = 0;
+    mtg::DBuf<mtg::u64> cand;         // [S_local * cap]  node | dist << 32
+    mtg::DBuf<mtg::u32> cand_meta;    // [S_local]        count | truncated << 31
+    mtg::DBuf<mtg::DevStats> dstats;  // [1]
+    bool have_cand = false;
+
+    // ---- matching (step 3) ----
+    mtg::DBuf<mtg::u32> triples;      // [3 * n_triples] device
+    uint64_t n_triples = 0;
+    std::vector<uint32_t> h_triples;
+    bool have_triples = false;
+
+    // ---- host tail ----
+    mtg::HostGraph hg;
+    std::vector<uint32_t> walk_edges;
+    std::vector<uint64_t> walk_limits;
+    bool have_walks = false;
+    mtg::DBuf<mtg::u32> d_walk_edges;
+    mtg::DBuf<mtg::u64> d_walk_limits;
+    mtg::DBuf<mtg::u32> d_dummy_w;    // weights of dummy edges, index = edge id - 2U
+
+    mtg_search_stats stats{};
+    // scratch
+    mtg::DBuf<mtg::u8> scratch_a, scratch_b;
+};
+
+namespace mtg {
+
+inline dim3 grid_for(size_t n, int block) { return dim3((unsigned)((n + block - 1) / block)); }
+
+#define MTG_LAUNCH(ctx, kernel, grid, block, smem, ...)                         \
+    do {                                                                        \
+        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);        \
+        (ctx)->launches++;                                                      \
+        MTG_CUDA(cudaGetLastError());                                           \
+    } while (0)
+
+// ---- primitives (prims.cu) ----
+// out[i] = sum_{j<i} in[j]; returns nothing; `total` (device pointer, may be null) receives the grand total.
+void exclusive_sum_u32(mtg_ctx* ctx, const u32* in, u32* out, size_t n, u32* d_total);
+void exclusive_sum_u32_to_u64(mtg_ctx* ctx, const u32* in, u64* out, size_t n, u64* d_total);
+// out[i] = max_{j<=i} in[j]
+void inclusive_max_u32(mtg_ctx* ctx, const u32* in, u32* out, size_t n);
+// Stable LSD radix sort of (key words, value) by bits [0, key_bits) of the 64*nwords-bit key (word 0 = least significant).
+// Buffers ping-pong; returns 0 if the result is in the *_a buffers, 1 if in *_b.
+int radix_sort_pairs(mtg_ctx* ctx, u64* k0_a, u64* k0_b, u64* k1_a, u64* k1_b, u32* v_a, u32* v_b, size_t n,
+                     int nwords, int key_bits);
+int radix_sort_pairs_u32(mtg_ctx* ctx, u32* k_a, u32* k_b, u32* v_a, u32* v_b, size_t n, int key_bits);
+
+// ---- graph construction (graph.cu) ----
+void build_graph_from_sequences(mtg_ctx* ctx, const char* seq, const u64* offsets, u64 U, u32 k, bool on_device);
+void build_graph_from_links(mtg_ctx* ctx, u64 U, const u64* weights, u64 n_links, const u64* a, const u8* sa, const u64* b,
+                            const u8* sb, u32 k, const char* seq, const u64* offsets);
+
+// ---- search + matching (dijkstra.cu, match.cu) ----
+void dijkstra_candidates(mtg_ctx* ctx, u32 cap, u32 shard_rank, u32 shard_count);
+void greedy_match(mtg_ctx* ctx, const u64* d_records_all, const u32* d_meta_all, u32 shard_count);
+
+// ---- outputs (emit.cu) ----
+u64 dup_bitvector(mtg_ctx* ctx, char* out, u64 cap);
+u64 assemble_tigs(mtg_ctx* ctx, int format, char* out, u64 cap);
+
+// ---- host tail (host_tail.cpp) ----
+void finish_walks(mtg_ctx* ctx);
+
+}  // namespace mtg

@@ -1,0 +1,258 @@
+"""GPU parity tests: every stage of the CUDA path against the CPU oracle, through the C ABI.
+
+Run on the B200 box: ``python -m pytest tests -m gpu -x -q``.  Integer / byte work: bit-exact.
+"""
+import random
+
+import numpy as np
+import pytest
+
+import oracle
+import tools
+from helpers import check_tig_invariants, random_fasta
+
+pytestmark = pytest.mark.gpu
+
+META_COUNT = 0x00FFFFFF
+META_TRUNC = 0x80000000
+
+
+@pytest.fixture(scope="module")
+def mt():
+    import matchtigs_b200
+    return matchtigs_b200
+
+
+@pytest.fixture(scope="module")
+def ctx(mt):
+    c = mt.Context(0)
+    yield c
+    c.close()
+
+
+def run_oracle(text, k, mode):
+    o = oracle.Oracle()
+    (o.load_fasta if mode == "fasta" else o.load_bcalm)(text, k)
+    return o.run()
+
+
+def build(mt, ctx, text, k, mode):
+    if mode == "fasta":
+        return mt.read_bigraph_from_fasta_as_edge_centric(text, k, ctx)
+    return mt.read_bigraph_from_bcalm2_as_edge_centric(text, k, ctx)
+
+
+def compare_all(mt, ctx, text, k, mode, cap=8, dbg_valid=False, check_props=False):
+    o = run_oracle(text, k, mode)
+    g = build(mt, ctx, text, k, mode)
+    U = o.num("unitigs")
+    # --- step 1: graph ---
+    gi = ctx.graph_info()
+    assert gi["unitigs"] == U
+    assert gi["nodes"] == o.num("nodes"), "node count"
+    ex = ctx.graph_export()
+    assert np.array_equal(ex["edge_from"], o.array("edge_from")[:2 * U]), "edge_from"
+    assert np.array_equal(ex["edge_to"], o.array("edge_to")[:2 * U]), "edge_to"
+    assert np.array_equal(ex["mirror"], o.array("mirror")), "mirror"
+    assert np.array_equal(ex["imbalance"].astype(np.int64), o.array("mult0")), "imbalance"
+    assert np.array_equal(ex["sources"], o.array("out_nodes")), "sources"
+    assert gi["targets"] == int(o.array("in_node_map0").sum())
+    # --- step 2: candidate lists ---
+    ctx.dijkstra_candidates(cap)
+    nodes, dists, meta = ctx.candidates_export()
+    on, od, ol = o.candidates(cap)
+    cnt = (meta & META_COUNT).astype(np.int64)
+    assert np.array_equal(cnt, np.minimum(ol, cap)), "candidate counts"
+    trunc = (meta & META_TRUNC) != 0
+    assert not np.any(trunc & (ol <= cap) & (cnt < cap)), "truncated flag on a complete short list"
+    assert np.all(trunc[ol > cap]), "missing truncated flag"
+    mask = np.arange(cap)[None, :] < cnt[:, None]
+    assert np.array_equal(nodes[mask], on[mask]), "candidate nodes"
+    assert np.array_equal(dists[mask], od[mask]), "candidate distances"
+    # --- step 3: matching ---
+    tr = ctx.greedy_match()
+    assert np.array_equal(tr.reshape(-1), o.array("triples")), "matched triples"
+    # --- tail + outputs ---
+    ctx.finish_walks()
+    gw, ow = ctx.walks(), o.walks()
+    assert len(gw) == len(ow), "walk count"
+    for a, b in zip(gw, ow):
+        assert np.array_equal(a, b), "walk edges"
+    gfa, fa, bv = mt.write_walks_gfa(g), mt.write_walks_fasta(g), mt.write_duplication_bitvector(g)
+    assert gfa == o.text("gfa"), "GFA bytes"
+    assert fa == o.text("fasta"), "FASTA bytes"
+    assert bv == o.text("bitvector"), "bitvector bytes"
+    eo, io_, lim = ctx.walks_capi(U)
+    assert np.array_equal(eo, o.array("c_edge_out")) and np.array_equal(io_, o.array("c_insert_out"))
+    assert np.array_equal(lim, o.array("c_limits"))
+    if check_props:
+        check_tig_invariants(text, k, gfa, fa, bv, dbg_valid)
+    return o, ctx.search_stats()
+
+
+@pytest.mark.parametrize("mode", ["fasta", "bcalm"])
+@pytest.mark.parametrize("seed", range(3))
+def test_small_dbg(mt, ctx, mode, seed):
+    g = tools.genome(30_000, 10 + seed, families=6, copies=6, min_len=40, max_len=400, divergence=0.03, tandem_arrays=5)
+    text, _, _ = tools.unitigs(g, 21)
+    compare_all(mt, ctx, text, 21, mode, dbg_valid=True, check_props=True)
+
+
+@pytest.mark.parametrize("mode", ["fasta", "bcalm"])
+def test_pangenome_small(mt, ctx, mode):
+    anc = tools.genome(20_000, 51, families=3, copies=3, min_len=50, max_len=300, divergence=0.02)
+    strains = tools.pangenome(anc, 20, 7, snp_site_rate=0.04, indel_site_rate=0.003)
+    text, _, _ = tools.unitigs(strains, 15)
+    o, st = compare_all(mt, ctx, text, 15, mode, dbg_valid=True, check_props=True)
+    assert st["matched"] > 0
+
+
+@pytest.mark.parametrize("k", [2, 3, 4, 5, 8, 11, 16, 31, 32, 33, 34, 40, 51, 65])
+def test_arbitrary_fasta_all_k(mt, ctx, k):
+    for seed in range(4):
+        rng = random.Random(1000 * k + seed)
+        text = random_fasta(rng, rng.randint(1, 80), k, max_extra=12, pool=rng.choice([None, 3, 8]) if k > 2 else None)
+        compare_all(mt, ctx, text, k, "fasta", check_props=(k <= 11))
+
+
+@pytest.mark.parametrize("cap", [1, 2, 3, 8, 64])
+def test_cap_independence(mt, ctx, cap):
+    # dense graphs with many short edges: small caps force re-query phases, results must not change
+    for seed in range(4):
+        rng = random.Random(500 + seed)
+        k = rng.choice([7, 9, 11])
+        text = random_fasta(rng, rng.randint(100, 400), k, max_extra=6, pool=rng.choice([6, 12, 30]))
+        compare_all(mt, ctx, text, k, "fasta", cap=cap)
+
+
+def test_requery_phase_is_exercised(mt, ctx):
+    rng = random.Random(4242)
+    hit = 0
+    for _ in range(6):
+        text = random_fasta(rng, 400, 9, max_extra=4, pool=10)
+        _, st = compare_all(mt, ctx, text, 9, "fasta", cap=1)
+        hit += st["requery_phases"]
+    assert hit > 0, "cap=1 never ran out of candidates: the re-query path is untested"
+
+
+def test_overflow_tier(mt, ctx):
+    # single-k-mer unitigs (weight 1) drawn from a dense de Bruijn graph: balls of radius k-1 hold far more
+    # than the 320 labelled nodes of the shared-memory table, so tier 2 must produce the same lists
+    rng = random.Random(99)
+    k = 8
+    kmers = set()
+    while len(kmers) < 40000:
+        kmers.add(bytes(rng.choice(b"ACGT") for _ in range(k)))
+    text = b"".join(b">%d\n%s\n" % (i, s) for i, s in enumerate(sorted(kmers)))
+    _, st = compare_all(mt, ctx, text, k, "fasta", cap=16)
+    assert st["overflow_sources"] > 0, "tier 2 not exercised"
+
+
+def test_empty_and_degenerate_inputs(mt, ctx):
+    compare_all(mt, ctx, b"", 5, "fasta")
+    compare_all(mt, ctx, b">0\nACGTA\n", 5, "fasta")                # a single k-mer
+    compare_all(mt, ctx, b">0\nACGT\n", 5 - 1, "fasta")              # palindromic unitig, even k
+    compare_all(mt, ctx, b">0\nAAAAAA\n>1\nAAAAAA\n", 5, "fasta")   # duplicate records, self loops
+    compare_all(mt, ctx, b">0 LN:i:6\nACGTTT\n", 5, "bcalm")        # no links at all
+    compare_all(mt, ctx, b">0\nACGTA\nCCG\n>1\nCCGTT\n", 4, "fasta")  # multi-line record
+
+
+def test_input_errors(mt, ctx):
+    with pytest.raises(mt.MatchtigsError) as e:
+        mt.read_bigraph_from_fasta_as_edge_centric(b">0\nACGNT\n", 3, ctx)
+    assert e.value.code == -3
+    with pytest.raises(mt.MatchtigsError):
+        mt.read_bigraph_from_fasta_as_edge_centric(b">0\nAC\n", 5, ctx)
+    with pytest.raises(mt.MatchtigsError):
+        mt.read_bigraph_from_bcalm2_as_edge_centric(b">1 LN:i:5\nACGTA\n", 5, ctx)
+    with pytest.raises(mt.MatchtigsError):
+        mt.read_bigraph_from_bcalm2_as_edge_centric(b">0 LN:i:5 L:+:7:+\nACGTA\n", 5, ctx)
+    with pytest.raises(mt.MatchtigsError):
+        ctx.build_graph_from_sequences(np.frombuffer(b"ACGT", np.uint8), np.array([0, 4], np.uint64), 99)
+    # the context stays usable after errors
+    compare_all(mt, ctx, b">0\nACGTA\n", 5, "fasta")
+
+
+def test_sharded_candidates_equal_full(mt, ctx):
+    anc = tools.genome(20_000, 3, families=3, copies=3, min_len=50, max_len=300, divergence=0.02)
+    text, _, _ = tools.unitigs(tools.pangenome(anc, 10, 9, snp_site_rate=0.04), 15)
+    mt.read_bigraph_from_bcalm2_as_edge_centric(text, 15, ctx)
+    ctx.dijkstra_candidates(8)
+    fn, fd, fm = ctx.candidates_export()
+    for R in (2, 3):
+        for r in range(R):
+            ctx.dijkstra_candidates(8, r, R)
+            n, d, m = ctx.candidates_export()
+            assert np.array_equal(m, fm[r::R]) and np.array_equal(n, fn[r::R]) and np.array_equal(d, fd[r::R])
+
+
+def test_gathered_match_equals_single(mt, ctx):
+    """Matching from slices laid out [shard][local] (what the NCCL all-gather produces) == single-GPU result."""
+    import torch
+    anc = tools.genome(20_000, 4, families=3, copies=3, min_len=50, max_len=300, divergence=0.02)
+    text, _, _ = tools.unitigs(tools.pangenome(anc, 10, 11, snp_site_rate=0.04), 15)
+    mt.read_bigraph_from_bcalm2_as_edge_centric(text, 15, ctx)
+    ctx.dijkstra_candidates(8)
+    want = ctx.greedy_match().copy()
+    S = ctx.graph_info()["sources"]
+    R, cap = 3, 8
+    padded = (S + R - 1) // R
+    rec = torch.zeros((R, padded, cap), dtype=torch.int64, device="cuda")
+    meta = torch.zeros((R, padded), dtype=torch.int32, device="cuda")
+    for r in range(R):
+        ctx.dijkstra_candidates(cap, r, R)
+        prec, pmeta, n, c = ctx.candidates_local()
+        rec[r].copy_(mt.api.device_tensor(prec, (padded, cap), "<i8"))
+        meta[r].copy_(mt.api.device_tensor(pmeta, (padded,), "<i4"))
+    torch.cuda.synchronize()
+    got = ctx.greedy_match(rec.data_ptr(), meta.data_ptr(), R)
+    assert np.array_equal(got, want)
+
+
+def test_reference_c_api(mt):
+    """The five matchtigs_* symbols (src/clib.rs) against the oracle's C-API flavour."""
+    l = mt._lib.load() if hasattr(mt, "_lib") else None
+    from matchtigs_b200 import _lib
+    l = _lib.load()
+    rng = random.Random(31)
+    U, k = 60, 9
+    weights = np.array([rng.randint(1, 14) for _ in range(U)], dtype=np.uint64)
+    # consistent links: derive them from a random arbitrary FASTA via the oracle-independent rule "suffix == prefix"
+    seqs = []
+    text = random_fasta(rng, U, k, max_extra=6, pool=8)
+    from helpers import parse_fasta_seqs, revcomp
+    seqs = parse_fasta_seqs(text)
+    weights = np.array([len(s) - k + 1 for s in seqs], dtype=np.uint64)
+    links = []
+    ori = lambda s, f: s if f else revcomp(s)
+    for a in range(U):
+        for fa in (True, False):
+            for b in range(U):
+                for fb in (True, False):
+                    if ori(seqs[a], fa)[-(k - 1):] == ori(seqs[b], fb)[:k - 1]:
+                        links.append((a, fa, b, fb))
+    o = oracle.Oracle().load_links(weights, links, k).run()
+    l.matchtigs_initialise()
+    h = l.matchtigs_initialise_graph(U)
+    for a, fa, b, fb in links:
+        l.matchtigs_merge_nodes(h, a, fa, b, fb)
+    l.matchtigs_build_graph(h, weights.ctypes.data)
+    eo, io_ = np.zeros(4 * U, np.int64), np.zeros(4 * U, np.uint64)
+    lim = np.zeros(2 * U, np.uint64)
+    n = l.matchtigs_compute_tigs(h, 5, 1, k, b"unused", b"unused", eo.ctypes.data, io_.ctypes.data, lim.ctypes.data)
+    assert n == o.num("walks")
+    ne = int(lim[n - 1])
+    assert np.array_equal(eo[:ne], o.array("c_edge_out")) and np.array_equal(io_[:ne], o.array("c_insert_out"))
+    assert np.array_equal(lim[:n], o.array("c_limits"))
+    # algorithm 1 = unitigs
+    h = l.matchtigs_initialise_graph(3)
+    l.matchtigs_build_graph(h, np.array([1, 2, 3], np.uint64).ctypes.data)
+    n = l.matchtigs_compute_tigs(h, 1, 1, 5, b"", b"", eo.ctypes.data, io_.ctypes.data, lim.ctypes.data)
+    assert n == 3 and list(eo[:3]) == [0, 1, 2] and list(lim[:3]) == [1, 2, 3]
+
+
+def test_ecoli_scale_properties(mt, ctx):
+    """BASELINE config 2 at 1/4 scale: byte identity + the size-independent properties."""
+    text, k, info = tools.config_unitigs("ecoli", 0.25)
+    compare_all(mt, ctx, text, k, "bcalm", dbg_valid=True, check_props=False)
+    compare_all(mt, ctx, text, k, "fasta", dbg_valid=True, check_props=False)
