@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py -- greedy-matchtig throughput on synthetic unitigs (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME] [--scale F]
+
+One "step" = one pass of the whole hot path over one batch of unitigs:
+graph build (2-bit pack, end keys, radix sort, join, CSR) -> many-source bounded Dijkstra ->
+greedy matching -> host Euler tail -> duplicate-k-mer bitvector + GFA assembly.
+
+* ``value``: unitigs/s with the unitig characters already resident in HBM when the timed region starts.
+* ``e2e``:   the same through the public API with HOST buffers (H2D of the characters and D2H of the
+             GFA + bitvector bytes inside the timed region).
+* ``roofline``: the dominant kernel (the Dijkstra tier-1 kernel) against measured HBM bandwidth.
+* ``cpu_baseline``: the CPU oracle (a C++ restatement of matchtigs 2.1.9 greedy, NOT the Rust binary) on
+  the same workload, 1 thread (the deterministic reference semantics).
+* ``--impl reference``: the same oracle with all host threads it can use (the reference's worker scheme).
+
+N > 1 (torchrun): the graph is replicated, Dijkstra sources are sharded i % N == rank, candidate slices
+are all-gathered over NCCL, the matching is replicated, rank 0 finishes the walks and outputs.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name -> (tools.config_unitigs name, default scale, description)
+    "ecoli": ("ecoli", 1.0, "config[1]: synthetic 4.6 Mbp E. coli-sized genome with injected repeats, k=31, "
+                            "unitigs -> greedy matchtigs GFA + duplicate-kmer bitvector"),
+    "pangenome": ("pangenome", 0.25, "config[3] (scaled): synthetic pangenome, 100 strains with SNP/indel variation, k=31"),
+    "chr1": ("chr1", 0.1, "config[2] (scaled): synthetic chr1-like genome with repeat families, k=31"),
+    "human": ("human", 0.01, "config[4] (scaled): synthetic human-like genome, k=51"),
+}
+CAP = 8
+
+
+def load_peaks() -> tuple[float, str]:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_workload(name: str, scale: float | None):
+    import tools
+    cfg, dscale, desc = WORKLOADS[name]
+    scale = dscale if scale is None else scale
+    t0 = time.time()
+    text, k, info = tools.config_unitigs(cfg, scale)
+    info["generate_s"] = round(time.time() - t0, 2)
+    info["description"] = desc
+    return text, k, info
+
+
+# ----------------------------------------------------------------------------------------------
+# reference arm: the CPU oracle with every host thread (C++ restatement, not the Rust binary)
+# ----------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # other ranks exit 0 without work
+    import oracle
+    text, k, info = make_workload(args.workload, args.scale)
+    cores = os.cpu_count() or 1
+    U = info["unitigs"]
+    times, settled = [], 0
+    for it in range(args.warmup + args.steps):
+        o = oracle.Oracle(euler_fast=True)
+        t0 = time.perf_counter()
+        o.load_fasta(text, k)
+        o.run(threads=cores)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+            settled = o.num("settled")
+            dj = o.time("dijkstra")
+    ms = 1e3 * float(np.mean(times))
+    value = U / (ms / 1e3)
+    line = {
+        "impl": "reference", "metric": "greedy_matchtig_unitigs_per_sec", "value": value, "unit": "unitigs/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": args.workload, "k": k, **{k_: info[k_] for k_ in ("scale", "unitigs", "distinct_kmers", "input_bp")}},
+        "cpu_baseline": {"value": value, "unit": "unitigs/s", "cores": cores, "kind": "port",
+                         "sample": "whole workload per step; C++ restatement of matchtigs 2.1.9 greedy with the reference's "
+                                   "worker scheme (not the Rust binary, which cannot be built in this image)"},
+        "e2e": {"value": value, "unit": "unitigs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "settled_nodes_per_sec": settled / dj if dj > 0 else None,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import matchtigs_b200 as mt
+    from matchtigs_b200.api import device_tensor
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; matchtigs_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    text, k, info = make_workload(args.workload, args.scale)
+    units = mt.Unitigs(text, bcalm=False)
+    U = units.count
+    seq_host = torch.from_numpy(units.seq.copy()).pin_memory()
+    off_host = torch.from_numpy(units.offsets.astype(np.int64)).pin_memory()
+    seq_dev, off_dev = seq_host.cuda(), off_host.cuda()
+    ctx = mt.Context(local_rank)
+    ext = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step(resident: bool):
+        """One pass of the hot path.  Returns (gfa, bitvector) on rank 0."""
+        if resident:
+            ctx.build_graph_from_device_sequences(seq_dev.data_ptr(), off_dev.data_ptr(), U, k)
+        else:
+            ctx.build_graph_from_sequences(seq_host.numpy(), off_host.numpy().view(np.uint64), k)
+        if world == 1:
+            ctx.dijkstra_candidates(CAP, 0, 1)
+            ctx.greedy_match()
+        else:
+            ctx.dijkstra_candidates(CAP, rank, world)
+            prec, pmeta, n_local, cap = ctx.candidates_local()
+            S = ctx.graph_info()["sources"]
+            padded = max((S + world - 1) // world, 1)
+            rec_all = torch.empty((world, padded, cap), dtype=torch.int64, device="cuda")
+            meta_all = torch.empty((world, padded), dtype=torch.int32, device="cuda")
+            dist.all_gather_into_tensor(rec_all, device_tensor(prec, (padded, cap), "<i8"))
+            dist.all_gather_into_tensor(meta_all, device_tensor(pmeta, (padded,), "<i4"))
+            torch.cuda.synchronize()
+            ctx.greedy_match(rec_all.data_ptr(), meta_all.data_ptr(), world)
+        if rank == 0:
+            ctx.finish_walks()
+            return ctx.assemble_tigs("gfa"), ctx.dup_bitvector()
+        return None, None
+
+    def timed(resident: bool, steps: int, warmup: int):
+        for _ in range(warmup):
+            step(resident)
+        barrier()
+        total_ms, dj_ms, mt_ms, stats, out = 0.0, 0.0, 0.0, None, None
+        launches0 = ctx.kernel_launches
+        for _ in range(steps):
+            with torch.cuda.stream(ext):
+                flush.zero_()  # evict L2 between timed iterations (outside the event pair)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            e0.record(ext)
+            out = step(resident)
+            e1.record(ext)
+            barrier()
+            total_ms += e0.elapsed_time(e1)
+            stats = ctx.search_stats()
+            dj_ms += stats["dijkstra_ms"]
+            mt_ms += stats["match_ms"]
+        launches = ctx.kernel_launches - launches0
+        t = torch.tensor([total_ms, dj_ms, mt_ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, dj_ms, mt_ms = (float(x) for x in t.cpu())
+        return total_ms / steps, dj_ms / steps, mt_ms / steps, stats, launches, out
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_res, dj_ms, match_ms, stats, launches, _ = timed(True, args.steps, args.warmup)
+    ms_e2e, _, _, _, _, out = timed(False, args.steps, max(1, args.warmup // 2))
+    clocks = sampler.stop() if rank == 0 else None
+
+    # settled / relaxed / candidates summed over ranks for the roofline numerator
+    cnt = torch.tensor([stats["settled_nodes"], stats["relaxed_edges"], stats["candidates"], stats["sources_searched"]],
+                       dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    settled, relaxed, cands, searched = (float(x) for x in cnt.cpu())
+
+    if rank == 0:
+        gi = ctx.graph_info()
+        gfa, bv = out
+        peak, peak_src = load_peaks()
+        # algorithmic bytes of the Dijkstra kernel: 12 B per settled node (row_ptr pair + target probe),
+        # 5 B per relaxed short edge (col + weight), 8 B per emitted candidate
+        alg_bytes = 12.0 * settled + 5.0 * relaxed + 8.0 * cands
+        achieved = alg_bytes / world / (dj_ms * 1e-3) / 1e9 if dj_ms > 0 else 0.0
+        # cpu baseline: the oracle at 1 thread (deterministic reference semantics), whole workload, once
+        import oracle
+        o = oracle.Oracle(euler_fast=True)
+        t0 = time.perf_counter()
+        o.load_fasta(text, k)
+        o.run(1)
+        cpu_s = time.perf_counter() - t0
+        identical = (gfa == o.text("gfa")) and (bv == o.text("bitvector"))
+        line = {
+            "metric": "greedy_matchtig_unitigs_per_sec", "value": U / (ms_res * 1e-3), "unit": "unitigs/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_res,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": args.workload, "description": info["description"], "k": k, "scale": info["scale"],
+                       "unitigs": U, "nodes": gi["nodes"], "sources": gi["sources"], "short_edges": gi["short_edges"],
+                       "distinct_kmers": info["distinct_kmers"], "input_bp": info["input_bp"], "candidate_cap": CAP,
+                       "l2": "flushed between timed iterations (256 MiB memset)", "reader": "fa-in semantics (k-mer join)",
+                       "parallelism": f"sources sharded over {world} GPU(s), graph replicated"},
+            "e2e": {"value": U / (ms_e2e * 1e-3), "unit": "unitigs/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": int(seq_host.numel() + off_host.numel() * 8),
+                    "d2h_bytes_per_step": int(len(gfa) + len(bv))},
+            "gpu_launches": int(launches),
+            "settled_nodes_per_sec": settled / (dj_ms * 1e-3) if dj_ms > 0 else None,
+            "dijkstra": {"ms_per_step": dj_ms, "settled_nodes": settled, "relaxed_edges": relaxed, "candidates": cands,
+                         "sources_searched": searched, "match_ms_per_step": match_ms, "match_rounds": stats["match_rounds"],
+                         "requery_phases": stats["requery_phases"], "overflow_sources": stats["overflow_sources"]},
+            "roofline": {"kernel": "dijkstra_warp_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes / world,
+                         "note": "random 32-B-sector gather regime; working set of this workload fits in L2"},
+            "cpu_baseline": {"value": U / cpu_s, "unit": "unitigs/s", "cores": 1, "kind": "port",
+                             "sample": "whole workload, one run; C++ restatement of matchtigs 2.1.9 greedy at --threads 1 "
+                                       "(not the Rust binary)", "seconds": cpu_s},
+            "byte_identical_to_oracle": bool(identical),
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="ecoli", choices=sorted(WORKLOADS))
+    ap.add_argument("--scale", type=float, default=None)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -133,6 +133,17 @@ int mtg_walks_export(mtg_ctx* ctx, uint32_t* walk_edges, uint64_t* walk_limits);
 /* C-API encoding of the walks (src/clib.rs:393-407). */
 int mtg_walks_export_capi(mtg_ctx* ctx, ptrdiff_t* tigs_edge_out, size_t* tigs_insert_out, size_t* tigs_out_limits);
 
+/* The same tail on caller-supplied host arrays, no GPU involved (what mtg_finish_walks runs after copying
+ * the graph and the triples back).  edge_from/edge_to [2*unitigs], unitig_w [unitigs], mirror [nodes],
+ * triples [3*n_triples].  Outputs are malloc'd (release with mtg_host_free): walk_edges, walk_limits (end
+ * offsets), dummy_w (weight of dummy edge e at [e - 2*unitigs]).  phase_ms[5] (optional): degrees, eulerise,
+ * adjacency, Euler walk, breaking. */
+int mtg_host_tail(uint32_t k, uint64_t nodes, uint64_t unitigs, const uint32_t* edge_from, const uint32_t* edge_to,
+                  const uint32_t* unitig_w, const uint32_t* mirror, const uint32_t* triples, uint64_t n_triples,
+                  uint32_t** walk_edges, uint64_t** walk_limits, uint32_t** dummy_w, uint64_t* n_walks,
+                  uint64_t* n_walk_edges, uint64_t* n_dummy_edges, double* phase_ms, char* errbuf, size_t errcap);
+void mtg_host_free(void* p);
+
 /* ---- step 3b: outputs ----
  * Duplicate-k-mer bitvector (src/implementation/mod.rs:671-702) and tig strings
  * (write_walks_gfa src/bin.rs:667-818, write_walks_fasta :466-606), assembled on the device from the
@@ -145,6 +156,9 @@ int mtg_assemble_tigs(mtg_ctx* ctx, int format, char* out, uint64_t cap, uint64_
 int mtg_compute_greedytigs_from_sequences(mtg_ctx* ctx, const char* seq_ascii, const uint64_t* offsets,
                                           uint64_t unitigs, uint32_t k, uint32_t cap);
 int mtg_get_search_stats(mtg_ctx* ctx, mtg_search_stats* stats);
+/* Diagnostics of the last run: host-tail phases in ms (degrees, eulerise, adjacency, Euler walk, breaking) and the
+ * number of pending sources at the start of each of the first 48 matching rounds. */
+int mtg_get_diagnostics(mtg_ctx* ctx, double tail_ms[5], uint32_t match_pending[48]);
 
 /* ---- host-side record reader ----
  * Splits FASTA / bcalm2 text into the arrays the step API takes; stands where genome-graph's readers stand

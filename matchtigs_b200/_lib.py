@@ -20,9 +20,9 @@ EXPORTED_SYMBOLS = [
     "mtg_build_graph_from_sequences", "mtg_build_graph_from_links", "mtg_graph_get_info", "mtg_graph_export",
     "mtg_dijkstra_candidates", "mtg_candidates_local", "mtg_candidates_export",
     "mtg_greedy_match", "mtg_triples_export",
-    "mtg_finish_walks", "mtg_walks_export", "mtg_walks_export_capi",
+    "mtg_finish_walks", "mtg_walks_export", "mtg_walks_export_capi", "mtg_host_tail", "mtg_host_free",
     "mtg_dup_bitvector", "mtg_assemble_tigs",
-    "mtg_compute_greedytigs_from_sequences", "mtg_get_search_stats",
+    "mtg_compute_greedytigs_from_sequences", "mtg_get_search_stats", "mtg_get_diagnostics",
     "mtg_unitigs_parse", "mtg_unitigs_free", "mtg_unitigs_view",
     "matchtigs_initialise", "matchtigs_initialise_graph", "matchtigs_merge_nodes", "matchtigs_build_graph",
     "matchtigs_compute_tigs",
@@ -82,10 +82,15 @@ def load() -> C.CDLL:
     l.mtg_finish_walks.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
     l.mtg_walks_export.argtypes = [vp, vp, vp]
     l.mtg_walks_export_capi.argtypes = [vp, vp, vp, vp]
+    l.mtg_host_tail.argtypes = [u32, u64, u64, vp, vp, vp, vp, vp, u64, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp),
+                                C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), C.POINTER(C.c_double), C.c_char_p, C.c_size_t]
+    l.mtg_host_free.argtypes = [vp]
+    l.mtg_host_free.restype = None
     l.mtg_dup_bitvector.argtypes = [vp, vp, u64, C.POINTER(u64)]
     l.mtg_assemble_tigs.argtypes = [vp, i32, vp, u64, C.POINTER(u64)]
     l.mtg_compute_greedytigs_from_sequences.argtypes = [vp, vp, vp, u64, u32, u32]
     l.mtg_get_search_stats.argtypes = [vp, C.POINTER(SearchStats)]
+    l.mtg_get_diagnostics.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint32)]
     l.mtg_unitigs_parse.argtypes = [C.c_char_p, C.c_size_t, i32, C.POINTER(vp), C.c_char_p, C.c_size_t]
     l.mtg_unitigs_free.argtypes = [vp]
     l.mtg_unitigs_free.restype = None

@@ -195,6 +195,12 @@ class Context:
         self._check(self._l.mtg_get_search_stats(self._h, C.byref(st)))
         return st.as_dict()
 
+    def diagnostics(self) -> dict:
+        ms, hist = (C.c_double * 5)(), (C.c_uint32 * 48)()
+        self._check(self._l.mtg_get_diagnostics(self._h, ms, hist))
+        names = ["degrees", "eulerise", "adjacency", "euler_walk", "breaking"]
+        return {"tail_ms": {n: round(float(v), 3) for n, v in zip(names, ms)}, "match_pending": [int(x) for x in hist if x]}
+
     @property
     def kernel_launches(self) -> int:
         return self._l.mtg_ctx_kernel_launches(self._h)
@@ -202,6 +208,36 @@ class Context:
     @property
     def stream(self) -> int:
         return self._l.mtg_ctx_stream(self._h) or 0
+
+
+def host_tail(k: int, edge_from, edge_to, unitig_w, mirror, triples):
+    """The host-sequential tail (dummy insertion, eulerise, Euler decomposition, breaking) on host arrays; no GPU.
+
+    Returns (walks, dummy_w, phase_ms) with walks as a list of edge-id arrays (ids >= 2U are dummy edges)."""
+    l = _lib.load()
+    ef, et = np.ascontiguousarray(edge_from, np.uint32), np.ascontiguousarray(edge_to, np.uint32)
+    uw, mi = np.ascontiguousarray(unitig_w, np.uint32), np.ascontiguousarray(mirror, np.uint32)
+    tr = np.ascontiguousarray(triples, np.uint32).reshape(-1)
+    we, wl, dw = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    nw, ne, nd = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    ms = (C.c_double * 5)()
+    err = C.create_string_buffer(256)
+    rc = l.mtg_host_tail(k, len(mi), len(uw), _ptr(ef), _ptr(et), _ptr(uw), _ptr(mi), _ptr(tr), len(tr) // 3, C.byref(we),
+                         C.byref(wl), C.byref(dw), C.byref(nw), C.byref(ne), C.byref(nd), ms, err, len(err))
+    if rc != 0:
+        raise MatchtigsError(rc, err.value.decode())
+    try:
+        def take(p, n, dt):
+            if n == 0:
+                return np.zeros(0, dt)
+            return np.frombuffer((C.c_char * (n * np.dtype(dt).itemsize)).from_address(p.value), dtype=dt).copy()
+        edges, limits = take(we, ne.value, np.uint32), take(wl, nw.value, np.uint64)
+        dummy_w = take(dw, nd.value, np.uint32)
+    finally:
+        for p in (we, wl, dw):
+            l.mtg_host_free(p)
+    walks = np.split(edges, limits[:-1].astype(np.int64)) if nw.value else []
+    return walks, dummy_w, list(ms)
 
 
 class Graph:

@@ -223,14 +223,13 @@ int mtg_walks_export_capi(mtg_ctx* ctx, ptrdiff_t* tigs_edge_out, size_t* tigs_i
     return guarded(ctx, [&] {
         MTG_REQUIRE(ctx->have_walks, MTG_ERR_INVALID, "mtg_finish_walks has not run");
         MTG_REQUIRE(tigs_edge_out && tigs_insert_out && tigs_out_limits, MTG_ERR_INVALID, "null output array");
-        const HostGraph& g = ctx->hg;
         // src/clib.rs:393-407: +-unitig id (dummies carry the default handle 0), dummy weight or 0, end offsets
         for (size_t j = 0; j < ctx->walk_edges.size(); j++) {
             u32 e = ctx->walk_edges[j];
             bool fwd = !(e & 1);
-            if (g.dummy[e]) {
+            if (e >= ctx->E) {
                 tigs_edge_out[j] = 0;
-                tigs_insert_out[j] = g.weight[e];
+                tigs_insert_out[j] = ctx->h_dummy_w[e - ctx->E];
             } else {
                 tigs_edge_out[j] = (ptrdiff_t)(e >> 1) * (fwd ? 1 : -1);
                 tigs_insert_out[j] = 0;
@@ -268,6 +267,13 @@ int mtg_get_search_stats(mtg_ctx* ctx, mtg_search_stats* stats) {
     return guarded(ctx, [&] {
         MTG_REQUIRE(stats, MTG_ERR_INVALID, "null stats");
         *stats = ctx->stats;
+    });
+}
+
+int mtg_get_diagnostics(mtg_ctx* ctx, double tail_ms[5], uint32_t match_pending[48]) {
+    return guarded(ctx, [&] {
+        if (tail_ms) memcpy(tail_ms, ctx->tail_ms, sizeof(ctx->tail_ms));
+        if (match_pending) memcpy(match_pending, ctx->match_hist, sizeof(ctx->match_hist));
     });
 }
 

@@ -510,7 +510,7 @@ void finish_graph(mtg_ctx* ctx) {
 }  // namespace
 
 void build_graph_from_sequences(mtg_ctx* ctx, const char* seq, const u64* offsets, u64 U, u32 k, bool on_device) {
-    MTG_REQUIRE(k >= 2 && k <= 65, MTG_ERR_INVALID, "k must be in [2, 65]");
+    MTG_REQUIRE(k >= 2 && k <= 64, MTG_ERR_INVALID, "k must be in [2, 64]");
     MTG_REQUIRE(U < (1ull << 30), MTG_ERR_UNSUPPORTED, "more than 2^30 unitigs");
     MTG_REQUIRE(U == 0 || (seq && offsets), MTG_ERR_INVALID, "null sequence input");
     cudaStream_t s = ctx->stream;
@@ -584,7 +584,7 @@ void build_graph_from_sequences(mtg_ctx* ctx, const char* seq, const u64* offset
 
 void build_graph_from_links(mtg_ctx* ctx, u64 U, const u64* weights, u64 n_links, const u64* a, const u8* sa, const u64* b,
                             const u8* sb, u32 k, const char* seq, const u64* offsets) {
-    MTG_REQUIRE(k >= 2 && k <= 65, MTG_ERR_INVALID, "k must be in [2, 65]");
+    MTG_REQUIRE(k >= 2 && k <= 64, MTG_ERR_INVALID, "k must be in [2, 64]");
     MTG_REQUIRE(U < (1ull << 30), MTG_ERR_UNSUPPORTED, "more than 2^30 unitigs");
     MTG_REQUIRE(U == 0 || weights, MTG_ERR_INVALID, "null weights");
     MTG_REQUIRE(n_links == 0 || (a && sa && b && sb), MTG_ERR_INVALID, "null links");

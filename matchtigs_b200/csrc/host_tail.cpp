@@ -7,12 +7,17 @@
 //   F  minimum bidirected Eulerian cycle decomposition greedytigs/mod.rs:722 (bigraph)
 //   G  rotate to the heaviest dummy + break            greedytigs/mod.rs:726-789
 //
-// Same results as the reference, different machinery: flat arrays instead of petgraph +
-// BTreeMaps, two monotone cursors instead of ordered-map lookups in D, and in F a circular
-// doubly linked list (rotate == move the head) with a ring of not-yet-exhausted positions, which
-// makes the decomposition linear instead of quadratic in the cycle length.
+// Same results as the reference, different machinery, laid out for the cache instead of for
+// generality: D works on degree arrays with two monotone cursors instead of BTreeMaps and runs
+// before any adjacency exists; the adjacency is then built once as a CSR whose rows are ordered
+// newest edge first (petgraph's iteration order); F keeps the cycle as a circular
+// doubly linked list (rotate == move the head), a FIFO of not-yet-exhausted positions instead of
+// rescanning the cycle, per-node row cursors and a used-edge bitset, which makes it linear in the
+// number of edges with ~4 cache lines touched per edge.
 #include <algorithm>
+#include <chrono>
 #include <cstring>
+#include <memory>
 
 #include "mtg_internal.cuh"
 
@@ -20,40 +25,39 @@ namespace mtg {
 
 namespace {
 
-struct Tail {
-    HostGraph& g;
-    u32 k;
-    Tail(HostGraph& g_, u32 k_) : g(g_), k(k_) {}
+double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
-    u32 add_edge(u32 a, u32 b, u32 w, bool dummy) {
-        u32 e = (u32)g.from.size();
-        g.from.push_back(a);
-        g.to.push_back(b);
-        g.weight.push_back(w);
-        g.dummy.push_back(dummy ? 1 : 0);
-        g.next_out.push_back(g.head_out[a]);  // newest edge first (petgraph head insertion)
-        g.head_out[a] = e;
-        g.out_deg[a]++;
-        g.in_deg[b]++;
-        return e;
-    }
-    void add_dummy_pair(u32 out_node, u32 in_node, u32 w) {
-        add_edge(out_node, in_node, w, true);
-        add_edge(g.mirror[in_node], g.mirror[out_node], w, true);
-    }
+struct TailInput {
+    u32 k;
+    u64 n_nodes, n_orig;  // n_orig = 2U original edges
+    const u32 *from, *to, *unitig_w, *mirror;
+    const u32* triples;
+    u64 n_triples;
 };
 
-// D. Pairs the remaining imbalance with breaking edges of weight k.
-void eulerise(Tail& t) {
-    HostGraph& g = t.g;
-    const u32 n = g.n_nodes;
+struct TailOutput {
+    std::vector<u32> walk_edges;
+    std::vector<u64> walk_limits;
+    std::vector<u32> dummy_w;  // weight of dummy edge e at [(e - n_orig)]
+    u64 cycles = 0, breaking = 0;
+    double ms_degrees = 0, ms_eulerise = 0, ms_csr = 0, ms_walk = 0, ms_break = 0;
+};
+
+struct Pair {
+    u32 out_node, in_node, w;
+};
+
+// D. Pairs the remaining imbalance with breaking edges of weight k.  Needs degrees and mirrors only.
+void eulerise(const TailInput& in, const std::vector<u32>& out_deg, const std::vector<u32>& in_deg, std::vector<Pair>& pairs) {
+    const u32 n = (u32)in.n_nodes;
+    const u32* mirror = in.mirror;
     std::vector<i32> diff(n, 0);
     std::vector<u32> outs, ins, selfs;  // ascending node id
     for (u32 v = 0; v < n; v++) {
-        if (g.mirror[v] == v) {
-            if (g.out_deg[v] & 1) selfs.push_back(v);
+        if (mirror[v] == v) {
+            if (out_deg[v] & 1) selfs.push_back(v);
         } else {
-            i32 d = (i32)g.out_deg[v] - (i32)g.in_deg[v];
+            i32 d = (i32)out_deg[v] - (i32)in_deg[v];
             diff[v] = d;
             if (d < 0) outs.push_back(v);
             else if (d > 0) ins.push_back(v);
@@ -70,15 +74,15 @@ void eulerise(Tail& t) {
     // self-mirrors pairwise in ascending order; an odd one out takes the smallest in-node (:481-524)
     for (size_t i = 0; i < selfs.size(); i += 2) {
         if (i + 1 < selfs.size()) {
-            t.add_dummy_pair(selfs[i], selfs[i + 1], t.k);
+            pairs.push_back({selfs[i], selfs[i + 1], in.k});
         } else {
             skip_ins();
             MTG_REQUIRE(ip < ins.size(), MTG_ERR_INTERNAL,
                         "Have an uneven number of self-mirrors, but no other nodes with missing in edges.");
             u32 in_node = ins[ip];
-            t.add_dummy_pair(selfs[i], in_node, t.k);
+            pairs.push_back({selfs[i], in_node, in.k});
             diff[in_node] -= 1;
-            diff[g.mirror[in_node]] += 1;
+            diff[mirror[in_node]] += 1;
         }
     }
     // largest out-node with smallest in-node (:526-645)
@@ -90,14 +94,14 @@ void eulerise(Tail& t) {
         MTG_REQUIRE(ip < ins.size(), MTG_ERR_INTERNAL, "No further in_nodes left");
         u32 in_node = ins[ip];
         // choose_in_node_from_iterator (:252-285): do not join a node to its own mirror unless it misses >= 2 edges
-        if ((in_node == g.mirror[out_node] && diff[out_node] > -2) || in_node == out_node) {
+        if ((in_node == mirror[out_node] && diff[out_node] > -2) || in_node == out_node) {
             size_t q = ip + 1;
             while (q < ins.size() && diff[ins[q]] <= 0) q++;
             MTG_REQUIRE(q < ins.size(), MTG_ERR_INTERNAL, "No further in_nodes left");
             in_node = ins[q];
         }
-        const u32 mirror_out_node = g.mirror[in_node], mirror_in_node = g.mirror[out_node];
-        t.add_dummy_pair(out_node, in_node, t.k);
+        const u32 mirror_out_node = mirror[in_node], mirror_in_node = mirror[out_node];
+        pairs.push_back({out_node, in_node, in.k});
         diff[out_node] += 1;
         diff[in_node] -= 1;
         if (diff[mirror_out_node] < 0) diff[mirror_out_node] += 1;  // only while it is still listed (:609-627)
@@ -107,193 +111,330 @@ void eulerise(Tail& t) {
     MTG_REQUIRE(ip == ins.size(), MTG_ERR_INTERNAL, "eulerise: in-nodes left over");
 }
 
-// E. decomposes_into_eulerian_bicycles
-bool is_eulerian(const HostGraph& g) {
-    for (u32 v = 0; v < g.n_nodes; v++) {
-        if (g.mirror[v] == v) {
-            if (g.out_deg[v] & 1) return false;
-        } else if (g.out_deg[v] != g.in_deg[v]) {
-            return false;
+struct AdjEntry {
+    u32 edge, to;
+};
+// One 32-byte record per node: row cursor + up to three out-edges inline, so that stepping through a node
+// touches a single cache line.  Rows with more than three edges live in `ext` (cur/end index into it).
+constexpr u32 ROW_INLINE = 3;
+constexpr u32 ROW_EXT = 0x80000000u;
+struct alignas(32) NodeRow {
+    u32 cur, end;  // next position to inspect / end of the row (ROW_EXT flag: positions refer to `ext`)
+    AdjEntry inl[ROW_INLINE];
+};
+
+void run_tail(const TailInput& in, TailOutput& out) {
+    const u32 n = (u32)in.n_nodes;
+    const u64 E0 = in.n_orig;
+    double t0 = now_ms();
+    // ---- degrees after the matching dummies (C) ----
+    std::vector<u32> out_deg(n, 0), in_deg(n, 0);
+    for (u64 e = 0; e < E0; e++) {
+        out_deg[in.from[e]]++;
+        in_deg[in.to[e]]++;
+    }
+    std::vector<Pair> pairs;
+    pairs.reserve(in.n_triples + 1024);
+    for (u64 j = 0; j < in.n_triples; j++) {
+        const u32 o = in.triples[3 * j], i = in.triples[3 * j + 1];
+        pairs.push_back({o, i, in.triples[3 * j + 2]});
+        out_deg[o]++;
+        in_deg[i]++;
+        out_deg[in.mirror[i]]++;
+        in_deg[in.mirror[o]]++;
+    }
+    double t1 = now_ms();
+    // ---- D ----
+    eulerise(in, out_deg, in_deg, pairs);
+    for (size_t j = in.n_triples; j < pairs.size(); j++) {
+        out_deg[pairs[j].out_node]++;
+        in_deg[pairs[j].in_node]++;
+        out_deg[in.mirror[pairs[j].in_node]]++;
+        in_deg[in.mirror[pairs[j].out_node]]++;
+    }
+    // ---- E ----
+    for (u32 v = 0; v < n; v++) {
+        const bool ok = in.mirror[v] == v ? !(out_deg[v] & 1) : out_deg[v] == in_deg[v];
+        MTG_REQUIRE(ok, MTG_ERR_INTERNAL, "Failed to make the graph Eulerian.");
+    }
+    double t2 = now_ms();
+    // ---- CSR, rows newest edge first.  Dummy pair j = edges E0+2j (out->in) and E0+2j+1 (mirror(in)->mirror(out)) ----
+    const u64 E = E0 + 2 * pairs.size();
+    MTG_REQUIRE(E < 0xFFFFFFF0ull, MTG_ERR_UNSUPPORTED, "more than 2^32 edges");
+    out.dummy_w.resize(2 * pairs.size());
+    std::vector<NodeRow> rows(n);
+    u64 n_ext = 0;
+    for (u32 v = 0; v < n; v++) {
+        if (out_deg[v] <= ROW_INLINE) {
+            rows[v].cur = 0;  // used as fill cursor first
+            rows[v].end = out_deg[v];
+        } else {
+            rows[v].cur = (u32)n_ext;
+            n_ext += out_deg[v];
+            rows[v].end = (u32)n_ext | ROW_EXT;
         }
     }
-    return true;
-}
-
-// F + G fused: every finished cycle is rotated and cut into walks right away.
-struct WalkSink {
-    const HostGraph& g;
-    u32 k;
-    std::vector<u32>& edges;
-    std::vector<u64>& limits;
-    u64 breaking = 0;
-    void emit(const u32* b, const u32* e) {
-        edges.insert(edges.end(), b, e);
-        limits.push_back(edges.size());
+    MTG_REQUIRE(n_ext < ROW_EXT, MTG_ERR_UNSUPPORTED, "too many edges at high-degree nodes");
+    std::unique_ptr<AdjEntry[]> ext(new AdjEntry[n_ext ? n_ext : 1]);
+    auto place = [&](u32 v, AdjEntry a) {
+        NodeRow& r = rows[v];
+        if (r.end & ROW_EXT) ext[r.cur++] = a;
+        else r.inl[r.cur++] = a;
+    };
+    for (size_t j = pairs.size(); j-- > 0;) {  // descending edge id => newest first inside every row
+        const Pair& p = pairs[j];
+        const u32 e = (u32)(E0 + 2 * j);
+        place(in.mirror[p.in_node], {e + 1, in.mirror[p.out_node]});
+        place(p.out_node, {e, p.in_node});
+        out.dummy_w[2 * j] = out.dummy_w[2 * j + 1] = p.w;
     }
-    // greedytigs/mod.rs:736-788
-    void cycle(std::vector<u32>& cyc) {
+    for (u64 e = E0; e-- > 0;) place(in.from[e], {(u32)e, in.to[e]});
+    for (u32 v = 0; v < n; v++) rows[v].cur = (rows[v].end & ROW_EXT) ? (rows[v].end & ~ROW_EXT) - out_deg[v] : 0;
+    double t3 = now_ms();
+    // ---- F + G ----
+    std::vector<u64> used((E + 63) / 64 + 1, 0);
+    auto is_used = [&](u32 e) { return (used[e >> 6] >> (e & 63)) & 1ull; };
+    auto mark_pair = [&](u32 e) { used[e >> 6] |= 3ull << (e & 62); };  // e and e^1 share a word
+    // The cycle under construction.  Every extension appends a contiguous run of elements to `queue`
+    // (creation order == the order in which positions are scanned for leftover out-edges).  A run created
+    // while position i was the head sits, in cycle order, immediately before element i ("push_back on the
+    // rotated vector"); all runs created at i are consecutive in `queue`, so element i only needs the
+    // range [child_begin, child_end) of its block.  Cycle order == in-order expansion of this tree.
+    struct QEntry {
+        u32 edge, from;
+        u32 child_begin, child_end;
+    };
+    std::vector<QEntry> queue;
+    queue.reserve(E / 2 + 16);
+    auto first_unused = [&](u32 v) -> const AdjEntry* {
+        NodeRow& r = rows[v];
+        if (!(r.end & ROW_EXT)) {
+            while (r.cur < r.end && is_used(r.inl[r.cur].edge)) r.cur++;
+            return r.cur < r.end ? &r.inl[r.cur] : nullptr;
+        }
+        const u32 end = r.end & ~ROW_EXT;
+        while (r.cur < end && is_used(ext[r.cur].edge)) r.cur++;
+        return r.cur < end ? &ext[r.cur] : nullptr;
+    };
+    std::vector<u32> cyc;
+    std::vector<std::pair<u32, u32>> stack;  // (next index, block end)
+    out.walk_edges.clear();
+    out.walk_limits.clear();
+    out.walk_edges.reserve(E / 2);
+    double ms_break = 0;
+    auto emit = [&](const u32* b, const u32* e) {
+        MTG_REQUIRE(*b < E0, MTG_ERR_INTERNAL, "walk starts with a dummy edge");
+        out.walk_edges.insert(out.walk_edges.end(), b, e);
+        out.walk_limits.push_back(out.walk_edges.size());
+    };
+    auto is_dummy = [&](u32 e) { return e >= E0; };
+    auto dummy_weight = [&](u32 e) { return out.dummy_w[e - E0]; };
+    for (u64 e0 = 0; e0 < E; e0++) {
+        if (is_used((u32)e0)) continue;
+        // one closed walk per component, started at the lowest unused edge id
+        size_t qf = 0;
+        queue.clear();
+        u32 start_edge = (u32)e0, start_from, start_to;
+        if (e0 < E0) {
+            start_from = in.from[e0];
+            start_to = in.to[e0];
+        } else {
+            const Pair& p = pairs[(e0 - E0) >> 1];
+            const bool fwd = !((e0 - E0) & 1);
+            start_from = fwd ? p.out_node : in.mirror[p.in_node];
+            start_to = fwd ? p.in_node : in.mirror[p.out_node];
+        }
+        size_t head_idx = 0;  // queue index of the element the (rotated) cycle vector currently starts with
+        size_t n0 = 0;        // length of the initial closed walk == the root block [0, n0)
+        bool rooted = false;
+        for (;;) {
+            mark_pair(start_edge);
+            queue.push_back({start_edge, start_from, 0, 0});
+            u32 cur_node = start_to;
+            for (const AdjEntry* a; (a = first_unused(cur_node)) != nullptr;) {
+                __builtin_prefetch(&rows[a->to]);
+                mark_pair(a->edge);
+                queue.push_back({a->edge, cur_node, 0, 0});
+                cur_node = a->to;
+            }
+            if (rooted) queue[head_idx].child_end = (u32)queue.size();  // the run just appended belongs to the head's block
+            else n0 = queue.size();
+            // re-root at the first cycle position (from the head) whose from-node still has an unused out-edge
+            bool found = false;
+            while (qf < queue.size()) {
+                if (qf + 12 < queue.size()) __builtin_prefetch(&rows[queue[qf + 12].from]);  // independent misses: overlap them
+                const AdjEntry* a = first_unused(queue[qf].from);
+                if (a) {
+                    head_idx = qf;  // rotate_left(position)
+                    rooted = true;
+                    if (!queue[qf].child_end) queue[qf].child_begin = (u32)queue.size();  // first run spliced before qf
+                    start_edge = a->edge;
+                    start_from = queue[qf].from;
+                    start_to = a->to;
+                    found = true;
+                    break;
+                }
+                qf++;  // exhausted for good
+            }
+            if (!found) break;
+        }
+        double tb = now_ms();
+        const size_t len = queue.size();
+        // in-order expansion; the root block is the initial closed walk [0, n0)
+        cyc.clear();
+        cyc.reserve(len);
+        stack.clear();
+        stack.push_back({0u, (u32)n0});
+        size_t head_pos = 0;
+        while (!stack.empty()) {
+            auto& fr = stack.back();
+            if (fr.first == fr.second) {
+                stack.pop_back();
+                if (!stack.empty()) {  // the block of element (first) is done: emit the element itself
+                    auto& up = stack.back();
+                    const u32 i = up.first++;
+                    if (i == head_idx) head_pos = cyc.size();
+                    cyc.push_back(queue[i].edge);
+                }
+                continue;
+            }
+            const u32 i = fr.first;
+            const QEntry& q = queue[i];
+            if (q.child_end > q.child_begin) {
+                stack.push_back({q.child_begin, q.child_end});
+            } else {
+                fr.first++;
+                if (i == head_idx) head_pos = cyc.size();
+                cyc.push_back(q.edge);
+            }
+        }
+        MTG_REQUIRE(cyc.size() == len, MTG_ERR_INTERNAL, "cycle expansion lost elements");
+        // G. greedytigs/mod.rs:736-788
+        // the reference's cycle vector is `cyc` rotated left by head_pos; the heaviest-dummy rotation is applied on top
         u32 longest_w = 0;
         size_t longest_i = 0;
-        for (size_t i = 0; i < cyc.size(); i++) {
-            u32 e = cyc[i];
-            if (g.dummy[e] && g.weight[e] > longest_w) {  // strict: first heaviest wins
-                longest_w = g.weight[e];
+        for (size_t i = 0; i < len; i++) {
+            size_t j = head_pos + i;
+            if (j >= len) j -= len;
+            const u32 x = cyc[j];
+            if (is_dummy(x) && dummy_weight(x) > longest_w) {  // strict: the first heaviest dummy wins
+                longest_w = dummy_weight(x);
                 longest_i = i;
             }
         }
-        if (longest_w > 0) std::rotate(cyc.begin(), cyc.begin() + longest_i, cyc.end());
+        size_t rot = head_pos + (longest_w > 0 ? longest_i : 0);
+        if (rot >= len) rot -= len;
+        if (rot) std::rotate(cyc.begin(), cyc.begin() + rot, cyc.end());
         size_t offset = 0;
         const u32* p = cyc.data();
-        for (size_t i = 0; i < cyc.size(); i++) {
-            u32 e = cyc[i];
-            if (g.dummy[e] && (g.weight[e] >= k || i == 0)) {
+        for (size_t i = 0; i < len; i++) {
+            const u32 x = cyc[i];
+            if (is_dummy(x) && (dummy_weight(x) >= in.k || i == 0)) {
                 if (offset < i) emit(p + offset, p + i);
                 offset = i + 1;
-                breaking++;
+                out.breaking++;
             }
         }
-        if (offset < cyc.size()) {
-            if (!g.dummy[cyc.back()]) emit(p + offset, p + cyc.size());
-            else if (offset < cyc.size() - 1) emit(p + offset, p + cyc.size() - 1);
+        if (offset < len) {
+            if (!is_dummy(cyc[len - 1])) emit(p + offset, p + len);
+            else if (offset < len - 1) emit(p + offset, p + len - 1);
         }
+        out.cycles++;
+        ms_break += now_ms() - tb;
     }
-};
-
-void euler_walks(const HostGraph& g, WalkSink& sink, u64* n_cycles) {
-    const u32 E = (u32)g.from.size();
-    std::vector<u8> used(E, 0);
-    std::vector<u32> cursor(g.head_out);
-    std::vector<u32> nxt(E), prv(E), cnxt(E), cprv(E);
-    std::vector<u32> cyc;
-    auto first_unused = [&](u32 v) -> u32 {
-        u32 e = cursor[v];
-        while (e != NONE32 && used[e]) e = g.next_out[e];
-        cursor[v] = e;
-        return e;
-    };
-    u64 cycles = 0;
-    for (u32 e0 = 0; e0 < E; e0++) {
-        if (used[e0]) continue;
-        u32 head = NONE32, chead = NONE32;
-        size_t len = 0;
-        // appending to the cycle vector == inserting before `head` in the ring; `chead` is the first
-        // position at or after head whose from-node may still own an unused out-edge.
-        auto append = [&](u32 e) {
-            if (head == NONE32) {
-                head = e;
-                nxt[e] = prv[e] = e;
-            } else {
-                u32 tail = prv[head];
-                nxt[tail] = e;
-                prv[e] = tail;
-                nxt[e] = head;
-                prv[head] = e;
-            }
-            if (chead == NONE32) {
-                chead = e;
-                cnxt[e] = cprv[e] = e;
-            } else {
-                u32 ct = cprv[chead];
-                cnxt[ct] = e;
-                cprv[e] = ct;
-                cnxt[e] = chead;
-                cprv[chead] = e;
-            }
-            len++;
-        };
-        u32 start_edge = e0;
-        while (start_edge != NONE32) {
-            used[start_edge] = used[start_edge ^ 1u] = 1;
-            append(start_edge);
-            u32 cur = g.to[start_edge];
-            for (u32 e; (e = first_unused(cur)) != NONE32;) {
-                used[e] = used[e ^ 1u] = 1;
-                append(e);
-                cur = g.to[e];
-            }
-            start_edge = NONE32;
-            while (chead != NONE32) {
-                u32 found = first_unused(g.from[chead]);
-                if (found != NONE32) {
-                    start_edge = found;
-                    head = chead;  // rotate_left(position of chead)
-                    break;
-                }
-                if (cnxt[chead] == chead) {
-                    chead = NONE32;
-                } else {  // exhausted for good
-                    u32 a = cprv[chead], b = cnxt[chead];
-                    cnxt[a] = b;
-                    cprv[b] = a;
-                    chead = b;
-                }
-            }
-        }
-        cyc.resize(len);
-        u32 e = head;
-        for (size_t i = 0; i < len; i++) {
-            cyc[i] = e;
-            e = nxt[e];
-        }
-        sink.cycle(cyc);
-        cycles++;
-    }
-    *n_cycles = cycles;
+    double t4 = now_ms();
+    out.ms_degrees = t1 - t0;
+    out.ms_eulerise = t2 - t1;
+    out.ms_csr = t3 - t2;
+    out.ms_break = ms_break;
+    out.ms_walk = t4 - t3 - ms_break;
 }
 
 }  // namespace
+
+}  // namespace mtg
+
+namespace mtg {
 
 void finish_walks(mtg_ctx* ctx) {
     MTG_REQUIRE(ctx->have_graph && ctx->have_triples, MTG_ERR_INVALID, "mtg_greedy_match has not run");
     cudaStream_t s = ctx->stream;
     const u64 U = ctx->U, N = ctx->N, E = ctx->E;
-    HostGraph& g = ctx->hg;
-    g = HostGraph();
-    g.n_nodes = (u32)N;
-    g.n_orig_edges = (u32)E;
-    std::vector<u32> from(E), to(E), uw(U);
-    g.mirror.resize(N);
+    std::vector<u32> from(E), to(E), uw(U), mirror(N);
     if (E) {
         MTG_CUDA(cudaMemcpyAsync(from.data(), ctx->edge_from.p, E * sizeof(u32), cudaMemcpyDeviceToHost, s));
         MTG_CUDA(cudaMemcpyAsync(to.data(), ctx->edge_to.p, E * sizeof(u32), cudaMemcpyDeviceToHost, s));
         MTG_CUDA(cudaMemcpyAsync(uw.data(), ctx->unitig_w.p, U * sizeof(u32), cudaMemcpyDeviceToHost, s));
     }
-    if (N) MTG_CUDA(cudaMemcpyAsync(g.mirror.data(), ctx->mirror.p, N * sizeof(u32), cudaMemcpyDeviceToHost, s));
+    if (N) MTG_CUDA(cudaMemcpyAsync(mirror.data(), ctx->mirror.p, N * sizeof(u32), cudaMemcpyDeviceToHost, s));
     MTG_CUDA(cudaStreamSynchronize(s));
-    const u64 n_trip = ctx->n_triples;
-    const size_t reserve = E + 2 * n_trip + 64;
-    g.from.reserve(reserve);
-    g.to.reserve(reserve);
-    g.weight.reserve(reserve);
-    g.dummy.reserve(reserve);
-    g.next_out.reserve(reserve);
-    g.head_out.assign(N, NONE32);
-    g.out_deg.assign(N, 0);
-    g.in_deg.assign(N, 0);
-    Tail t(g, ctx->k);
-    for (u64 e = 0; e < E; e++) t.add_edge(from[e], to[e], uw[e >> 1], false);
-    // C. dummy edges in result order (greedytigs/mod.rs:678-689)
-    const u32* tr = ctx->h_triples.data();
-    for (u64 j = 0; j < n_trip; j++) t.add_dummy_pair(tr[3 * j], tr[3 * j + 1], tr[3 * j + 2]);
-    eulerise(t);
-    MTG_REQUIRE(is_eulerian(g), MTG_ERR_INTERNAL, "Failed to make the graph Eulerian.");
-    ctx->walk_edges.clear();
-    ctx->walk_limits.clear();
-    ctx->walk_edges.reserve(g.from.size() / 2);
-    WalkSink sink{g, ctx->k, ctx->walk_edges, ctx->walk_limits};
-    u64 n_cycles = 0;
-    euler_walks(g, sink, &n_cycles);
-    for (size_t w = 0; w < ctx->walk_limits.size(); w++) {
-        u64 b = w ? ctx->walk_limits[w - 1] : 0;
-        MTG_REQUIRE(!g.dummy[ctx->walk_edges[b]], MTG_ERR_INTERNAL, "walk starts with a dummy edge");
-    }
+    TailInput in{ctx->k, N, E, from.data(), to.data(), uw.data(), mirror.data(), ctx->h_triples.data(), ctx->n_triples};
+    TailOutput out;
+    run_tail(in, out);
+    ctx->walk_edges.swap(out.walk_edges);
+    ctx->walk_limits.swap(out.walk_limits);
+    ctx->h_dummy_w.swap(out.dummy_w);
+    ctx->tail_ms[0] = out.ms_degrees;
+    ctx->tail_ms[1] = out.ms_eulerise;
+    ctx->tail_ms[2] = out.ms_csr;
+    ctx->tail_ms[3] = out.ms_walk;
+    ctx->tail_ms[4] = out.ms_break;
     // device copies for the output kernels
     ctx->d_walk_edges.upload(ctx->walk_edges.data(), ctx->walk_edges.size(), s);
     ctx->d_walk_limits.upload(ctx->walk_limits.data(), ctx->walk_limits.size(), s);
-    std::vector<u32> dummy_w(g.weight.begin() + E, g.weight.end());
-    ctx->d_dummy_w.upload(dummy_w.data(), dummy_w.size(), s);
+    ctx->d_dummy_w.upload(ctx->h_dummy_w.data(), ctx->h_dummy_w.size(), s);
     MTG_CUDA(cudaStreamSynchronize(s));
     ctx->have_walks = true;
 }
 
 }  // namespace mtg
+
+// Host-only entry: the sequential tail on caller-supplied arrays (no GPU involved).  Lets the host
+// logic be tested and timed on its own.
+extern "C" int mtg_host_tail(uint32_t k, uint64_t nodes, uint64_t unitigs, const uint32_t* edge_from, const uint32_t* edge_to,
+                             const uint32_t* unitig_w, const uint32_t* mirror, const uint32_t* triples, uint64_t n_triples,
+                             uint32_t** walk_edges, uint64_t** walk_limits, uint32_t** dummy_w, uint64_t* n_walks,
+                             uint64_t* n_walk_edges, uint64_t* n_dummy_edges, double* phase_ms /* [5] or NULL */, char* errbuf,
+                             size_t errcap) {
+    using namespace mtg;
+    auto fail = [&](int code, const std::string& m) {
+        if (errbuf && errcap) {
+            size_t n = std::min(errcap - 1, m.size());
+            memcpy(errbuf, m.data(), n);
+            errbuf[n] = 0;
+        }
+        return code;
+    };
+    if (!walk_edges || !walk_limits || !dummy_w || !n_walks || !n_walk_edges || !n_dummy_edges) return fail(MTG_ERR_INVALID, "null output");
+    try {
+        TailInput in{k, nodes, 2 * unitigs, edge_from, edge_to, unitig_w, mirror, triples, n_triples};
+        TailOutput out;
+        run_tail(in, out);
+        auto dup = [](const auto& v) {
+            using T = typename std::decay<decltype(v)>::type::value_type;
+            T* p = (T*)malloc(std::max<size_t>(v.size(), 1) * sizeof(T));
+            if (!v.empty()) memcpy(p, v.data(), v.size() * sizeof(T));
+            return p;
+        };
+        *walk_edges = dup(out.walk_edges);
+        *walk_limits = dup(out.walk_limits);
+        *dummy_w = dup(out.dummy_w);
+        *n_walks = out.walk_limits.size();
+        *n_walk_edges = out.walk_edges.size();
+        *n_dummy_edges = out.dummy_w.size();
+        if (phase_ms) {
+            phase_ms[0] = out.ms_degrees;
+            phase_ms[1] = out.ms_eulerise;
+            phase_ms[2] = out.ms_csr;
+            phase_ms[3] = out.ms_walk;
+            phase_ms[4] = out.ms_break;
+        }
+        return MTG_OK;
+    } catch (const Error& e) {
+        return fail(e.code, e.msg);
+    } catch (const std::exception& e) {
+        return fail(MTG_ERR_INTERNAL, e.what());
+    }
+}
+
+extern "C" void mtg_host_free(void* p) { free(p); }

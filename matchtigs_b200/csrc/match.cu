@@ -38,6 +38,7 @@ constexpr int TB = 256;
 constexpr u32 META_TRUNC = 0x80000000u;
 constexpr u32 META_COUNT = 0x00FFFFFFu;
 constexpr u32 NO_INDEX = 0xFFFFFFFFu;
+constexpr u32 MATCH_HIST = 48;
 
 struct MatchArgs {
     const u32* sources;
@@ -53,6 +54,8 @@ struct MatchArgs {
     u32* trip_slots;       // [3 * total]
     u32* min_insufficient; // [1]
     u32* rounds;           // [1]
+    u32* hist;             // [MATCH_HIST] pending sources at the start of each of the first rounds (diagnostic)
+    u32* error;            // [1] invariant violations
     u32 round_base;
 };
 
@@ -62,135 +65,148 @@ __device__ __forceinline__ i32 ldm(const i32* mult, u32 x) { return __ldcg(&mult
 __device__ __forceinline__ void addm(i32* mult, u32 x, i32 d) { __stcg(&mult[x], __ldcg(&mult[x]) + d); }
 __device__ __forceinline__ unsigned long long ldr(const unsigned long long* res, u32 x) { return __ldcg(&res[x]); }
 
-// Applies the reference's matching rules to source i.  Returns false if the capped list ran dry.
-__device__ bool process_source(const MatchArgs& a, u32 i) {
+// Reservations are asymmetric.  A pending source RESERVES mirror(src) and every still-open entry of its
+// whole list (anything it might ever take: closed entries never reopen, so they need no protection), but to
+// COMMIT it only has to HOLD what it reads and writes in the current state: mirror(src) and the first m+1
+// open entries.  Only in-type nodes are reserved: every access a commit makes to an out-type node v
+// (v = src, or v = mirror(x) of an accepted entry x) is shared only with sources that have mirror(v) in
+// their own set.  Holding x means no lower-indexed pending source lists x, so its value is final for this
+// source; a higher-indexed source can never hold x while this one is pending.  Unheld entries may be read
+// racily: they can only flip open -> closed, by a lower-indexed source, which is what the sequential order
+// would have shown; an unheld entry read as open blocks the commit.
+__device__ __forceinline__ void reserve_source(const MatchArgs& a, u32 i, unsigned long long word) {
+    reserve(a.res, a.mirror[a.sources[i]], word);
+    const u64* list = reinterpret_cast<const u64*>(a.list_addr[i]);
+    const u32 count = a.list_meta[i] & META_COUNT;
+    for (u32 p = 0; p < count; p++) {
+        const u32 x = (u32)list[p];
+        if (ldm(a.mult, x) > 0) reserve(a.res, x, word);
+    }
+}
+
+enum TryResult { TRY_BLOCKED = 0, TRY_DONE = 1, TRY_INSUFFICIENT = 2 };
+
+// Applies the reference's matching rules (greedytigs/mod.rs:301-523) to source i if it holds its reservations.
+__device__ TryResult try_source(const MatchArgs& a, u32 i, unsigned long long word) {
     const u32 out_node = a.sources[i];
     const u32 M = a.mirror[out_node];
+    if (ldr(a.res, M) != word) return TRY_BLOCKED;
     const bool out_self = M == out_node;
-    i32 m = ldm(a.mult, M);  // greedytigs/mod.rs:306-311
-    u32 emitted = 0;
-    if (m == 0) {       // :318-320
+    i32 m = ldm(a.mult, M);  // :306-311
+    if (m == 0) {            // :318-320
         a.trip_cnt[i] = 0;
-        return true;
+        return TRY_DONE;
     }
     const u64* list = reinterpret_cast<const u64*>(a.list_addr[i]);
     const u32 meta = a.list_meta[i];
     const u32 count = meta & META_COUNT;
     const bool truncated = (meta & META_TRUNC) != 0;
+    // The Dijkstra call (:324-335) == the first m+1 entries of the list that are open now.
+    const u32 target_amount = (u32)m + 1;
+    u32 found = 0, last_pos = 0;
+    for (u32 p = 0; p < count && found < target_amount; p++) {
+        const u32 x = (u32)list[p];
+        if (x != M) {
+            if (ldm(a.mult, x) <= 0) continue;
+            if (ldr(a.res, x) != word) return TRY_BLOCKED;
+        }
+        found++;
+        last_pos = p;
+    }
+    if (found == 0) {  // distances.is_empty() :338-346
+        a.trip_cnt[i] = 0;
+        return truncated ? TRY_INSUFFICIENT : TRY_DONE;
+    }
+    const bool abort_after_this = found < target_amount;  // :348
     u32* slots = a.trip_slots + 3ull * a.trip_off[i];
-    bool ok = true;
-    while (m > 0) {  // :322
-        const u32 target_amount = (u32)m + 1;
-        // Dijkstra call == the first target_amount open entries of the list (snapshot at call time).
-        // Snapshot via a bitmask over list positions would need `count` bits; instead walk the list twice:
-        // entries are re-checked against a per-call "was open at call time" rule below.
-        u32 found = 0, last_pos = 0;
-        for (u32 p = 0; p < count && found < target_amount; p++) {
-            u32 x = (u32)list[p];
-            if (ldm(a.mult, x) > 0) {
-                found++;
-                last_pos = p;
-            }
+    u32 emitted = 0;
+    for (u32 p = 0; p <= last_pos; p++) {  // :350
+        const u64 rec = list[p];
+        const u32 in_node = (u32)rec;
+        // entries of `distances` = open at call time; M was open (m > 0), every other node is touched only by its own iteration
+        if (in_node != M && ldm(a.mult, in_node) <= 0) continue;
+        bool sme = false;
+        if (in_node == M) {  // :352-358
+            if (m < 2) continue;
+            sme = true;
         }
-        const bool exhausted_known = found < target_amount;
-        if (found == 0) {  // distances.is_empty() :338-346
-            if (truncated) ok = false;
-            break;
+        m = out_self ? ldm(a.mult, out_node) : -ldm(a.mult, out_node);  // :401-410
+        if (m == 0) break;                                               // :412-414
+        const u32 in_mirror = a.mirror[in_node];
+        const i32 r = sme ? 2 : 1;
+        slots[3 * emitted + 0] = out_node;  // :461
+        slots[3 * emitted + 1] = in_node;
+        slots[3 * emitted + 2] = (u32)(rec >> 32);
+        emitted++;
+        if (out_self) {  // :463-473
+            addm(a.mult, out_node, -1);
+        } else {
+            addm(a.mult, out_node, r);
+            addm(a.mult, M, -r);
         }
-        const bool abort_after_this = exhausted_known;  // :348 (only meaningful if the list is complete)
-        // Entries that were open at call time and lie at positions <= last_pos form `distances`.  An entry's
-        // openness can change while the list is processed only for M (rule 1 handles it through m) --
-        // every other node appears once and is touched only by its own iteration -- so re-evaluating
-        // "open at call time" lazily is exact as long as M is special-cased.
-        const bool m_open_at_call = ldm(a.mult, M) > 0;
-        for (u32 p = 0; p <= last_pos; p++) {  // :350
-            const u64 rec = list[p];
-            const u32 in_node = (u32)rec;
-            const bool was_open = (in_node == M) ? m_open_at_call : (ldm(a.mult, in_node) > 0);
-            if (!was_open) continue;
-            bool sme = false;
-            if (in_node == M) {  // :352-358
-                if (m < 2) continue;
-                sme = true;
-            }
-            m = out_self ? ldm(a.mult, out_node) : -ldm(a.mult, out_node);  // :401-410
-            if (m == 0) break;                                     // :412-414
-            const u32 in_mirror = a.mirror[in_node];
-            const i32 r = sme ? 2 : 1;
-            slots[3 * emitted + 0] = out_node;  // :461
-            slots[3 * emitted + 1] = in_node;
-            slots[3 * emitted + 2] = (u32)(rec >> 32);
-            emitted++;
-            if (out_self) {  // :463-473
-                addm(a.mult, out_node, -1);
-            } else {
-                addm(a.mult, out_node, r);
-                addm(a.mult, M, -r);
-            }
-            m = -ldm(a.mult, out_node);  // :474
-            if (!sme) {                  // :476-491
-                addm(a.mult, in_node, -1);
-                if (in_mirror != in_node) addm(a.mult, in_mirror, 1);
-            }
-        }
-        if (abort_after_this) {  // :504-511
-            if (truncated && m > 0) ok = false;  // the real call would have returned more entries
-            break;
+        m = -ldm(a.mult, out_node);  // :474
+        if (!sme) {                  // :476-491
+            addm(a.mult, in_node, -1);
+            if (in_mirror != in_node) addm(a.mult, in_mirror, 1);
         }
     }
     a.trip_cnt[i] = emitted;
-    return ok;
+    if (m > 0) {
+        // With m+1 candidates at most one (mirror(src)) is skipped, so m reaches 0 unless the list ran out (:504-511).
+        if (!abort_after_this) atomicExch(a.error, 1u);  // would be a second Dijkstra call: impossible at --threads 1
+        if (truncated) return TRY_INSUFFICIENT;           // the real call would have returned more entries
+    }
+    return TRY_DONE;
 }
+
+constexpr u32 LOCAL_MODE_MAX = 2048;  // at most this many pending sources: finish inside one CTA (no grid barriers)
 
 __global__ void __launch_bounds__(TB) match_rounds_kernel(MatchArgs a) {
     cg::grid_group grid = cg::this_grid();
-    const u64 gtid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    const u64 gsize = (u64)gridDim.x * blockDim.x;
+    u64 tid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 nthreads = (u64)gridDim.x * blockDim.x;
+    bool local = false;
     u32 round = 0;
     for (;; round++) {
         const u32 cur = round % 3, nxt = (round + 1) % 3, spare = (round + 2) % 3;
         const u32 n = ((volatile u32*)a.counts)[cur];
         if (n == 0) break;
+        if (!local && n <= LOCAL_MODE_MAX) {  // uniform decision: every CTA reads the same n after the barrier
+            if (blockIdx.x != 0) return;
+            local = true;
+            tid = threadIdx.x;
+            nthreads = blockDim.x;
+        }
+        if (tid == 0 && round < MATCH_HIST) a.hist[round] = n;
         const unsigned long long tag = (unsigned long long)(0xFFFFFFFFu - (a.round_base + round)) << 32;
         const u32* pend = a.pend[cur];
-        for (u64 idx = gtid; idx < n; idx += gsize) {
+        for (u64 idx = tid; idx < n; idx += nthreads) {
             const u32 i = __ldcg(&pend[idx]);
             if (i > ((volatile u32*)a.min_insufficient)[0]) continue;
-            const unsigned long long word = tag | i;
-            const u32 out_node = a.sources[i];
-            reserve(a.res, out_node, word);
-            reserve(a.res, a.mirror[out_node], word);
-            const u64* list = reinterpret_cast<const u64*>(a.list_addr[i]);
-            const u32 count = a.list_meta[i] & META_COUNT;
-            for (u32 p = 0; p < count; p++) {
-                u32 x = (u32)list[p];
-                reserve(a.res, x, word);
-                reserve(a.res, a.mirror[x], word);
-            }
+            reserve_source(a, i, tag | i);
         }
-        if (gtid == 0) a.counts[spare] = 0;
-        grid.sync();
-        for (u64 idx = gtid; idx < n; idx += gsize) {
+        if (tid == 0) a.counts[spare] = 0;
+        if (local) {
+            __threadfence();
+            __syncthreads();
+        } else {
+            grid.sync();
+        }
+        for (u64 idx = tid; idx < n; idx += nthreads) {
             const u32 i = __ldcg(&pend[idx]);
             if (i > ((volatile u32*)a.min_insufficient)[0]) continue;  // will be discarded anyway
-            const unsigned long long word = tag | i;
-            const u32 out_node = a.sources[i];
-            bool mine = ldr(a.res, out_node) == word && ldr(a.res, a.mirror[out_node]) == word;
-            const u64* list = reinterpret_cast<const u64*>(a.list_addr[i]);
-            const u32 count = a.list_meta[i] & META_COUNT;
-            for (u32 p = 0; mine && p < count; p++) {
-                u32 x = (u32)list[p];
-                mine = ldr(a.res, x) == word && ldr(a.res, a.mirror[x]) == word;
-            }
-            if (mine) {
-                if (!process_source(a, i)) atomicMin(a.min_insufficient, i);
-            } else {
-                a.pend[nxt][atomicAdd(&a.counts[nxt], 1u)] = i;
-            }
+            const TryResult r = try_source(a, i, tag | i);
+            if (r == TRY_BLOCKED) a.pend[nxt][atomicAdd(&a.counts[nxt], 1u)] = i;
+            else if (r == TRY_INSUFFICIENT) atomicMin(a.min_insufficient, i);
         }
-        grid.sync();
+        if (local) {
+            __threadfence();
+            __syncthreads();
+        } else {
+            grid.sync();
+        }
     }
-    if (gtid == 0) *a.rounds = round;
+    if (tid == 0) *a.rounds = round;
 }
 
 __global__ void __launch_bounds__(TB)
@@ -314,7 +330,8 @@ void greedy_match(mtg_ctx* ctx, const u64* d_records_all, const u32* d_meta_all,
     pend0.resize(S, s);
     pend1.resize(S, s);
     pend2.resize(S, s);
-    small.resize(16, s);  // [0..2] counts, [3] min_insufficient, [4] rounds, [5] scan total, [6] scan total 2
+    small.resize(16 + MATCH_HIST, s);  // [0..2] counts, [3] min_insufficient, [4] rounds, [5] scan total, [6] scan total 2, [16..] hist
+    small.zero(s);
     MTG_LAUNCH(ctx, init_lists, grid_for(S, TB), TB, 0, ctx->sources.p, ctx->mirror.p, ctx->imbalance.p, d_records_all, d_meta_all, S,
                shard_count, padded, cap, list_addr.p, list_meta.p, max_trip.p);
     exclusive_sum_u32(ctx, max_trip.p, trip_off.p, S, small.p + 5);
@@ -327,7 +344,7 @@ void greedy_match(mtg_ctx* ctx, const u64* d_records_all, const u32* d_meta_all,
     int dev_blocks = 0;
     MTG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&dev_blocks, match_rounds_kernel, TB, 0));
     MTG_REQUIRE(dev_blocks >= 1, MTG_ERR_CUDA, "matching kernel does not fit on an SM");
-    const u32 coop_grid = (u32)ctx->num_sms * (u32)std::min(dev_blocks, 4);
+    const u32 coop_grid = (u32)ctx->num_sms * (u32)std::min(dev_blocks, 8);
 
     u64 lo = 0, n_final = 0;
     u32 round_base = 0;
@@ -356,14 +373,18 @@ void greedy_match(mtg_ctx* ctx, const u64* d_records_all, const u32* d_meta_all,
         a.trip_slots = trip_slots.p;
         a.min_insufficient = small.p + 3;
         a.rounds = small.p + 4;
+        a.hist = small.p + 16;
+        a.error = small.p + 7;
         a.round_base = round_base;
         void* kargs[] = {&a};
         MTG_CUDA(cudaLaunchCooperativeKernel((void*)match_rounds_kernel, dim3(coop_grid), dim3(TB), kargs, 0, s));
         ctx->launches++;
-        u32 h_small[5];
+        u32 h_small[8];
         MTG_CUDA(cudaMemcpyAsync(h_small, small.p, sizeof(h_small), cudaMemcpyDeviceToHost, s));
         MTG_CUDA(cudaStreamSynchronize(s));
+        MTG_REQUIRE(h_small[7] == 0, MTG_ERR_INTERNAL, "matching invariant violated (second Dijkstra call for one source)");
         const u32 rounds = h_small[4];
+        if (phase == 0) MTG_CUDA(cudaMemcpyAsync(ctx->match_hist, small.p + 16, sizeof(ctx->match_hist), cudaMemcpyDeviceToHost, s));
         round_base += rounds + 1;
         ctx->stats.match_rounds += rounds;
         const u64 jstar = std::min<u64>(h_small[3], S);

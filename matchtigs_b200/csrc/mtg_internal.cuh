@@ -86,16 +86,6 @@ struct DevStats {
     unsigned long long overflow;
 };
 
-// Host-side graph used by the sequential tail (host_tail.cpp).
-struct HostGraph {
-    u32 n_nodes = 0, n_orig_edges = 0;
-    std::vector<u32> from, to, mirror;   // all edges incl. dummies
-    std::vector<u32> weight;             // per edge (k-mers)
-    std::vector<u8> dummy;               // 1 = dummy edge
-    std::vector<u32> head_out, next_out; // newest-first out-adjacency
-    std::vector<u32> out_deg, in_deg;
-};
-
 }  // namespace mtg
 
 struct mtg_ctx {
@@ -139,7 +129,9 @@ struct mtg_ctx {
     bool have_triples = false;
 
     // ---- host tail ----
-    mtg::HostGraph hg;
+    std::vector<uint32_t> h_dummy_w;  // weight of dummy edge e at [e - 2U]
+    double tail_ms[5] = {0, 0, 0, 0, 0};  // degrees, eulerise, csr, walk, break
+    uint32_t match_hist[48] = {0};        // pending sources per matching round (first phase)
     std::vector<uint32_t> walk_edges;
     std::vector<uint64_t> walk_limits;
     bool have_walks = false;

@@ -1,0 +1,99 @@
+"""CPU tests of the product's host-side logic (no GPU): the C ABI loads and exports every declared symbol,
+the record reader, and the host-sequential tail against the oracle on the oracle's own graph + triples."""
+import random
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle
+import tools
+from helpers import random_fasta
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+@pytest.fixture(scope="module")
+def mt():
+    from matchtigs_b200 import _build
+    _build.build_product()
+    import matchtigs_b200
+    return matchtigs_b200
+
+
+def test_library_exports_every_declared_symbol(mt):
+    from matchtigs_b200 import _lib
+    lib = _lib.load()
+    header = (ROOT / "include" / "matchtigs_b200.h").read_text()
+    declared = set(re.findall(r"\b((?:mtg|matchtigs)_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations found"
+    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+    assert not missing, f"declared but not exported: {missing}"
+    assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
+
+
+def test_context_creation_fails_loudly_without_gpu(mt):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(mt.MatchtigsError) as e:
+        mt.Context(0)
+    assert e.value.code == -2  # MTG_ERR_CUDA: there is no CPU fallback
+
+
+def test_reader_fasta_and_bcalm(mt):
+    u = mt.Unitigs(b">0 LN:i:5 L:+:1:- L:-:0:+\nACGTA\n>1 LN:i:6\r\nACG\nTAC\n\n", True)
+    assert u.count == 2 and list(u.offsets) == [0, 5, 11] and u.seq.tobytes() == b"ACGTAACGTAC"
+    assert list(u.link_a) == [0, 0] and list(u.strand_a) == [1, 0] and list(u.link_b) == [1, 0] and list(u.strand_b) == [0, 1]
+    assert mt.Unitigs(b"", False).count == 0
+    for bad in (b"ACGT\n", b">1\nACGT\n", b">0 L:+:x:+\nACGT\n", b">0 L:*:1:+\nACGT\n"):
+        with pytest.raises(mt.MatchtigsError):
+            mt.Unitigs(bad, True)
+    # the reader agrees with the oracle's reader on generated bcalm files
+    g = tools.genome(20_000, 2, families=4, copies=4, min_len=40, max_len=200, divergence=0.03)
+    text, _, nu = tools.unitigs(g, 21)
+    u = mt.Unitigs(text, True)
+    o = oracle.Oracle().load_bcalm(text, 21)
+    assert u.count == nu == o.num("unitigs")
+    assert np.array_equal((np.diff(u.offsets.astype(np.int64)) + 1 - 21).astype(np.uint64), o.array("edge_weight")[::2])
+
+
+def oracle_inputs(text, k, mode):
+    o = oracle.Oracle()
+    (o.load_fasta if mode == "fasta" else o.load_bcalm)(text, k)
+    o.run()
+    U = o.num("unitigs")
+    return o, (o.array("edge_from")[:2 * U], o.array("edge_to")[:2 * U], o.array("edge_weight")[:2 * U:2].astype(np.uint32),
+               o.array("mirror"), o.array("triples"))
+
+
+def check_tail(mt, text, k, mode):
+    o, (ef, et, uw, mi, tr) = oracle_inputs(text, k, mode)
+    walks, dummy_w, ms = mt.api.host_tail(k, ef, et, uw, mi, tr)
+    ow = o.walks()
+    assert len(walks) == len(ow)
+    for a, b in zip(walks, ow):
+        assert np.array_equal(a, b)
+    U = o.num("unitigs")
+    assert np.array_equal(dummy_w.astype(np.uint64), o.array("edge_weight")[2 * U:])
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_host_tail_equals_oracle_arbitrary(mt, seed):
+    rng = random.Random(900 + seed)
+    k = rng.choice([4, 5, 7, 8, 11])
+    text = random_fasta(rng, rng.randint(1, 300), k, max_extra=10, pool=rng.choice([None, 3, 8, 25]))
+    check_tail(mt, text, k, "fasta")
+
+
+@pytest.mark.parametrize("mode", ["fasta", "bcalm"])
+def test_host_tail_equals_oracle_dbg(mt, mode):
+    anc = tools.genome(15_000, 8, families=3, copies=3, min_len=50, max_len=300, divergence=0.02)
+    text, _, _ = tools.unitigs(tools.pangenome(anc, 10, 5, snp_site_rate=0.04, indel_site_rate=0.003), 15)
+    check_tail(mt, text, 15, mode)
+
+
+def test_host_tail_empty(mt):
+    walks, dummy_w, _ = mt.api.host_tail(5, [], [], [], [], [])
+    assert walks == [] and len(dummy_w) == 0
