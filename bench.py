@@ -43,7 +43,7 @@ WORKLOADS = {
     "chr1": ("chr1", 0.1, "config[2] (scaled): synthetic chr1-like genome with repeat families, k=31"),
     "human": ("human", 0.01, "config[4] (scaled): synthetic human-like genome, k=51"),
 }
-CAP = 8
+CAP = 16
 
 
 def load_peaks() -> tuple[float, str]:
@@ -155,7 +155,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     import matchtigs_b200 as mt
-    from matchtigs_b200.api import device_tensor
+    from matchtigs_b200 import sharding
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -194,18 +194,12 @@ def run_ours(args):
             ctx.greedy_match()
         else:
             ctx.dijkstra_candidates(CAP, rank, world)
-            prec, pmeta, n_local, cap = ctx.candidates_local()
-            S = ctx.graph_info()["sources"]
-            padded = max((S + world - 1) // world, 1)
-            rec_all = torch.empty((world, padded, cap), dtype=torch.int64, device="cuda")
-            meta_all = torch.empty((world, padded), dtype=torch.int32, device="cuda")
-            dist.all_gather_into_tensor(rec_all, device_tensor(prec, (padded, cap), "<i8"))
-            dist.all_gather_into_tensor(meta_all, device_tensor(pmeta, (padded,), "<i4"))
-            torch.cuda.synchronize()
+            rec_all, meta_all = sharding.all_gather_candidates(ctx, dist, torch, world)  # NCCL over NVLink
             ctx.greedy_match(rec_all.data_ptr(), meta_all.data_ptr(), world)
         if rank == 0:
             ctx.finish_walks()
-            return ctx.assemble_tigs("gfa"), ctx.dup_bitvector()
+            # results land in page-locked host memory owned by the context (zero-copy views)
+            return ctx.assemble_tigs_view("gfa"), ctx.dup_bitvector_view()
         return None, None
 
     def timed(resident: bool, steps: int, warmup: int):
@@ -250,7 +244,7 @@ def run_ours(args):
 
     if rank == 0:
         gi = ctx.graph_info()
-        gfa, bv = out
+        gfa, bv = (x.tobytes() for x in out)
         peak, peak_src = load_peaks()
         # algorithmic bytes of the Dijkstra kernel: 12 B per settled node (row_ptr pair + target probe),
         # 5 B per relaxed short edge (col + weight), 8 B per emitted candidate

@@ -151,6 +151,10 @@ void mtg_host_free(void* p);
 int mtg_dup_bitvector(mtg_ctx* ctx, char* out, uint64_t cap, uint64_t* out_len);
 typedef enum mtg_text_format { MTG_FORMAT_GFA = 0, MTG_FORMAT_FASTA = 1 } mtg_text_format;
 int mtg_assemble_tigs(mtg_ctx* ctx, int format, char* out, uint64_t cap, uint64_t* out_len);
+/* Zero-copy variants: *out points into page-locked memory owned by the context (filled by DMA at full PCIe
+ * speed) and stays valid until the next call that produces the same kind of text or mtg_ctx_destroy. */
+int mtg_dup_bitvector_view(mtg_ctx* ctx, const char** out, uint64_t* out_len);
+int mtg_assemble_tigs_view(mtg_ctx* ctx, int format, const char** out, uint64_t* out_len);
 
 /* Everything above in order (single GPU): build -> search -> match -> walks. */
 int mtg_compute_greedytigs_from_sequences(mtg_ctx* ctx, const char* seq_ascii, const uint64_t* offsets,

@@ -21,7 +21,7 @@ EXPORTED_SYMBOLS = [
     "mtg_dijkstra_candidates", "mtg_candidates_local", "mtg_candidates_export",
     "mtg_greedy_match", "mtg_triples_export",
     "mtg_finish_walks", "mtg_walks_export", "mtg_walks_export_capi", "mtg_host_tail", "mtg_host_free",
-    "mtg_dup_bitvector", "mtg_assemble_tigs",
+    "mtg_dup_bitvector", "mtg_assemble_tigs", "mtg_dup_bitvector_view", "mtg_assemble_tigs_view",
     "mtg_compute_greedytigs_from_sequences", "mtg_get_search_stats", "mtg_get_diagnostics",
     "mtg_unitigs_parse", "mtg_unitigs_free", "mtg_unitigs_view",
     "matchtigs_initialise", "matchtigs_initialise_graph", "matchtigs_merge_nodes", "matchtigs_build_graph",
@@ -88,6 +88,8 @@ def load() -> C.CDLL:
     l.mtg_host_free.restype = None
     l.mtg_dup_bitvector.argtypes = [vp, vp, u64, C.POINTER(u64)]
     l.mtg_assemble_tigs.argtypes = [vp, i32, vp, u64, C.POINTER(u64)]
+    l.mtg_dup_bitvector_view.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
+    l.mtg_assemble_tigs_view.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(u64)]
     l.mtg_compute_greedytigs_from_sequences.argtypes = [vp, vp, vp, u64, u32, u32]
     l.mtg_get_search_stats.argtypes = [vp, C.POINTER(SearchStats)]
     l.mtg_get_diagnostics.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint32)]

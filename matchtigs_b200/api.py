@@ -177,18 +177,25 @@ class Context:
         self._check(self._l.mtg_walks_export_capi(self._h, _ptr(eo), _ptr(io_), _ptr(lim)))
         return eo[:self._n_walk_edges], io_[:self._n_walk_edges], lim[:self._n_walks]
 
-    def _text(self, fn, *args) -> bytes:
-        n = C.c_uint64()
-        self._check(fn(self._h, *args, None, 0, C.byref(n)))
-        buf = np.zeros(n.value, np.uint8)
-        self._check(fn(self._h, *args, _ptr(buf), n.value, C.byref(n)))
-        return buf.tobytes()
+    def _view(self, fn, *args) -> np.ndarray:
+        p, n = C.c_void_p(), C.c_uint64()
+        self._check(fn(self._h, *args, C.byref(p), C.byref(n)))
+        if n.value == 0:
+            return np.zeros(0, np.uint8)
+        return np.frombuffer((C.c_char * n.value).from_address(p.value), dtype=np.uint8)
+
+    def dup_bitvector_view(self) -> np.ndarray:
+        """Bitvector bytes as a zero-copy uint8 view of the context's pinned buffer (valid until the next call)."""
+        return self._view(self._l.mtg_dup_bitvector_view)
+
+    def assemble_tigs_view(self, fmt: str = "gfa") -> np.ndarray:
+        return self._view(self._l.mtg_assemble_tigs_view, 0 if fmt == "gfa" else 1)
 
     def dup_bitvector(self) -> bytes:
-        return self._text(self._l.mtg_dup_bitvector)
+        return self.dup_bitvector_view().tobytes()
 
     def assemble_tigs(self, fmt: str = "gfa") -> bytes:
-        return self._text(self._l.mtg_assemble_tigs, 0 if fmt == "gfa" else 1)
+        return self.assemble_tigs_view(fmt).tobytes()
 
     def search_stats(self) -> dict:
         st = _lib.SearchStats()

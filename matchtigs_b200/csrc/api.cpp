@@ -104,6 +104,8 @@ void mtg_ctx_destroy(mtg_ctx* ctx) {
     ctx->d_dummy_w.release(s);
     ctx->scratch_a.release(s);
     ctx->scratch_b.release(s);
+    for (auto& b : ctx->text_stage) b.release();
+    for (auto& b : ctx->tail_stage) b.release();
     if (s) {
         cudaStreamSynchronize(s);
         cudaStreamDestroy(s);
@@ -241,14 +243,28 @@ int mtg_walks_export_capi(mtg_ctx* ctx, ptrdiff_t* tigs_edge_out, size_t* tigs_i
 
 int mtg_dup_bitvector(mtg_ctx* ctx, char* out, uint64_t cap, uint64_t* out_len) {
     return guarded(ctx, [&] {
-        u64 n = dup_bitvector(ctx, out, cap);
+        u64 n = dup_bitvector(ctx, out, cap, out == nullptr, nullptr);
         if (out_len) *out_len = n;
+    });
+}
+
+int mtg_dup_bitvector_view(mtg_ctx* ctx, const char** out, uint64_t* out_len) {
+    return guarded(ctx, [&] {
+        MTG_REQUIRE(out && out_len, MTG_ERR_INVALID, "null output");
+        *out_len = dup_bitvector(ctx, nullptr, 0, false, out);
+    });
+}
+
+int mtg_assemble_tigs_view(mtg_ctx* ctx, int format, const char** out, uint64_t* out_len) {
+    return guarded(ctx, [&] {
+        MTG_REQUIRE(out && out_len, MTG_ERR_INVALID, "null output");
+        *out_len = assemble_tigs(ctx, format, nullptr, 0, false, out);
     });
 }
 
 int mtg_assemble_tigs(mtg_ctx* ctx, int format, char* out, uint64_t cap, uint64_t* out_len) {
     return guarded(ctx, [&] {
-        u64 n = assemble_tigs(ctx, format, out, cap);
+        u64 n = assemble_tigs(ctx, format, out, cap, out == nullptr, nullptr);
         if (out_len) *out_len = n;
     });
 }

@@ -160,7 +160,9 @@ __global__ void __launch_bounds__(TB)
     }
 }
 
-u64 emit(mtg_ctx* ctx, int mode, const char* prefix, size_t prefix_len, char* out, u64 cap) {
+// Produces the text of `mode` into the context's pinned staging buffer (full-speed DMA) and returns its length.
+// out != nullptr: additionally copied to the caller's buffer.  size_only: nothing is materialised.
+u64 emit(mtg_ctx* ctx, int mode, const char* prefix, size_t prefix_len, char* out, u64 cap, bool size_only, const char** view) {
     MTG_REQUIRE(ctx->have_walks, MTG_ERR_INVALID, "no walks: call mtg_finish_walks first");
     MTG_REQUIRE(mode == 0 || ctx->have_seqs, MTG_ERR_INVALID, "sequences were not supplied: tig strings cannot be assembled");
     cudaStream_t s = ctx->stream;
@@ -174,30 +176,34 @@ u64 emit(mtg_ctx* ctx, int mode, const char* prefix, size_t prefix_len, char* ou
     w.T = ctx->walk_limits.size();
     w.E = ctx->E;
     w.k = ctx->k;
-    if (w.W == 0) {
-        if (out && cap >= prefix_len && prefix_len) memcpy(out, prefix, prefix_len);
-        return prefix_len;
-    }
+    PinnedBuf& stage = ctx->text_stage[mode];
+    u64 total = 0;
     DBuf<u32> seg_len, seg_tig;
     DBuf<u64> seg_off;
-    seg_len.resize(w.W, s);
-    seg_tig.resize(w.W, s);
-    seg_off.resize(w.W + 1, s);
-    MTG_LAUNCH(ctx, segment_lengths, grid_for(w.W, TB), TB, 0, w, mode, seg_len.p, seg_tig.p);
-    exclusive_sum_u32_to_u64(ctx, seg_len.p, seg_off.p, w.W, seg_off.p + w.W);
-    u64 total = 0;
-    MTG_CUDA(cudaMemcpyAsync(&total, seg_off.p + w.W, sizeof(u64), cudaMemcpyDeviceToHost, s));
-    MTG_CUDA(cudaStreamSynchronize(s));
-    if (out) {
-        MTG_REQUIRE(cap >= total + prefix_len, MTG_ERR_INVALID, "output buffer too small");
-        char* d_out = nullptr;
-        MTG_CUDA(cudaMallocAsync((void**)&d_out, total + CHUNK, s));
-        u64 chunks = (total + CHUNK - 1) / CHUNK;
-        MTG_LAUNCH(ctx, fill_text, grid_for(chunks, TB), TB, 0, w, mode, seg_off.p, seg_len.p, seg_tig.p, ctx->seq_words.p, total, d_out);
-        if (prefix_len) memcpy(out, prefix, prefix_len);
-        MTG_CUDA(cudaMemcpyAsync(out + prefix_len, d_out, total, cudaMemcpyDeviceToHost, s));
+    if (w.W) {
+        seg_len.resize(w.W, s);
+        seg_tig.resize(w.W, s);
+        seg_off.resize(w.W + 1, s);
+        MTG_LAUNCH(ctx, segment_lengths, grid_for(w.W, TB), TB, 0, w, mode, seg_len.p, seg_tig.p);
+        exclusive_sum_u32_to_u64(ctx, seg_len.p, seg_off.p, w.W, seg_off.p + w.W);
+        MTG_CUDA(cudaMemcpyAsync(&total, seg_off.p + w.W, sizeof(u64), cudaMemcpyDeviceToHost, s));
         MTG_CUDA(cudaStreamSynchronize(s));
-        MTG_CUDA(cudaFreeAsync(d_out, s));
+    }
+    if (!size_only) {
+        MTG_REQUIRE(!out || cap >= total + prefix_len, MTG_ERR_INVALID, "output buffer too small");
+        stage.ensure(total + prefix_len + 1);
+        if (prefix_len) memcpy(stage.p, prefix, prefix_len);
+        if (total) {
+            char* d_out = nullptr;
+            MTG_CUDA(cudaMallocAsync((void**)&d_out, total + CHUNK, s));
+            u64 chunks = (total + CHUNK - 1) / CHUNK;
+            MTG_LAUNCH(ctx, fill_text, grid_for(chunks, TB), TB, 0, w, mode, seg_off.p, seg_len.p, seg_tig.p, ctx->seq_words.p, total, d_out);
+            MTG_CUDA(cudaMemcpyAsync(stage.p + prefix_len, d_out, total, cudaMemcpyDeviceToHost, s));
+            MTG_CUDA(cudaStreamSynchronize(s));
+            MTG_CUDA(cudaFreeAsync(d_out, s));
+        }
+        if (out && total + prefix_len) memcpy(out, stage.p, total + prefix_len);
+        if (view) *view = stage.p;
     }
     seg_len.release(s);
     seg_tig.release(s);
@@ -207,15 +213,17 @@ u64 emit(mtg_ctx* ctx, int mode, const char* prefix, size_t prefix_len, char* ou
 
 }  // namespace
 
-u64 dup_bitvector(mtg_ctx* ctx, char* out, u64 cap) { return emit(ctx, 0, nullptr, 0, out, cap); }
+u64 dup_bitvector(mtg_ctx* ctx, char* out, u64 cap, bool size_only, const char** view) {
+    return emit(ctx, 0, nullptr, 0, out, cap, size_only, view);
+}
 
-u64 assemble_tigs(mtg_ctx* ctx, int format, char* out, u64 cap) {
+u64 assemble_tigs(mtg_ctx* ctx, int format, char* out, u64 cap, bool size_only, const char** view) {
     MTG_REQUIRE(format == MTG_FORMAT_GFA || format == MTG_FORMAT_FASTA, MTG_ERR_INVALID, "unknown text format");
     if (format == MTG_FORMAT_GFA) {
         std::string header = "H\tKL:Z:" + std::to_string(ctx->k) + "\n";  // src/bin.rs:688-693
-        return emit(ctx, 1, header.data(), header.size(), out, cap);
+        return emit(ctx, 1, header.data(), header.size(), out, cap, size_only, view);
     }
-    return emit(ctx, 2, nullptr, 0, out, cap);
+    return emit(ctx, 2, nullptr, 0, out, cap, size_only, view);
 }
 
 }  // namespace mtg

@@ -14,12 +14,38 @@
 // doubly linked list (rotate == move the head), a FIFO of not-yet-exhausted positions instead of
 // rescanning the cycle, per-node row cursors and a used-edge bitset, which makes it linear in the
 // number of edges with ~4 cache lines touched per edge.
+#include <sys/mman.h>
+
 #include <algorithm>
 #include <chrono>
 #include <cstring>
 #include <memory>
 
 #include "mtg_internal.cuh"
+
+namespace mtg {
+
+// Anonymous mapping advised to use transparent huge pages: the Euler walk is a chain of dependent random
+// accesses over tens of megabytes, and with 4 KiB pages most of them also miss the TLB.
+void* HugeBuf::ensure(size_t bytes) {
+    if (bytes <= cap) return p;
+    release();
+    const size_t two_mb = size_t(2) << 20;
+    size_t want = (bytes + bytes / 8 + two_mb - 1) / two_mb * two_mb;
+    void* q = mmap(nullptr, want, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    MTG_REQUIRE(q != MAP_FAILED, MTG_ERR_INTERNAL, "out of host memory (mmap)");
+    madvise(q, want, MADV_HUGEPAGE);
+    p = q;
+    cap = want;
+    return p;
+}
+void HugeBuf::release() {
+    if (p) munmap(p, cap);
+    p = nullptr;
+    cap = 0;
+}
+
+}  // namespace mtg
 
 namespace mtg {
 
@@ -47,11 +73,30 @@ struct Pair {
     u32 out_node, in_node, w;
 };
 
+// Minimal vector-like view over a cached HugeBuf (trivially copyable element types only).
+template <class T>
+struct HVec {
+    T* p = nullptr;
+    size_t n = 0;
+    void bind(HugeBuf& b, size_t capacity, size_t count, bool zero) {
+        p = static_cast<T*>(b.ensure(std::max<size_t>(capacity, 1) * sizeof(T)));
+        n = count;
+        if (zero && count) memset(p, 0, count * sizeof(T));
+    }
+    T& operator[](size_t i) { return p[i]; }
+    const T& operator[](size_t i) const { return p[i]; }
+    void push_back(const T& v) { p[n++] = v; }
+    size_t size() const { return n; }
+    void clear() { n = 0; }
+    T* data() { return p; }
+    T* begin() { return p; }
+    T* end() { return p + n; }
+};
+
 // D. Pairs the remaining imbalance with breaking edges of weight k.  Needs degrees and mirrors only.
-void eulerise(const TailInput& in, const std::vector<u32>& out_deg, const std::vector<u32>& in_deg, std::vector<Pair>& pairs) {
+void eulerise(const TailInput& in, const u32* out_deg, const u32* in_deg, HVec<i32>& diff, std::vector<Pair>& pairs) {
     const u32 n = (u32)in.n_nodes;
     const u32* mirror = in.mirror;
-    std::vector<i32> diff(n, 0);
     std::vector<u32> outs, ins, selfs;  // ascending node id
     for (u32 v = 0; v < n; v++) {
         if (mirror[v] == v) {
@@ -123,12 +168,16 @@ struct alignas(32) NodeRow {
     AdjEntry inl[ROW_INLINE];
 };
 
-void run_tail(const TailInput& in, TailOutput& out) {
+void run_tail(const TailInput& in, TailOutput& out, TailScratch& scratch) {
     const u32 n = (u32)in.n_nodes;
     const u64 E0 = in.n_orig;
     double t0 = now_ms();
     // ---- degrees after the matching dummies (C) ----
-    std::vector<u32> out_deg(n, 0), in_deg(n, 0);
+    HVec<u32> out_deg, in_deg;
+    HVec<i32> diff;
+    out_deg.bind(scratch.out_deg, n, n, true);
+    in_deg.bind(scratch.in_deg, n, n, true);
+    diff.bind(scratch.diff, n, n, true);
     for (u64 e = 0; e < E0; e++) {
         out_deg[in.from[e]]++;
         in_deg[in.to[e]]++;
@@ -145,7 +194,7 @@ void run_tail(const TailInput& in, TailOutput& out) {
     }
     double t1 = now_ms();
     // ---- D ----
-    eulerise(in, out_deg, in_deg, pairs);
+    eulerise(in, out_deg.data(), in_deg.data(), diff, pairs);
     for (size_t j = in.n_triples; j < pairs.size(); j++) {
         out_deg[pairs[j].out_node]++;
         in_deg[pairs[j].in_node]++;
@@ -162,7 +211,8 @@ void run_tail(const TailInput& in, TailOutput& out) {
     const u64 E = E0 + 2 * pairs.size();
     MTG_REQUIRE(E < 0xFFFFFFF0ull, MTG_ERR_UNSUPPORTED, "more than 2^32 edges");
     out.dummy_w.resize(2 * pairs.size());
-    std::vector<NodeRow> rows(n);
+    HVec<NodeRow> rows;
+    rows.bind(scratch.rows, n, n, false);
     u64 n_ext = 0;
     for (u32 v = 0; v < n; v++) {
         if (out_deg[v] <= ROW_INLINE) {
@@ -175,7 +225,8 @@ void run_tail(const TailInput& in, TailOutput& out) {
         }
     }
     MTG_REQUIRE(n_ext < ROW_EXT, MTG_ERR_UNSUPPORTED, "too many edges at high-degree nodes");
-    std::unique_ptr<AdjEntry[]> ext(new AdjEntry[n_ext ? n_ext : 1]);
+    HVec<AdjEntry> ext;
+    ext.bind(scratch.ext, n_ext, n_ext, false);
     auto place = [&](u32 v, AdjEntry a) {
         NodeRow& r = rows[v];
         if (r.end & ROW_EXT) ext[r.cur++] = a;
@@ -192,7 +243,8 @@ void run_tail(const TailInput& in, TailOutput& out) {
     for (u32 v = 0; v < n; v++) rows[v].cur = (rows[v].end & ROW_EXT) ? (rows[v].end & ~ROW_EXT) - out_deg[v] : 0;
     double t3 = now_ms();
     // ---- F + G ----
-    std::vector<u64> used((E + 63) / 64 + 1, 0);
+    HVec<u64> used;
+    used.bind(scratch.used, (E + 63) / 64 + 1, (E + 63) / 64 + 1, true);
     auto is_used = [&](u32 e) { return (used[e >> 6] >> (e & 63)) & 1ull; };
     auto mark_pair = [&](u32 e) { used[e >> 6] |= 3ull << (e & 62); };  // e and e^1 share a word
     // The cycle under construction.  Every extension appends a contiguous run of elements to `queue`
@@ -204,8 +256,8 @@ void run_tail(const TailInput& in, TailOutput& out) {
         u32 edge, from;
         u32 child_begin, child_end;
     };
-    std::vector<QEntry> queue;
-    queue.reserve(E / 2 + 16);
+    HVec<QEntry> queue;
+    queue.bind(scratch.queue, E / 2 + 16, 0, false);
     auto first_unused = [&](u32 v) -> const AdjEntry* {
         NodeRow& r = rows[v];
         if (!(r.end & ROW_EXT)) {
@@ -216,7 +268,8 @@ void run_tail(const TailInput& in, TailOutput& out) {
         while (r.cur < end && is_used(ext[r.cur].edge)) r.cur++;
         return r.cur < end ? &ext[r.cur] : nullptr;
     };
-    std::vector<u32> cyc;
+    HVec<u32> cyc;
+    cyc.bind(scratch.cyc, E / 2 + 16, 0, false);
     std::vector<std::pair<u32, u32>> stack;  // (next index, block end)
     out.walk_edges.clear();
     out.walk_limits.clear();
@@ -282,7 +335,6 @@ void run_tail(const TailInput& in, TailOutput& out) {
         const size_t len = queue.size();
         // in-order expansion; the root block is the initial closed walk [0, n0)
         cyc.clear();
-        cyc.reserve(len);
         stack.clear();
         stack.push_back({0u, (u32)n0});
         size_t head_pos = 0;
@@ -360,17 +412,20 @@ void finish_walks(mtg_ctx* ctx) {
     MTG_REQUIRE(ctx->have_graph && ctx->have_triples, MTG_ERR_INVALID, "mtg_greedy_match has not run");
     cudaStream_t s = ctx->stream;
     const u64 U = ctx->U, N = ctx->N, E = ctx->E;
-    std::vector<u32> from(E), to(E), uw(U), mirror(N);
+    u32* from = ctx->tail_stage[0].as<u32>(E + 1);
+    u32* to = ctx->tail_stage[1].as<u32>(E + 1);
+    u32* uw = ctx->tail_stage[2].as<u32>(U + 1);
+    u32* mirror = ctx->tail_stage[3].as<u32>(N + 1);
     if (E) {
-        MTG_CUDA(cudaMemcpyAsync(from.data(), ctx->edge_from.p, E * sizeof(u32), cudaMemcpyDeviceToHost, s));
-        MTG_CUDA(cudaMemcpyAsync(to.data(), ctx->edge_to.p, E * sizeof(u32), cudaMemcpyDeviceToHost, s));
-        MTG_CUDA(cudaMemcpyAsync(uw.data(), ctx->unitig_w.p, U * sizeof(u32), cudaMemcpyDeviceToHost, s));
+        MTG_CUDA(cudaMemcpyAsync(from, ctx->edge_from.p, E * sizeof(u32), cudaMemcpyDeviceToHost, s));
+        MTG_CUDA(cudaMemcpyAsync(to, ctx->edge_to.p, E * sizeof(u32), cudaMemcpyDeviceToHost, s));
+        MTG_CUDA(cudaMemcpyAsync(uw, ctx->unitig_w.p, U * sizeof(u32), cudaMemcpyDeviceToHost, s));
     }
-    if (N) MTG_CUDA(cudaMemcpyAsync(mirror.data(), ctx->mirror.p, N * sizeof(u32), cudaMemcpyDeviceToHost, s));
+    if (N) MTG_CUDA(cudaMemcpyAsync(mirror, ctx->mirror.p, N * sizeof(u32), cudaMemcpyDeviceToHost, s));
     MTG_CUDA(cudaStreamSynchronize(s));
-    TailInput in{ctx->k, N, E, from.data(), to.data(), uw.data(), mirror.data(), ctx->h_triples.data(), ctx->n_triples};
+    TailInput in{ctx->k, N, E, from, to, uw, mirror, ctx->h_triples.data(), ctx->n_triples};
     TailOutput out;
-    run_tail(in, out);
+    run_tail(in, out, ctx->tail_scratch);
     ctx->walk_edges.swap(out.walk_edges);
     ctx->walk_limits.swap(out.walk_limits);
     ctx->h_dummy_w.swap(out.dummy_w);
@@ -409,7 +464,8 @@ extern "C" int mtg_host_tail(uint32_t k, uint64_t nodes, uint64_t unitigs, const
     try {
         TailInput in{k, nodes, 2 * unitigs, edge_from, edge_to, unitig_w, mirror, triples, n_triples};
         TailOutput out;
-        run_tail(in, out);
+        TailScratch scratch;
+        run_tail(in, out, scratch);
         auto dup = [](const auto& v) {
             using T = typename std::decay<decltype(v)>::type::value_type;
             T* p = (T*)malloc(std::max<size_t>(v.size(), 1) * sizeof(T));

@@ -76,6 +76,45 @@ struct DBuf {
     }
 };
 
+// Page-locked host staging memory (grow-only): DMA runs at full PCIe speed only from/to pinned memory.
+struct PinnedBuf {
+    char* p = nullptr;
+    size_t cap = 0;
+    void ensure(size_t bytes) {
+        if (bytes <= cap) return;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        size_t want = bytes + bytes / 8 + 4096;
+        MTG_CUDA(cudaHostAlloc((void**)&p, want, cudaHostAllocDefault));
+        cap = want;
+    }
+    template <class T>
+    T* as(size_t count) {
+        ensure(count * sizeof(T));
+        return reinterpret_cast<T*>(p);
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+// Host arena backed by an anonymous mapping with MADV_HUGEPAGE (host_tail.cpp); grow-only, cached across calls.
+struct HugeBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    void* ensure(size_t bytes);
+    void release();
+    HugeBuf() = default;
+    HugeBuf(const HugeBuf&) = delete;
+    HugeBuf& operator=(const HugeBuf&) = delete;
+    ~HugeBuf() { release(); }
+};
+struct TailScratch {
+    HugeBuf out_deg, in_deg, diff, rows, ext, used, queue, cyc;
+};
+
 // Device-side counters of the search / matching kernels.
 struct DevStats {
     unsigned long long sources_searched;
@@ -139,6 +178,10 @@ struct mtg_ctx {
     mtg::DBuf<mtg::u64> d_walk_limits;
     mtg::DBuf<mtg::u32> d_dummy_w;    // weights of dummy edges, index = edge id - 2U
 
+    mtg::PinnedBuf text_stage[3];     // bitvector / GFA / FASTA bytes, valid until the next call of the same kind
+    mtg::PinnedBuf tail_stage[4];     // edge_from, edge_to, unitig_w, mirror for the host tail
+    mtg::TailScratch tail_scratch;    // cached working arrays of the host tail
+
     mtg_search_stats stats{};
     // scratch
     mtg::DBuf<mtg::u8> scratch_a, scratch_b;
@@ -177,8 +220,8 @@ void dijkstra_candidates(mtg_ctx* ctx, u32 cap, u32 shard_rank, u32 shard_count)
 void greedy_match(mtg_ctx* ctx, const u64* d_records_all, const u32* d_meta_all, u32 shard_count);
 
 // ---- outputs (emit.cu) ----
-u64 dup_bitvector(mtg_ctx* ctx, char* out, u64 cap);
-u64 assemble_tigs(mtg_ctx* ctx, int format, char* out, u64 cap);
+u64 dup_bitvector(mtg_ctx* ctx, char* out, u64 cap, bool size_only, const char** view);
+u64 assemble_tigs(mtg_ctx* ctx, int format, char* out, u64 cap, bool size_only, const char** view);
 
 // ---- host tail (host_tail.cpp) ----
 void finish_walks(mtg_ctx* ctx);
