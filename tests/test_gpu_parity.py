@@ -258,3 +258,20 @@ def test_ecoli_scale_properties(mt, ctx):
     text, k, info = tools.config_unitigs("ecoli", 0.25)
     compare_all(mt, ctx, text, k, "bcalm", dbg_valid=True, check_props=False)
     compare_all(mt, ctx, text, k, "fasta", dbg_valid=True, check_props=False)
+
+
+def test_cli_end_to_end(mt, tmp_path):
+    """`matchtigs`-compatible CLI: files in, files out, bytes equal to the oracle (incl. a gzipped output)."""
+    import gzip
+    from matchtigs_b200 import cli
+    g = tools.genome(20_000, 77, families=4, copies=4, min_len=40, max_len=300, divergence=0.03)
+    text, _, _ = tools.unitigs(g, 21)
+    (tmp_path / "u.fa").write_bytes(text)
+    for flag, mode in (("--bcalm-in", "bcalm"), ("--fa-in", "fasta")):
+        o = run_oracle(text, 21, mode)
+        rc = cli.main([flag, str(tmp_path / "u.fa"), "-k", "21", "--greedytigs-gfa-out", str(tmp_path / "o.gfa.gz"),
+                       "--greedytigs-fa-out", str(tmp_path / "o.fa"), "--greedytigs-duplication-bitvector-out", str(tmp_path / "o.bv")])
+        assert rc == 0
+        assert gzip.open(tmp_path / "o.gfa.gz", "rb").read() == o.text("gfa")
+        assert (tmp_path / "o.fa").read_bytes() == o.text("fasta")
+        assert (tmp_path / "o.bv").read_bytes() == o.text("bitvector")

@@ -97,3 +97,23 @@ def test_host_tail_equals_oracle_dbg(mt, mode):
 def test_host_tail_empty(mt):
     walks, dummy_w, _ = mt.api.host_tail(5, [], [], [], [], [])
     assert walks == [] and len(dummy_w) == 0
+
+
+def test_cli_flag_surface(mt, tmp_path):
+    """The stand-in CLI accepts the reference's flag names (src/bin.rs:56-205) and rejects reference-only work."""
+    from matchtigs_b200 import cli
+    p = cli.build_parser()
+    a = p.parse_args(["--bcalm-in", "x.fa", "-k", "31", "-t", "4", "--greedytigs-gfa-out", "o.gfa", "--greedytigs-fa-out", "o.fa",
+                      "--greedytigs-duplication-bitvector-out", "o.bv", "--dijkstra-node-weight-array-type", "EpochNodeWeightArray",
+                      "--dijkstra-heap-type", "StdBinaryHeap", "--dijkstra-performance-data-type", "Complete",
+                      "--dijkstra-staged-parallelism-divisor", "2.0", "--dijkstra-resource-limit-factor", "3",
+                      "--log-level", "Debug", "--compression-level", "3", "--debug-print-walks"])
+    assert a.k == 31 and a.threads == 4 and a.greedytigs_gfa_out == "o.gfa"
+    for bad in (["--fa-in", "a", "--bcalm-in", "b", "-k", "5", "--greedytigs-fa-out", "o"],
+                ["--gfa-in", "a", "--greedytigs-fa-out", "o"],
+                ["--fa-in", "a", "-k", "5", "--matchtigs-fa-out", "o"],
+                ["--fa-in", "a", "-k", "5", "--eulertigs-gfa-out", "o"],
+                ["--fa-in", "a", "--greedytigs-fa-out", "o"]):
+        with pytest.raises(SystemExit) as e:
+            cli.main(bad)
+        assert e.value.code not in (0, None)
