@@ -24,7 +24,7 @@ SYNTH_SO = ROOT / "tools" / "libmtg_synth.so"
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
-    "-Xcompiler", "-fPIC,-O3,-Wall,-pthread",
+    "-Xcompiler", "-fPIC,-O3,-Wall,-pthread,-fopenmp",
     "--expt-relaxed-constexpr",
 ]
 
@@ -84,7 +84,7 @@ def build_product(force: bool = False, verbose: bool = False, ptxas_info: bool =
     deps = srcs + sorted(CSRC.glob("*.h")) + sorted(CSRC.glob("*.cuh")) + sorted((ROOT / "include").glob("*.h"))
     if force or _stale(PRODUCT_SO, deps):
         cmd = [_nvcc(), *NVCC_FLAGS, "-ccbin", _gxx(), "-I", str(ROOT / "include"), "-I", str(CSRC),
-               "-shared", "-o", str(PRODUCT_SO), *[str(s) for s in srcs], "-lcudart"]
+               "-shared", "-o", str(PRODUCT_SO), *[str(s) for s in srcs], "-lcudart", "-lgomp"]
         if ptxas_info:
             cmd[1:1] = ["-Xptxas", "-v"]
         _run(cmd, verbose or ptxas_info)

@@ -29,7 +29,7 @@ constexpr int DJ_TABLE = 512;         // slots per warp
 constexpr int DJ_TABLE_BITS = 9;
 constexpr int DJ_MAX_ENTRIES = 320;   // distinct labelled nodes per search before tier 2
 constexpr int DJ_LVL_TARGETS = 64;    // targets of one distance level kept for sorting
-constexpr int DJ_CHUNK = 4;           // work items fetched per atomic
+constexpr int DJ_CHUNK = 1;           // work items fetched per atomic (tier 1 only sees the overflow of tier 0)
 constexpr u32 EMPTY = 0xFFFFFFFFu;
 constexpr u32 META_TRUNC = 0x80000000u;
 constexpr u32 META_OVERFLOW = 0x40000000u;
@@ -51,6 +51,8 @@ struct SearchArgs {
     const u32* sources;    // node id of every source
     const u32* work_list;  // optional: global source index per work item
     u64 n_work;
+    const u32* todo;       // optional: the work items this launch processes (tier overflow lists)
+    u64 n_items;           // number of work items of this launch
     u32 shard_rank, shard_count;
     u32 cap, max_weight;
     u64* records;          // [n_work * cap]
@@ -92,6 +94,120 @@ __device__ __forceinline__ u64 warp_or64(u64 v) {
     return ((u64)hi << 32) | lo;
 }
 
+// ---------------- tier 0: one THREAD per source ----------------
+// Most searches label a few dozen nodes and settle one node per distance level, so a whole warp per
+// source idles 31 lanes and pays every per-level warp operation for nothing.  Here every lane runs its own
+// search: labels live in a per-thread slice of shared memory (lane-interleaved, so equal indices never
+// conflict), extraction is a scan for the smallest unsettled (dist, node) -- exactly the heap's pop order --
+// and relaxation is a linear search of the few labelled nodes.  32 independent load chains per warp hide the
+// L2 latency that a single chain cannot.  Searches that outgrow T0_ENTRIES labels go to the warp tier.
+constexpr int T0_THREADS = 128;
+constexpr int T0_ENTRIES = 48;
+constexpr u32 T0_SETTLED = 0x80u;
+
+__global__ void __launch_bounds__(T0_THREADS) dijkstra_thread_kernel(SearchArgs a) {
+    __shared__ u32 s_key[T0_ENTRIES][T0_THREADS];
+    __shared__ u8 s_dist[T0_ENTRIES][T0_THREADS];
+    const unsigned tid = threadIdx.x, lane = tid & 31;
+    unsigned long long st_settled = 0, st_relaxed = 0, st_cand = 0, st_searched = 0, st_trunc = 0, st_ovf = 0;
+    for (;;) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(a.work_counter, 32ull);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= a.n_items) break;
+        const u64 q = base + lane;
+        if (q >= a.n_items) continue;
+        const u64 t = a.todo ? (u64)a.todo[q] : q;
+        const u64 gi = a.work_list ? (u64)a.work_list[t] : t * a.shard_count + a.shard_rank;
+        const u32 src = a.sources[gi];
+        if (a.row_s[src] == a.row_s[src + 1]) {  // no traversable out-edge: the search settles the source only
+            a.meta[t] = 0;
+            st_settled++;
+            continue;
+        }
+        st_searched++;
+        u32 n = 1, emitted = 0;
+        bool truncated = false, overflow = false;
+        unsigned long long settled = 0, relaxed = 0;
+        s_key[0][tid] = src;
+        s_dist[0][tid] = 0;
+        u64* out = a.records + t * a.cap;
+        for (;;) {
+            // extract-min over the unsettled labels: total order (dist, node id)
+            unsigned long long best = ~0ull;
+            u32 bi = 0;
+            for (u32 i = 0; i < n; i++) {
+                const u32 dd = s_dist[i][tid];
+                if (dd & T0_SETTLED) continue;
+                const unsigned long long val = ((unsigned long long)dd << 32) | s_key[i][tid];
+                if (val < best) {
+                    best = val;
+                    bi = i;
+                }
+            }
+            if (best == ~0ull) break;
+            const u32 d = (u32)(best >> 32), v = (u32)best;
+            s_dist[bi][tid] = (u8)(d | T0_SETTLED);
+            settled++;
+            if (v != src && ((a.bitmap[v >> 5] >> (v & 31)) & 1u)) out[emitted++] = (u64)v | ((u64)d << 32);
+            const u32 e0 = a.row_s[v], e1 = a.row_s[v + 1];
+            for (u32 e = e0; e < e1; e++) {
+                const u32 nw = d + a.w_s[e];
+                relaxed++;
+                if (nw > a.max_weight) continue;
+                const u32 u = a.col_s[e];
+                u32 j = 0;
+                while (j < n && s_key[j][tid] != u) j++;
+                if (j < n) {
+                    const u32 dd = s_dist[j][tid];
+                    if (!(dd & T0_SETTLED) && nw < dd) s_dist[j][tid] = (u8)nw;
+                } else if (n < T0_ENTRIES) {
+                    s_key[n][tid] = u;
+                    s_dist[n][tid] = (u8)nw;
+                    n++;
+                } else {
+                    overflow = true;
+                    break;
+                }
+            }
+            if (overflow) break;
+            if (emitted == a.cap) {
+                // the list is full; it is complete only if nothing is left to settle (checked after v's own relaxation,
+                // because the last target may be the only way to further ones)
+                for (u32 i = 0; i < n; i++) truncated |= !(s_dist[i][tid] & T0_SETTLED);
+                break;
+            }
+        }
+        if (overflow) {
+            a.meta[t] = META_OVERFLOW;
+            a.overflow_list[atomicAdd(a.overflow_count, 1u)] = (u32)t;
+            st_ovf++;
+        } else {
+            a.meta[t] = emitted | (truncated ? META_TRUNC : 0u);
+            st_settled += settled;
+            st_relaxed += relaxed;
+            st_cand += emitted;
+            st_trunc += truncated;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        st_settled += __shfl_down_sync(0xffffffffu, st_settled, o);
+        st_relaxed += __shfl_down_sync(0xffffffffu, st_relaxed, o);
+        st_cand += __shfl_down_sync(0xffffffffu, st_cand, o);
+        st_searched += __shfl_down_sync(0xffffffffu, st_searched, o);
+        st_trunc += __shfl_down_sync(0xffffffffu, st_trunc, o);
+        st_ovf += __shfl_down_sync(0xffffffffu, st_ovf, o);
+    }
+    if (lane == 0) {
+        if (st_searched) atomicAdd(&a.stats->sources_searched, st_searched);
+        if (st_settled) atomicAdd(&a.stats->settled, st_settled);
+        if (st_relaxed) atomicAdd(&a.stats->relaxed, st_relaxed);
+        if (st_cand) atomicAdd(&a.stats->candidates, st_cand);
+        if (st_trunc) atomicAdd(&a.stats->truncated, st_trunc);
+        if (st_ovf) atomicAdd(&a.stats->overflow, st_ovf);
+    }
+}
+
 __global__ void __launch_bounds__(DJ_THREADS) dijkstra_warp_kernel(SearchArgs a) {
     __shared__ WarpState state[DJ_WARPS];
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -111,10 +227,11 @@ __global__ void __launch_bounds__(DJ_THREADS) dijkstra_warp_kernel(SearchArgs a)
         unsigned long long chunk0 = 0;
         if (lane == 0) chunk0 = atomicAdd(a.work_counter, (unsigned long long)DJ_CHUNK);
         chunk0 = __shfl_sync(0xffffffffu, chunk0, 0);
-        if (chunk0 >= a.n_work) break;
+        if (chunk0 >= a.n_items) break;
         for (int c = 0; c < DJ_CHUNK; c++) {
-            const u64 t = chunk0 + c;
-            if (t >= a.n_work) break;
+            const u64 q = chunk0 + c;
+            if (q >= a.n_items) break;
+            const u64 t = a.todo ? (u64)a.todo[q] : q;
             const u64 gi = a.work_list ? (u64)a.work_list[t] : t * a.shard_count + a.shard_rank;
             const u32 src = a.sources[gi];
             u32 r0 = 0, r1 = 0;
@@ -129,7 +246,6 @@ __global__ void __launch_bounds__(DJ_THREADS) dijkstra_warp_kernel(SearchArgs a)
                 st_settled += (lane == 0);
                 continue;
             }
-            st_searched += (lane == 0);
             if (lane == 0) {
                 u32 slot = hash_slot(src);
                 ws->key[slot] = src;
@@ -361,13 +477,13 @@ void run_searches(mtg_ctx* ctx, const u32* bitmap, const u32* work_list, u64 n_w
     if (n_work == 0) return;
     cudaStream_t s = ctx->stream;
     MTG_REQUIRE(n_work < 0xFFFFFFFFull, MTG_ERR_UNSUPPORTED, "too many sources");
-    u32* overflow_list = nullptr;
-    u32* overflow_count = nullptr;
+    u32 *list0 = nullptr, *list1 = nullptr;  // work items leaving tier 0 / tier 1
+    u32* counts = nullptr;                   // [0] |list0|, [1] |list1|
     unsigned long long* work_counter = nullptr;
-    MTG_CUDA(cudaMallocAsync((void**)&overflow_list, n_work * sizeof(u32), s));
-    MTG_CUDA(cudaMallocAsync((void**)&overflow_count, sizeof(u32), s));
+    MTG_CUDA(cudaMallocAsync((void**)&list0, n_work * sizeof(u32), s));
+    MTG_CUDA(cudaMallocAsync((void**)&counts, 2 * sizeof(u32), s));
     MTG_CUDA(cudaMallocAsync((void**)&work_counter, sizeof(unsigned long long), s));
-    MTG_CUDA(cudaMemsetAsync(overflow_count, 0, sizeof(u32), s));
+    MTG_CUDA(cudaMemsetAsync(counts, 0, 2 * sizeof(u32), s));
     MTG_CUDA(cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), s));
     SearchArgs a{};
     a.row_s = ctx->row_s.p;
@@ -383,20 +499,40 @@ void run_searches(mtg_ctx* ctx, const u32* bitmap, const u32* work_list, u64 n_w
     a.max_weight = ctx->k - 1;
     a.records = records;
     a.meta = meta;
-    a.overflow_list = overflow_list;
-    a.overflow_count = overflow_count;
     a.stats = ctx->dstats.p;
     a.work_counter = work_counter;
+    // ---- tier 0: thread per source ----
+    a.todo = nullptr;
+    a.n_items = n_work;
+    a.overflow_list = list0;
+    a.overflow_count = counts;
     int occ = 0;
-    MTG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dijkstra_warp_kernel, DJ_THREADS, 0));
+    MTG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dijkstra_thread_kernel, T0_THREADS, 0));
     if (occ < 1) occ = 1;
-    u64 want = (n_work + (u64)DJ_WARPS * DJ_CHUNK - 1) / ((u64)DJ_WARPS * DJ_CHUNK);
-    u32 grid = (u32)std::min<u64>(want, (u64)ctx->num_sms * occ);  // persistent: a whole number of CTAs per SM
-    MTG_LAUNCH(ctx, dijkstra_warp_kernel, grid, DJ_THREADS, 0, a);
-    u32 n_ovf = 0;
-    MTG_CUDA(cudaMemcpyAsync(&n_ovf, overflow_count, sizeof(u32), cudaMemcpyDeviceToHost, s));
+    u32 grid = (u32)std::min<u64>((n_work + T0_THREADS - 1) / T0_THREADS, (u64)ctx->num_sms * occ);  // persistent CTAs
+    MTG_LAUNCH(ctx, dijkstra_thread_kernel, grid, T0_THREADS, 0, a);
+    u32 h_counts[2] = {0, 0};
+    MTG_CUDA(cudaMemcpyAsync(h_counts, counts, sizeof(u32), cudaMemcpyDeviceToHost, s));
     MTG_CUDA(cudaStreamSynchronize(s));
-    if (n_ovf) {
+    // ---- tier 1: warp per source, for searches with more than T0_ENTRIES labelled nodes ----
+    if (h_counts[0]) {
+        const u64 n1 = h_counts[0];
+        MTG_CUDA(cudaMallocAsync((void**)&list1, n1 * sizeof(u32), s));
+        MTG_CUDA(cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), s));
+        a.todo = list0;
+        a.n_items = n1;
+        a.overflow_list = list1;
+        a.overflow_count = counts + 1;
+        MTG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dijkstra_warp_kernel, DJ_THREADS, 0));
+        if (occ < 1) occ = 1;
+        grid = (u32)std::min<u64>((n1 + DJ_WARPS - 1) / DJ_WARPS, (u64)ctx->num_sms * occ);
+        MTG_LAUNCH(ctx, dijkstra_warp_kernel, grid, DJ_THREADS, 0, a);
+        MTG_CUDA(cudaMemcpyAsync(h_counts + 1, counts + 1, sizeof(u32), cudaMemcpyDeviceToHost, s));
+        MTG_CUDA(cudaStreamSynchronize(s));
+    }
+    // ---- tier 2: CTA per source with dense labels in global memory ----
+    if (h_counts[1]) {
+        const u32 n_ovf = h_counts[1];
         const u64 N = ctx->N;
         size_t free_b = 0, total_b = 0;
         MTG_CUDA(cudaMemGetInfo(&free_b, &total_b));
@@ -412,7 +548,7 @@ void run_searches(mtg_ctx* ctx, const u32* bitmap, const u32* work_list, u64 n_w
         MTG_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), s));
         BigArgs b{};
         b.s = a;
-        b.todo = overflow_list;
+        b.todo = list1;
         b.n_todo = n_ovf;
         b.labels = labels;
         b.visited = visited;
@@ -430,8 +566,9 @@ void run_searches(mtg_ctx* ctx, const u32* bitmap, const u32* work_list, u64 n_w
         MTG_CUDA(cudaFreeAsync(d_err, s));
         MTG_REQUIRE(h_err == 0, MTG_ERR_INTERNAL, "tier-2 search exceeded its visited list");
     }
-    MTG_CUDA(cudaFreeAsync(overflow_list, s));
-    MTG_CUDA(cudaFreeAsync(overflow_count, s));
+    MTG_CUDA(cudaFreeAsync(list0, s));
+    if (list1) MTG_CUDA(cudaFreeAsync(list1, s));
+    MTG_CUDA(cudaFreeAsync(counts, s));
     MTG_CUDA(cudaFreeAsync(work_counter, s));
 }
 

@@ -178,19 +178,26 @@ void run_tail(const TailInput& in, TailOutput& out, TailScratch& scratch) {
     out_deg.bind(scratch.out_deg, n, n, true);
     in_deg.bind(scratch.in_deg, n, n, true);
     diff.bind(scratch.diff, n, n, true);
-    for (u64 e = 0; e < E0; e++) {
-        out_deg[in.from[e]]++;
-        in_deg[in.to[e]]++;
+    // Counting and the adjacency fill below are order-independent, so they run on all host cores
+    // (relaxed atomic increments); only the pairing loop and the walk are inherently sequential.
+    auto bump = [](u32& x) { return __atomic_fetch_add(&x, 1u, __ATOMIC_RELAXED); };
+    u32* od = out_deg.data();
+    u32* id = in_deg.data();
+#pragma omp parallel for schedule(static)
+    for (i64 e = 0; e < (i64)E0; e++) {
+        bump(od[in.from[e]]);
+        bump(id[in.to[e]]);
     }
-    std::vector<Pair> pairs;
+    std::vector<Pair> pairs(in.n_triples);
     pairs.reserve(in.n_triples + 1024);
-    for (u64 j = 0; j < in.n_triples; j++) {
+#pragma omp parallel for schedule(static)
+    for (i64 j = 0; j < (i64)in.n_triples; j++) {
         const u32 o = in.triples[3 * j], i = in.triples[3 * j + 1];
-        pairs.push_back({o, i, in.triples[3 * j + 2]});
-        out_deg[o]++;
-        in_deg[i]++;
-        out_deg[in.mirror[i]]++;
-        in_deg[in.mirror[o]]++;
+        pairs[j] = {o, i, in.triples[3 * j + 2]};
+        bump(od[o]);
+        bump(id[i]);
+        bump(od[in.mirror[i]]);
+        bump(id[in.mirror[o]]);
     }
     double t1 = now_ms();
     // ---- D ----
@@ -227,20 +234,38 @@ void run_tail(const TailInput& in, TailOutput& out, TailScratch& scratch) {
     MTG_REQUIRE(n_ext < ROW_EXT, MTG_ERR_UNSUPPORTED, "too many edges at high-degree nodes");
     HVec<AdjEntry> ext;
     ext.bind(scratch.ext, n_ext, n_ext, false);
-    auto place = [&](u32 v, AdjEntry a) {
-        NodeRow& r = rows[v];
-        if (r.end & ROW_EXT) ext[r.cur++] = a;
-        else r.inl[r.cur++] = a;
+    NodeRow* rowp = rows.data();
+    AdjEntry* extp = ext.data();
+    auto place = [&](u32 v, AdjEntry a) {  // any order: every row is sorted afterwards
+        NodeRow& r = rowp[v];
+        const u32 pos = __atomic_fetch_add(&r.cur, 1u, __ATOMIC_RELAXED);
+        if (r.end & ROW_EXT) extp[pos] = a;
+        else r.inl[pos] = a;
     };
-    for (size_t j = pairs.size(); j-- > 0;) {  // descending edge id => newest first inside every row
+#pragma omp parallel for schedule(static)
+    for (i64 j = 0; j < (i64)pairs.size(); j++) {
         const Pair& p = pairs[j];
         const u32 e = (u32)(E0 + 2 * j);
         place(in.mirror[p.in_node], {e + 1, in.mirror[p.out_node]});
         place(p.out_node, {e, p.in_node});
         out.dummy_w[2 * j] = out.dummy_w[2 * j + 1] = p.w;
     }
-    for (u64 e = E0; e-- > 0;) place(in.from[e], {(u32)e, in.to[e]});
-    for (u32 v = 0; v < n; v++) rows[v].cur = (rows[v].end & ROW_EXT) ? (rows[v].end & ~ROW_EXT) - out_deg[v] : 0;
+#pragma omp parallel for schedule(static)
+    for (i64 e = 0; e < (i64)E0; e++) place(in.from[e], {(u32)e, in.to[e]});
+    // newest edge first inside every row (descending edge id), and reset the cursors
+    const auto newer = [](const AdjEntry& a, const AdjEntry& b) { return a.edge > b.edge; };
+#pragma omp parallel for schedule(dynamic, 4096)
+    for (i64 v = 0; v < (i64)n; v++) {
+        NodeRow& r = rowp[v];
+        if (r.end & ROW_EXT) {
+            const u32 end = r.end & ~ROW_EXT, begin = end - od[v];
+            std::sort(extp + begin, extp + end, newer);
+            r.cur = begin;
+        } else {
+            if (r.end > 1) std::sort(r.inl, r.inl + r.end, newer);
+            r.cur = 0;
+        }
+    }
     double t3 = now_ms();
     // ---- F + G ----
     HVec<u64> used;

@@ -125,6 +125,26 @@ def test_cap_independence(mt, ctx, cap):
         compare_all(mt, ctx, text, k, "fasta", cap=cap)
 
 
+@pytest.mark.parametrize("cap", [1, 2, 3, 5])
+def test_targets_reachable_only_through_targets(mt, ctx, cap):
+    """A chain s -> v0 -> v1 -> ... of single-k-mer unitigs where every v_i is a target (extra out-tip) and is the only
+    way to v_{i+1}: a list cut at `cap` must be flagged truncated even though no unsettled label is left when the
+    cap-th target is popped (regression: the per-thread search tier forgot to relax the last target first)."""
+    k = 9
+    for seed in range(6):
+        rng = random.Random(7000 + seed)
+        R = bytes(rng.choice(b"ACGT") for _ in range(k - 1 + 14))
+        recs = [R[i:i + k] for i in range(len(R) - k + 1)]                      # the chain, weight 1 each
+        for i in range(1, len(R) - k + 2):                                      # out-tips: every chain node becomes a target
+            node = R[i:i + k - 1]
+            alt = bytes([c for c in b"ACGT" if c != R[i + k - 1]][:1]) if i + k - 1 < len(R) else b"A"
+            recs.append(node + alt + bytes(rng.choice(b"ACGT") for _ in range(12)))
+        for _ in range(2):                                                      # in-tips: the chain head becomes a source
+            recs.append(bytes(rng.choice(b"ACGT") for _ in range(12)) + R[:k - 1])
+        text = b"".join(b">%d\n%s\n" % (i, s) for i, s in enumerate(recs))
+        compare_all(mt, ctx, text, k, "fasta", cap=cap)
+
+
 def test_requery_phase_is_exercised(mt, ctx):
     rng = random.Random(4242)
     hit = 0
@@ -251,6 +271,14 @@ def test_reference_c_api(mt):
     l.matchtigs_build_graph(h, np.array([1, 2, 3], np.uint64).ctypes.data)
     n = l.matchtigs_compute_tigs(h, 1, 1, 5, b"", b"", eo.ctypes.data, io_.ctypes.data, lim.ctypes.data)
     assert n == 3 and list(eo[:3]) == [0, 1, 2] and list(lim[:3]) == [1, 2, 3]
+
+
+@pytest.mark.parametrize("name,scale", [("chr1", 0.04), ("pangenome", 0.06), ("human", 0.004)])
+def test_other_configs_scaled(mt, ctx, name, scale):
+    """BASELINE configs 3-5 at a scale the oracle finishes in seconds (repeat-rich, high-branching, k=51)."""
+    text, k, info = tools.config_unitigs(name, scale)
+    compare_all(mt, ctx, text, k, "fasta", cap=16)
+    compare_all(mt, ctx, text, k, "bcalm", cap=4)
 
 
 def test_ecoli_scale_properties(mt, ctx):
