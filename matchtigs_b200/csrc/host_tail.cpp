@@ -35,6 +35,7 @@ void* HugeBuf::ensure(size_t bytes) {
     void* q = mmap(nullptr, want, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
     MTG_REQUIRE(q != MAP_FAILED, MTG_ERR_INTERNAL, "out of host memory (mmap)");
     madvise(q, want, MADV_HUGEPAGE);
+    memset(q, 0, want);  // first touch by the thread that will run the sequential walk: keeps the pages on its NUMA node
     p = q;
     cap = want;
     return p;

@@ -4,28 +4,36 @@
 // sources are visited in ascending node id; each takes the nearest still-open in-nodes of its
 // Dijkstra list and updates up to four node multiplicities.  In the single-threaded reference
 // `in_node_map[v]` is set exactly while `mult[v] > 0`, so the whole state is the multiplicity
-// array, and a Dijkstra call with target_amount t against the current map equals "the first t
-// entries of the precomputed list L(src) whose multiplicity is still positive".
+// array, targets only ever close, and a Dijkstra call with target_amount m+1 against the
+// current map equals "the first m+1 entries of the precomputed list L(src) with mult > 0".
+// With m+1 candidates at most one (the source's own mirror) is skipped, so the reference's
+// `while` loop runs exactly once per source.
 //
-// Parallelisation = deterministic reservations.  A source's commit reads/writes only its
-// touch set {src, mirror(src)} + {x, mirror(x) : x in L(src)}.  Each round every pending source
-// writes its index into res[x] with atomicMin for all x in its touch set, and a source commits
-// iff it holds every reservation, i.e. no lower-indexed pending source shares a node with it.
-// Commits of one round touch disjoint state, and the lowest pending source always commits, so
-// the result equals the sequential pass.  One cooperative launch runs all rounds (grid.sync()).
+// Parallelisation = dataflow over per-target wait lists.  For every in-type node x we build the
+// sorted list rev[x] of the sources that might ever take x (x is mirror(src) or an open entry of
+// L(src)).  holder(x) is the lowest-indexed source of rev[x] that is not done yet.  A source
+// commits as soon as it is the holder of everything its commit reads and writes in the current
+// state -- mirror(src) and the first m+1 open entries -- i.e. as soon as every lower-indexed
+// source that could still touch those nodes is done.  Only in-type nodes need guarding: every
+// out-type node a commit touches (src, mirror of an accepted entry) is shared only with sources
+// that have its mirror in their own set.  Unheld entries may be read racily: they can only flip
+// open -> closed, through a lower-indexed source, which is what the sequential order shows.
 //
-// Capped lists: a source that runs out of known open candidates while its list is truncated is
-// "insufficient".  Everything from the smallest insufficient index j* on is discarded, the
-// multiplicities are rebuilt from the triples of sources < j*, truncated lists of sources >= j*
-// are searched again (4x cap, against the current open map) and matching resumes at j*.
-#include <cooperative_groups.h>
-
+// There are no rounds and no grid barriers: one persistent kernel hands sources out in ascending
+// index order (atomic counter), each thread spins until its source is the holder of what it needs,
+// commits, and publishes `done` with release semantics.  A waiting source only ever waits for
+// lower-indexed sources, all of which were handed out earlier to resident threads, and the lowest
+// unfinished source never waits -- so the kernel cannot deadlock and its critical path is the
+// longest dependency chain, not (#rounds x barrier latency).
+//
+// Capped lists: a source whose list is truncated and runs dry is "insufficient".  Everything
+// from the smallest insufficient index j* on is discarded, the multiplicities are rebuilt from
+// the triples of sources < j*, truncated lists of sources >= j* are searched again (4x cap,
+// against the current open map) and matching resumes at j*.
 #include <algorithm>
 #include <memory>
 
 #include "mtg_internal.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace mtg {
 
@@ -38,62 +46,64 @@ constexpr int TB = 256;
 constexpr u32 META_TRUNC = 0x80000000u;
 constexpr u32 META_COUNT = 0x00FFFFFFu;
 constexpr u32 NO_INDEX = 0xFFFFFFFFu;
-constexpr u32 MATCH_HIST = 48;
 
 struct MatchArgs {
     const u32* sources;
     const u32* mirror;
     i32* mult;
-    const u64* list_addr;  // device address of the first record of every source's list
-    const u32* list_meta;  // count | truncated << 31
-    unsigned long long* res;  // [N] reservation words: (~round) << 32 | source index
-    u32* pend[3];
-    u32* counts;           // [3]
-    const u32* trip_off;   // [S] first triple slot of every source
-    u32* trip_cnt;         // [S]
-    u32* trip_slots;       // [3 * total]
-    u32* min_insufficient; // [1]
-    u32* rounds;           // [1]
-    u32* hist;             // [MATCH_HIST] pending sources at the start of each of the first rounds (diagnostic)
-    u32* error;            // [1] invariant violations
-    u32 round_base;
+    const u64* list_addr;   // device address of the first record of every source's list
+    const u32* list_meta;   // count | truncated << 31
+    const u32* pend;        // pending sources of this phase, ascending
+    u32 n_pend;
+    const u32* rev_ptr;     // [N+1] wait lists per node
+    const u32* rev;         // [P] source indices, ascending inside every list
+    u32* cur;               // [N] first possibly-unfinished position of every wait list
+    u32* done;              // [S] 1 once a source has committed (or was dropped)
+    const u32* trip_off;    // [S] first triple slot of every source
+    u32* trip_cnt;          // [S]
+    u32* trip_slots;        // [3 * total]
+    u32* min_insufficient;  // [1]
+    unsigned long long* retries;  // [1] blocked attempts (diagnostic)
+    u32* error;             // [1] invariant violations
+    unsigned long long* counter;  // [1] hand-out position in `pend`
 };
 
-__device__ __forceinline__ void reserve(unsigned long long* res, u32 x, unsigned long long word) { atomicMin(&res[x], word); }
-// mult[] and res[] are rewritten by other SMs between rounds: read them through L2 (ld.global.cg).
+__device__ __forceinline__ u32 ld_acquire(const u32* p) {
+    u32 v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(u32* p, u32 v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+// mult[] is rewritten by other SMs while the kernel runs: always go through L2.
 __device__ __forceinline__ i32 ldm(const i32* mult, u32 x) { return __ldcg(&mult[x]); }
 __device__ __forceinline__ void addm(i32* mult, u32 x, i32 d) { __stcg(&mult[x], __ldcg(&mult[x]) + d); }
-__device__ __forceinline__ unsigned long long ldr(const unsigned long long* res, u32 x) { return __ldcg(&res[x]); }
 
-// Reservations are asymmetric.  A pending source RESERVES mirror(src) and every still-open entry of its
-// whole list (anything it might ever take: closed entries never reopen, so they need no protection), but to
-// COMMIT it only has to HOLD what it reads and writes in the current state: mirror(src) and the first m+1
-// open entries.  Only in-type nodes are reserved: every access a commit makes to an out-type node v
-// (v = src, or v = mirror(x) of an accepted entry x) is shared only with sources that have mirror(v) in
-// their own set.  Holding x means no lower-indexed pending source lists x, so its value is final for this
-// source; a higher-indexed source can never hold x while this one is pending.  Unheld entries may be read
-// racily: they can only flip open -> closed, by a lower-indexed source, which is what the sequential order
-// would have shown; an unheld entry read as open blocks the commit.
-__device__ __forceinline__ void reserve_source(const MatchArgs& a, u32 i, unsigned long long word) {
-    reserve(a.res, a.mirror[a.sources[i]], word);
-    const u64* list = reinterpret_cast<const u64*>(a.list_addr[i]);
-    const u32 count = a.list_meta[i] & META_COUNT;
-    for (u32 p = 0; p < count; p++) {
-        const u32 x = (u32)list[p];
-        if (ldm(a.mult, x) > 0) reserve(a.res, x, word);
-    }
+// Lowest-indexed unfinished source waiting on x.  The acquire loads of `done` order the caller's later reads of
+// mult[] after the commits of the sources it skips.
+__device__ __forceinline__ u32 holder(const MatchArgs& a, u32 x) {
+    const u32 end = a.rev_ptr[x + 1];
+    u32 c = __ldcg(&a.cur[x]);
+    const u32 c0 = c;
+    while (c < end && ld_acquire(&a.done[a.rev[c]])) c++;
+    if (c != c0) atomicMax(&a.cur[x], c);
+    return c < end ? a.rev[c] : NO_INDEX;
 }
 
 enum TryResult { TRY_BLOCKED = 0, TRY_DONE = 1, TRY_INSUFFICIENT = 2 };
 
-// Applies the reference's matching rules (greedytigs/mod.rs:301-523) to source i if it holds its reservations.
-__device__ TryResult try_source(const MatchArgs& a, u32 i, unsigned long long word) {
+// Applies the reference's matching rules (greedytigs/mod.rs:301-523) to source i if every lower-indexed source
+// that could touch what it reads or writes is done.
+__device__ TryResult try_source(const MatchArgs& a, u32 i) {
     const u32 out_node = a.sources[i];
     const u32 M = a.mirror[out_node];
-    if (ldr(a.res, M) != word) return TRY_BLOCKED;
+    if (ldm(a.mult, M) == 0) {  // :318-320; 0 is final (in-type multiplicities never grow), no need to wait for anyone
+        a.trip_cnt[i] = 0;
+        return TRY_DONE;
+    }
+    if (holder(a, M) != i) return TRY_BLOCKED;
     const bool out_self = M == out_node;
-    i32 m = ldm(a.mult, M);  // :306-311
-    if (m == 0) {            // :318-320
+    i32 m = ldm(a.mult, M);  // :306-311, stable now
+    if (m == 0) {
         a.trip_cnt[i] = 0;
         return TRY_DONE;
     }
@@ -107,8 +117,9 @@ __device__ TryResult try_source(const MatchArgs& a, u32 i, unsigned long long wo
     for (u32 p = 0; p < count && found < target_amount; p++) {
         const u32 x = (u32)list[p];
         if (x != M) {
-            if (ldm(a.mult, x) <= 0) continue;
-            if (ldr(a.res, x) != word) return TRY_BLOCKED;
+            if (ldm(a.mult, x) <= 0) continue;            // closed entries never reopen
+            if (holder(a, x) != i) return TRY_BLOCKED;    // a lower-indexed source may still take x
+            if (ldm(a.mult, x) <= 0) continue;            // re-read after the acquire: closed by a source that just finished
         }
         found++;
         last_pos = p;
@@ -159,56 +170,32 @@ __device__ TryResult try_source(const MatchArgs& a, u32 i, unsigned long long wo
     return TRY_DONE;
 }
 
-constexpr u32 LOCAL_MODE_MAX = 2048;  // at most this many pending sources: finish inside one CTA (no grid barriers)
-
-__global__ void __launch_bounds__(TB) match_rounds_kernel(MatchArgs a) {
-    cg::grid_group grid = cg::this_grid();
-    u64 tid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    u64 nthreads = (u64)gridDim.x * blockDim.x;
-    bool local = false;
-    u32 round = 0;
-    for (;; round++) {
-        const u32 cur = round % 3, nxt = (round + 1) % 3, spare = (round + 2) % 3;
-        const u32 n = ((volatile u32*)a.counts)[cur];
-        if (n == 0) break;
-        if (!local && n <= LOCAL_MODE_MAX) {  // uniform decision: every CTA reads the same n after the barrier
-            if (blockIdx.x != 0) return;
-            local = true;
-            tid = threadIdx.x;
-            nthreads = blockDim.x;
+__global__ void __launch_bounds__(TB) match_dataflow_kernel(MatchArgs a) {
+    const unsigned lane = threadIdx.x & 31;
+    unsigned long long retries = 0;
+    for (;;) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(a.counter, 32ull);  // ascending hand-out: whoever we wait for is already running
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= a.n_pend) break;
+        const unsigned long long idx = base + lane;
+        if (idx >= a.n_pend) continue;
+        const u32 i = a.pend[idx];
+        for (;;) {
+            if (i > ((volatile u32*)a.min_insufficient)[0]) break;  // everything above the smallest insufficient source is redone
+            const TryResult r = try_source(a, i);
+            if (r == TRY_INSUFFICIENT) atomicMin(a.min_insufficient, i);
+            if (r != TRY_BLOCKED) break;
+            retries++;
+            __nanosleep(100);
         }
-        if (tid == 0 && round < MATCH_HIST) a.hist[round] = n;
-        const unsigned long long tag = (unsigned long long)(0xFFFFFFFFu - (a.round_base + round)) << 32;
-        const u32* pend = a.pend[cur];
-        for (u64 idx = tid; idx < n; idx += nthreads) {
-            const u32 i = __ldcg(&pend[idx]);
-            if (i > ((volatile u32*)a.min_insufficient)[0]) continue;
-            reserve_source(a, i, tag | i);
-        }
-        if (tid == 0) a.counts[spare] = 0;
-        if (local) {
-            __threadfence();
-            __syncthreads();
-        } else {
-            grid.sync();
-        }
-        for (u64 idx = tid; idx < n; idx += nthreads) {
-            const u32 i = __ldcg(&pend[idx]);
-            if (i > ((volatile u32*)a.min_insufficient)[0]) continue;  // will be discarded anyway
-            const TryResult r = try_source(a, i, tag | i);
-            if (r == TRY_BLOCKED) a.pend[nxt][atomicAdd(&a.counts[nxt], 1u)] = i;
-            else if (r == TRY_INSUFFICIENT) atomicMin(a.min_insufficient, i);
-        }
-        if (local) {
-            __threadfence();
-            __syncthreads();
-        } else {
-            grid.sync();
-        }
+        st_release(&a.done[i], 1u);  // publishes the commit (release) to the sources waiting behind this one
     }
-    if (tid == 0) *a.rounds = round;
+    for (int o = 16; o > 0; o >>= 1) retries += __shfl_down_sync(0xffffffffu, retries, o);
+    if (lane == 0 && retries) atomicAdd(a.retries, retries);
 }
 
+// ---------------- per-phase set-up ----------------
 __global__ void __launch_bounds__(TB)
     init_lists(const u32* __restrict__ sources, const u32* __restrict__ mirror, const i32* __restrict__ imbalance,
                const u64* __restrict__ records_all, const u32* __restrict__ meta_all, u64 S, u32 shard_count, u64 padded, u32 cap,
@@ -234,6 +221,44 @@ __global__ void __launch_bounds__(TB) flag_requery(const u32* __restrict__ list_
 __global__ void __launch_bounds__(TB) compact_indices(const u32* __restrict__ flag, const u32* __restrict__ pos, u64 n, u32* __restrict__ out) {
     u64 i = (u64)blockIdx.x * TB + threadIdx.x;
     if (i < n && flag[i]) out[pos[i]] = (u32)i;
+}
+// wait-list entries of a pending source: mirror(src) + every entry that is open at the start of the phase
+__global__ void __launch_bounds__(TB)
+    count_waits(const u32* __restrict__ pend, u32 n_pend, const u64* __restrict__ list_addr, const u32* __restrict__ list_meta,
+                const i32* __restrict__ mult, u32* __restrict__ cnt) {
+    u32 r = blockIdx.x * TB + threadIdx.x;
+    if (r >= n_pend) return;
+    const u32 i = pend[r];
+    const u64* list = reinterpret_cast<const u64*>(list_addr[i]);
+    const u32 count = list_meta[i] & META_COUNT;
+    u32 c = 1;
+    for (u32 p = 0; p < count; p++) c += mult[(u32)list[p]] > 0;
+    cnt[r] = c;
+}
+__global__ void __launch_bounds__(TB)
+    write_waits(const u32* __restrict__ pend, u32 n_pend, const u64* __restrict__ list_addr, const u32* __restrict__ list_meta,
+                const i32* __restrict__ mult, const u32* __restrict__ sources, const u32* __restrict__ mirror,
+                const u32* __restrict__ off, u32* __restrict__ key, u32* __restrict__ val, u32* __restrict__ deg) {
+    u32 r = blockIdx.x * TB + threadIdx.x;
+    if (r >= n_pend) return;
+    const u32 i = pend[r];
+    const u64* list = reinterpret_cast<const u64*>(list_addr[i]);
+    const u32 count = list_meta[i] & META_COUNT;
+    u32 o = off[r];
+    const u32 M = mirror[sources[i]];
+    key[o] = M;
+    val[o] = i;
+    atomicAdd(&deg[M], 1u);
+    o++;
+    for (u32 p = 0; p < count; p++) {
+        const u32 x = (u32)list[p];
+        if (mult[x] > 0) {
+            key[o] = x;
+            val[o] = i;
+            atomicAdd(&deg[x], 1u);
+            o++;
+        }
+    }
 }
 __global__ void __launch_bounds__(TB) final_counts(const u32* __restrict__ trip_cnt, u64 S, u64 lo, u64 hi, u32* __restrict__ out) {
     u64 i = (u64)blockIdx.x * TB + threadIdx.x;
@@ -285,6 +310,12 @@ __global__ void __launch_bounds__(TB)
     list_meta[i] = pool_meta[t];
 }
 
+int bits_for(u64 n) {
+    int b = 1;
+    while (b < 32 && (1ull << b) < n) b++;
+    return b;
+}
+
 }  // namespace
 
 void greedy_match(mtg_ctx* ctx, const u64* d_records_all, const u32* d_meta_all, u32 shard_count) {
@@ -312,14 +343,13 @@ void greedy_match(mtg_ctx* ctx, const u64* d_records_all, const u32* d_meta_all,
     const u64 padded = (S + shard_count - 1) / shard_count;
     MTG_CUDA(cudaEventRecord(ctx->ev0, s));
     DBuf<i32> mult;
-    DBuf<unsigned long long> res;
     DBuf<u64> list_addr;
-    DBuf<u32> list_meta, max_trip, trip_off, trip_cnt, trip_slots, flag, pos, pend0, pend1, pend2, small, work_list, open_bits, pool_meta;
+    DBuf<u32> list_meta, max_trip, trip_off, trip_cnt, trip_slots, flag, pos, pend, small, work_list, open_bits, pool_meta;
+    DBuf<u32> wait_cnt, wait_off, key_a, key_b, val_a, val_b, rev_ptr, cur, done;
+    DBuf<unsigned long long> big;  // [0] hand-out counter, [1] retries
     std::vector<DBuf<u64>> pools;
     mult.resize(N, s);
     MTG_CUDA(cudaMemcpyAsync(mult.p, ctx->imbalance.p, N * sizeof(i32), cudaMemcpyDeviceToDevice, s));
-    res.resize(N, s);
-    res.fill_ff(s);
     list_addr.resize(S, s);
     list_meta.resize(S, s);
     max_trip.resize(S, s);
@@ -327,11 +357,15 @@ void greedy_match(mtg_ctx* ctx, const u64* d_records_all, const u32* d_meta_all,
     trip_cnt.resize(S, s);
     flag.resize(S, s);
     pos.resize(S, s);
-    pend0.resize(S, s);
-    pend1.resize(S, s);
-    pend2.resize(S, s);
-    small.resize(16 + MATCH_HIST, s);  // [0..2] counts, [3] min_insufficient, [4] rounds, [5] scan total, [6] scan total 2, [16..] hist
+    pend.resize(S, s);
+    done.resize(S, s);
+    wait_cnt.resize(S, s);
+    wait_off.resize(S, s);
+    rev_ptr.resize(N + 1, s);
+    cur.resize(N + 1, s);
+    small.resize(16, s);  // [0] pending count, [3] min_insufficient, [5..7] scan totals, [8] error
     small.zero(s);
+    big.resize(2, s);
     MTG_LAUNCH(ctx, init_lists, grid_for(S, TB), TB, 0, ctx->sources.p, ctx->mirror.p, ctx->imbalance.p, d_records_all, d_meta_all, S,
                shard_count, padded, cap, list_addr.p, list_meta.p, max_trip.p);
     exclusive_sum_u32(ctx, max_trip.p, trip_off.p, S, small.p + 5);
@@ -341,53 +375,74 @@ void greedy_match(mtg_ctx* ctx, const u64* d_records_all, const u32* d_meta_all,
     trip_slots.resize(3ull * std::max<u32>(total_slots, 1), s);
     ctx->triples.resize(3ull * std::max<u32>(total_slots, 1), s);
 
-    int dev_blocks = 0;
-    MTG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&dev_blocks, match_rounds_kernel, TB, 0));
-    MTG_REQUIRE(dev_blocks >= 1, MTG_ERR_CUDA, "matching kernel does not fit on an SM");
-    const u32 coop_grid = (u32)ctx->num_sms * (u32)std::min(dev_blocks, 8);
+    int occ = 0;
+    MTG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, match_dataflow_kernel, TB, 0));
+    if (occ < 1) occ = 1;
 
-    u64 lo = 0, n_final = 0;
-    u32 round_base = 0;
+    u64 lo = 0, n_final = 0, retries_total = 0;
     for (int phase = 0;; phase++) {
         MTG_REQUIRE(phase < 16, MTG_ERR_INTERNAL, "matching did not converge");
-        // pending = sources >= lo with a non-empty list
+        // pending = sources >= lo with a non-empty list, ascending
         MTG_LAUNCH(ctx, flag_pending, grid_for(S, TB), TB, 0, list_meta.p, S, lo, flag.p);
         exclusive_sum_u32(ctx, flag.p, pos.p, S, small.p + 0);
-        MTG_LAUNCH(ctx, compact_indices, grid_for(S, TB), TB, 0, flag.p, pos.p, S, pend0.p);
-        u32 init_small[5] = {0, 0, 0, NO_INDEX, 0};
-        MTG_CUDA(cudaMemcpyAsync(small.p + 1, init_small + 1, 4 * sizeof(u32), cudaMemcpyHostToDevice, s));
-        trip_cnt.zero(s);
-        MatchArgs a{};
-        a.sources = ctx->sources.p;
-        a.mirror = ctx->mirror.p;
-        a.mult = mult.p;
-        a.list_addr = list_addr.p;
-        a.list_meta = list_meta.p;
-        a.res = res.p;
-        a.pend[0] = pend0.p;
-        a.pend[1] = pend1.p;
-        a.pend[2] = pend2.p;
-        a.counts = small.p;
-        a.trip_off = trip_off.p;
-        a.trip_cnt = trip_cnt.p;
-        a.trip_slots = trip_slots.p;
-        a.min_insufficient = small.p + 3;
-        a.rounds = small.p + 4;
-        a.hist = small.p + 16;
-        a.error = small.p + 7;
-        a.round_base = round_base;
-        void* kargs[] = {&a};
-        MTG_CUDA(cudaLaunchCooperativeKernel((void*)match_rounds_kernel, dim3(coop_grid), dim3(TB), kargs, 0, s));
-        ctx->launches++;
-        u32 h_small[8];
-        MTG_CUDA(cudaMemcpyAsync(h_small, small.p, sizeof(h_small), cudaMemcpyDeviceToHost, s));
+        MTG_LAUNCH(ctx, compact_indices, grid_for(S, TB), TB, 0, flag.p, pos.p, S, pend.p);
+        u32 n_pend = 0;
+        MTG_CUDA(cudaMemcpyAsync(&n_pend, small.p + 0, sizeof(u32), cudaMemcpyDeviceToHost, s));
         MTG_CUDA(cudaStreamSynchronize(s));
-        MTG_REQUIRE(h_small[7] == 0, MTG_ERR_INTERNAL, "matching invariant violated (second Dijkstra call for one source)");
-        const u32 rounds = h_small[4];
-        if (phase == 0) MTG_CUDA(cudaMemcpyAsync(ctx->match_hist, small.p + 16, sizeof(ctx->match_hist), cudaMemcpyDeviceToHost, s));
-        round_base += rounds + 1;
-        ctx->stats.match_rounds += rounds;
-        const u64 jstar = std::min<u64>(h_small[3], S);
+        trip_cnt.zero(s);
+        u32 min_insuff = NO_INDEX;
+        if (n_pend) {
+            // wait lists: (node, source) pairs written in source order, stable sort by node => ascending sources per node
+            MTG_LAUNCH(ctx, count_waits, grid_for(n_pend, TB), TB, 0, pend.p, n_pend, list_addr.p, list_meta.p, mult.p, wait_cnt.p);
+            exclusive_sum_u32(ctx, wait_cnt.p, wait_off.p, n_pend, small.p + 6);
+            u32 P = 0;
+            MTG_CUDA(cudaMemcpyAsync(&P, small.p + 6, sizeof(u32), cudaMemcpyDeviceToHost, s));
+            MTG_CUDA(cudaStreamSynchronize(s));
+            key_a.resize(P, s);
+            key_b.resize(P, s);
+            val_a.resize(P, s);
+            val_b.resize(P, s);
+            MTG_CUDA(cudaMemsetAsync(cur.p, 0, (N + 1) * sizeof(u32), s));  // used as the degree histogram first
+            MTG_LAUNCH(ctx, write_waits, grid_for(n_pend, TB), TB, 0, pend.p, n_pend, list_addr.p, list_meta.p, mult.p, ctx->sources.p,
+                       ctx->mirror.p, wait_off.p, key_a.p, val_a.p, cur.p);
+            exclusive_sum_u32(ctx, cur.p, rev_ptr.p, N + 1, nullptr);
+            MTG_CUDA(cudaMemcpyAsync(cur.p, rev_ptr.p, (N + 1) * sizeof(u32), cudaMemcpyDeviceToDevice, s));
+            const int which = radix_sort_pairs_u32(ctx, key_a.p, key_b.p, val_a.p, val_b.p, P, bits_for(N));
+            done.zero(s);
+            u32 init_small[2] = {NO_INDEX, 0};
+            MTG_CUDA(cudaMemcpyAsync(small.p + 3, init_small, sizeof(u32), cudaMemcpyHostToDevice, s));
+            big.zero(s);
+            MatchArgs a{};
+            a.sources = ctx->sources.p;
+            a.mirror = ctx->mirror.p;
+            a.mult = mult.p;
+            a.list_addr = list_addr.p;
+            a.list_meta = list_meta.p;
+            a.pend = pend.p;
+            a.n_pend = n_pend;
+            a.rev_ptr = rev_ptr.p;
+            a.rev = which ? val_b.p : val_a.p;
+            a.cur = cur.p;
+            a.done = done.p;
+            a.trip_off = trip_off.p;
+            a.trip_cnt = trip_cnt.p;
+            a.trip_slots = trip_slots.p;
+            a.min_insufficient = small.p + 3;
+            a.retries = big.p + 1;
+            a.error = small.p + 8;
+            a.counter = big.p;
+            const u32 grid = (u32)std::min<u64>(((u64)n_pend + TB - 1) / TB, (u64)ctx->num_sms * occ);
+            MTG_LAUNCH(ctx, match_dataflow_kernel, grid, TB, 0, a);
+            u32 h_small[9];
+            unsigned long long h_big[2];
+            MTG_CUDA(cudaMemcpyAsync(h_small, small.p, sizeof(h_small), cudaMemcpyDeviceToHost, s));
+            MTG_CUDA(cudaMemcpyAsync(h_big, big.p, sizeof(h_big), cudaMemcpyDeviceToHost, s));
+            MTG_CUDA(cudaStreamSynchronize(s));
+            MTG_REQUIRE(h_small[8] == 0, MTG_ERR_INTERNAL, "matching invariant violated (second Dijkstra call for one source)");
+            min_insuff = h_small[3];
+            retries_total += h_big[1];
+        }
+        const u64 jstar = std::min<u64>(min_insuff, S);
         // finalise sources [lo, jstar)
         MTG_LAUNCH(ctx, final_counts, grid_for(S, TB), TB, 0, trip_cnt.p, S, lo, jstar, flag.p);
         exclusive_sum_u32(ctx, flag.p, pos.p, S, small.p + 5);
@@ -406,11 +461,11 @@ void greedy_match(mtg_ctx* ctx, const u64* d_records_all, const u32* d_meta_all,
         open_bits.resize((N + 31) / 32 + 1, s);
         MTG_LAUNCH(ctx, open_bits_from_mult, grid_for((N + 31) / 32 * 32, TB), TB, 0, mult.p, N, open_bits.p);
         MTG_LAUNCH(ctx, flag_requery, grid_for(S, TB), TB, 0, list_meta.p, S, jstar, flag.p);
-        exclusive_sum_u32(ctx, flag.p, pos.p, S, small.p + 6);
+        exclusive_sum_u32(ctx, flag.p, pos.p, S, small.p + 7);
         work_list.resize(S, s);
         MTG_LAUNCH(ctx, compact_indices, grid_for(S, TB), TB, 0, flag.p, pos.p, S, work_list.p);
         u32 n_req = 0;
-        MTG_CUDA(cudaMemcpyAsync(&n_req, small.p + 6, sizeof(u32), cudaMemcpyDeviceToHost, s));
+        MTG_CUDA(cudaMemcpyAsync(&n_req, small.p + 7, sizeof(u32), cudaMemcpyDeviceToHost, s));
         MTG_CUDA(cudaStreamSynchronize(s));
         MTG_REQUIRE(n_req > 0, MTG_ERR_INTERNAL, "insufficient source without a truncated list");
         pools.emplace_back();
@@ -423,6 +478,7 @@ void greedy_match(mtg_ctx* ctx, const u64* d_records_all, const u32* d_meta_all,
     }
     ctx->n_triples = n_final;
     ctx->stats.matched = n_final;
+    ctx->stats.match_rounds = retries_total;
     ctx->h_triples.resize(3 * n_final);
     if (n_final) MTG_CUDA(cudaMemcpyAsync(ctx->h_triples.data(), ctx->triples.p, 3 * n_final * sizeof(u32), cudaMemcpyDeviceToHost, s));
     MTG_CUDA(cudaEventRecord(ctx->ev1, s));
@@ -439,10 +495,10 @@ void greedy_match(mtg_ctx* ctx, const u64* d_records_all, const u32* d_meta_all,
     ctx->stats.overflow_sources = h.overflow;
     for (auto& p : pools) p.release(s);
     mult.release(s);
-    res.release(s);
     list_addr.release(s);
-    for (DBuf<u32>* b : {&list_meta, &max_trip, &trip_off, &trip_cnt, &trip_slots, &flag, &pos, &pend0, &pend1, &pend2, &small, &work_list,
-                         &open_bits, &pool_meta})
+    big.release(s);
+    for (DBuf<u32>* b : {&list_meta, &max_trip, &trip_off, &trip_cnt, &trip_slots, &flag, &pos, &pend, &small, &work_list, &open_bits,
+                         &pool_meta, &wait_cnt, &wait_off, &key_a, &key_b, &val_a, &val_b, &rev_ptr, &cur, &done})
         b->release(s);
     ctx->have_triples = true;
     ctx->have_walks = false;
