@@ -99,6 +99,7 @@ void mtg_ctx_destroy(mtg_ctx* ctx) {
     ctx->cand_meta.release(s);
     ctx->dstats.release(s);
     ctx->triples.release(s);
+    ctx->final_mult.release(s);
     ctx->d_walk_edges.release(s);
     ctx->d_walk_limits.release(s);
     ctx->d_dummy_w.release(s);

@@ -18,6 +18,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 
@@ -40,10 +41,21 @@ void* HugeBuf::ensure(size_t bytes) {
     cap = want;
     return p;
 }
+void* HugeBuf::ensure_pinned(size_t bytes) {
+    if (bytes <= cap && pinned) return p;
+    ensure(bytes);
+    if (!pinned) {
+        MTG_CUDA(cudaHostRegister(p, cap, cudaHostRegisterDefault));
+        pinned = true;
+    }
+    return p;
+}
 void HugeBuf::release() {
+    if (p && pinned) cudaHostUnregister(p);
     if (p) munmap(p, cap);
     p = nullptr;
     cap = 0;
+    pinned = false;
 }
 
 }  // namespace mtg
@@ -157,17 +169,18 @@ void eulerise(const TailInput& in, const u32* out_deg, const u32* in_deg, HVec<i
     MTG_REQUIRE(ip == ins.size(), MTG_ERR_INTERNAL, "eulerise: in-nodes left over");
 }
 
-struct AdjEntry {
-    u32 edge, to;
+// What the walk needs: the row records (mutable cursors), the overflow rows, the endpoints of the original edges
+// (a closed walk always starts at an original edge: every node owns one) and the dummy weights.
+struct WalkInput {
+    u32 k;
+    u64 n_nodes, E0, E;
+    const u32 *from, *to;
+    NodeRow* rows;
+    const AdjEntry* ext;
+    const u32* dummy_w;  // weight of dummy edge e at [e - E0]
 };
-// One 32-byte record per node: row cursor + up to three out-edges inline, so that stepping through a node
-// touches a single cache line.  Rows with more than three edges live in `ext` (cur/end index into it).
-constexpr u32 ROW_INLINE = 3;
-constexpr u32 ROW_EXT = 0x80000000u;
-struct alignas(32) NodeRow {
-    u32 cur, end;  // next position to inspect / end of the row (ROW_EXT flag: positions refer to `ext`)
-    AdjEntry inl[ROW_INLINE];
-};
+
+void walk_and_break(const WalkInput& w, TailOutput& out, TailScratch& scratch);
 
 void run_tail(const TailInput& in, TailOutput& out, TailScratch& scratch) {
     const u32 n = (u32)in.n_nodes;
@@ -268,7 +281,19 @@ void run_tail(const TailInput& in, TailOutput& out, TailScratch& scratch) {
         }
     }
     double t3 = now_ms();
-    // ---- F + G ----
+    out.ms_degrees = t1 - t0;
+    out.ms_eulerise = t2 - t1;
+    out.ms_csr = t3 - t2;
+    WalkInput w{in.k, in.n_nodes, E0, E, in.from, in.to, rows.data(), ext.data(), out.dummy_w.data()};
+    walk_and_break(w, out, scratch);
+}
+
+// ---- F + G ----
+void walk_and_break(const WalkInput& in, TailOutput& out, TailScratch& scratch) {
+    const u64 E0 = in.E0, E = in.E;
+    NodeRow* rows = in.rows;
+    const AdjEntry* ext = in.ext;
+    double t3 = now_ms();
     HVec<u64> used;
     used.bind(scratch.used, (E + 63) / 64 + 1, (E + 63) / 64 + 1, true);
     auto is_used = [&](u32 e) { return (used[e >> 6] >> (e & 63)) & 1ull; };
@@ -307,22 +332,15 @@ void run_tail(const TailInput& in, TailOutput& out, TailScratch& scratch) {
         out.walk_limits.push_back(out.walk_edges.size());
     };
     auto is_dummy = [&](u32 e) { return e >= E0; };
-    auto dummy_weight = [&](u32 e) { return out.dummy_w[e - E0]; };
+    auto dummy_weight = [&](u32 e) { return in.dummy_w[e - E0]; };
     for (u64 e0 = 0; e0 < E; e0++) {
         if (is_used((u32)e0)) continue;
         // one closed walk per component, started at the lowest unused edge id
         size_t qf = 0;
         queue.clear();
-        u32 start_edge = (u32)e0, start_from, start_to;
-        if (e0 < E0) {
-            start_from = in.from[e0];
-            start_to = in.to[e0];
-        } else {
-            const Pair& p = pairs[(e0 - E0) >> 1];
-            const bool fwd = !((e0 - E0) & 1);
-            start_from = fwd ? p.out_node : in.mirror[p.in_node];
-            start_to = fwd ? p.in_node : in.mirror[p.out_node];
-        }
+        // every node owns an original edge, so the lowest unused edge of a component is never a dummy
+        MTG_REQUIRE(e0 < E0, MTG_ERR_INTERNAL, "closed walk would start at a dummy edge");
+        u32 start_edge = (u32)e0, start_from = in.from[e0], start_to = in.to[e0];
         size_t head_idx = 0;  // queue index of the element the (rotated) cycle vector currently starts with
         size_t n0 = 0;        // length of the initial closed walk == the root block [0, n0)
         bool rooted = false;
@@ -421,9 +439,6 @@ void run_tail(const TailInput& in, TailOutput& out, TailScratch& scratch) {
         ms_break += now_ms() - tb;
     }
     double t4 = now_ms();
-    out.ms_degrees = t1 - t0;
-    out.ms_eulerise = t2 - t1;
-    out.ms_csr = t3 - t2;
     out.ms_break = ms_break;
     out.ms_walk = t4 - t3 - ms_break;
 }
@@ -434,22 +449,73 @@ void run_tail(const TailInput& in, TailOutput& out, TailScratch& scratch) {
 
 namespace mtg {
 
-void finish_walks(mtg_ctx* ctx) {
-    MTG_REQUIRE(ctx->have_graph && ctx->have_triples, MTG_ERR_INVALID, "mtg_greedy_match has not run");
+// D on the compacted leftover lists (same rules as `eulerise` above; positions instead of node-indexed arrays).
+static void eulerise_sparse(u32 k, TailLeftover& lo, std::vector<u32>& breaking) {
+    (void)k;
+    auto& ins = lo.in_nodes;
+    auto& outs = lo.out_nodes;
+    auto& idiff = lo.in_diff;
+    auto& odiff = lo.out_diff;
+    size_t ip = 0, op = outs.size();
+    auto skip_ins = [&] {
+        while (ip < ins.size() && idiff[ip] <= 0) ip++;
+    };
+    auto skip_outs = [&] {
+        while (op > 0 && odiff[op - 1] >= 0) op--;
+    };
+    auto& selfs = lo.self_nodes;
+    for (size_t i = 0; i < selfs.size(); i += 2) {  // src/implementation/mod.rs:481-524
+        if (i + 1 < selfs.size()) {
+            breaking.push_back(selfs[i]);
+            breaking.push_back(selfs[i + 1]);
+        } else {
+            skip_ins();
+            MTG_REQUIRE(ip < ins.size(), MTG_ERR_INTERNAL,
+                        "Have an uneven number of self-mirrors, but no other nodes with missing in edges.");
+            breaking.push_back(selfs[i]);
+            breaking.push_back(ins[ip]);
+            idiff[ip] -= 1;
+            odiff[lo.in_partner[ip]] += 1;
+        }
+    }
+    for (;;) {  // :526-645
+        skip_outs();
+        if (op == 0) break;
+        const size_t o = op - 1;
+        skip_ins();
+        MTG_REQUIRE(ip < ins.size(), MTG_ERR_INTERNAL, "No further in_nodes left");
+        size_t i = ip;
+        if (i == lo.out_partner[o] && odiff[o] > -2) {  // choose_in_node_from_iterator :252-285 (in_node == mirror(out_node))
+            size_t q = ip + 1;
+            while (q < ins.size() && idiff[q] <= 0) q++;
+            MTG_REQUIRE(q < ins.size(), MTG_ERR_INTERNAL, "No further in_nodes left");
+            i = q;
+        }
+        breaking.push_back(outs[o]);
+        breaking.push_back(ins[i]);
+        odiff[o] += 1;
+        idiff[i] -= 1;
+        const size_t mo = lo.in_partner[i], mi = lo.out_partner[o];  // mirror(in_node) among the outs, mirror(out_node) among the ins
+        if (odiff[mo] < 0) odiff[mo] += 1;
+        if (idiff[mi] > 0) idiff[mi] -= 1;
+    }
+    skip_ins();
+    MTG_REQUIRE(ip == ins.size(), MTG_ERR_INTERNAL, "eulerise: in-nodes left over");
+}
+
+// Variant kept for A/B measurements (MTG_TAIL_HOST=1): everything after the matching on the host.
+static void finish_walks_host_prep(mtg_ctx* ctx) {
     cudaStream_t s = ctx->stream;
     const u64 U = ctx->U, N = ctx->N, E = ctx->E;
-    u32* from = ctx->tail_stage[0].as<u32>(E + 1);
-    u32* to = ctx->tail_stage[1].as<u32>(E + 1);
-    u32* uw = ctx->tail_stage[2].as<u32>(U + 1);
-    u32* mirror = ctx->tail_stage[3].as<u32>(N + 1);
+    std::vector<u32> from(E), to(E), uw(U), mirror(N);
     if (E) {
-        MTG_CUDA(cudaMemcpyAsync(from, ctx->edge_from.p, E * sizeof(u32), cudaMemcpyDeviceToHost, s));
-        MTG_CUDA(cudaMemcpyAsync(to, ctx->edge_to.p, E * sizeof(u32), cudaMemcpyDeviceToHost, s));
-        MTG_CUDA(cudaMemcpyAsync(uw, ctx->unitig_w.p, U * sizeof(u32), cudaMemcpyDeviceToHost, s));
+        MTG_CUDA(cudaMemcpyAsync(from.data(), ctx->edge_from.p, E * sizeof(u32), cudaMemcpyDeviceToHost, s));
+        MTG_CUDA(cudaMemcpyAsync(to.data(), ctx->edge_to.p, E * sizeof(u32), cudaMemcpyDeviceToHost, s));
+        MTG_CUDA(cudaMemcpyAsync(uw.data(), ctx->unitig_w.p, U * sizeof(u32), cudaMemcpyDeviceToHost, s));
     }
-    if (N) MTG_CUDA(cudaMemcpyAsync(mirror, ctx->mirror.p, N * sizeof(u32), cudaMemcpyDeviceToHost, s));
+    if (N) MTG_CUDA(cudaMemcpyAsync(mirror.data(), ctx->mirror.p, N * sizeof(u32), cudaMemcpyDeviceToHost, s));
     MTG_CUDA(cudaStreamSynchronize(s));
-    TailInput in{ctx->k, N, E, from, to, uw, mirror, ctx->h_triples.data(), ctx->n_triples};
+    TailInput in{ctx->k, N, E, from.data(), to.data(), uw.data(), mirror.data(), ctx->h_triples.data(), ctx->n_triples};
     TailOutput out;
     run_tail(in, out, ctx->tail_scratch);
     ctx->walk_edges.swap(out.walk_edges);
@@ -458,6 +524,69 @@ void finish_walks(mtg_ctx* ctx) {
     ctx->tail_ms[0] = out.ms_degrees;
     ctx->tail_ms[1] = out.ms_eulerise;
     ctx->tail_ms[2] = out.ms_csr;
+    ctx->tail_ms[3] = out.ms_walk;
+    ctx->tail_ms[4] = out.ms_break;
+    ctx->d_walk_edges.upload(ctx->walk_edges.data(), ctx->walk_edges.size(), s);
+    ctx->d_walk_limits.upload(ctx->walk_limits.data(), ctx->walk_limits.size(), s);
+    ctx->d_dummy_w.upload(ctx->h_dummy_w.data(), ctx->h_dummy_w.size(), s);
+    MTG_CUDA(cudaStreamSynchronize(s));
+    ctx->have_walks = true;
+}
+
+void finish_walks(mtg_ctx* ctx) {
+    MTG_REQUIRE(ctx->have_graph && ctx->have_triples, MTG_ERR_INVALID, "mtg_greedy_match has not run");
+    if (const char* e = getenv("MTG_TAIL_HOST")) {
+        if (*e == '1') return finish_walks_host_prep(ctx);
+    }
+    cudaStream_t s = ctx->stream;
+    const u64 N = ctx->N, E0 = ctx->E;
+    TailScratch& scratch = ctx->tail_scratch;
+    double t0 = now_ms();
+    // leftover imbalance (device compaction) -> pairing loop (host) -> breaking pairs
+    TailLeftover lo;
+    tail_leftover(ctx, lo);
+    std::vector<u32> breaking;
+    eulerise_sparse(ctx->k, lo, breaking);
+    const u64 n_break = breaking.size() / 2;
+    double t1 = now_ms();
+    // adjacency rows on the device, DMA into the walk's arenas; endpoints of the original edges for the walk starts
+    // DMA lands in page-locked staging memory; the walk then works on a copy inside its huge-page arena
+    // (page-locking the arena itself made the walk ~40 % slower: the pinned mapping loses the huge pages)
+    NodeRow* rows_stage = ctx->tail_stage[2].as<NodeRow>(N + 1);
+    u32* from = ctx->tail_stage[0].as<u32>(E0 + 1);
+    u32* to = ctx->tail_stage[1].as<u32>(E0 + 1);
+    if (E0) {
+        MTG_CUDA(cudaMemcpyAsync(from, ctx->edge_from.p, E0 * sizeof(u32), cudaMemcpyDeviceToHost, s));
+        MTG_CUDA(cudaMemcpyAsync(to, ctx->edge_to.p, E0 * sizeof(u32), cudaMemcpyDeviceToHost, s));
+    }
+    u64 n_ext = 0, P = 0;
+    tail_build_rows(ctx, breaking.data(), n_break, rows_stage, ctx->tail_stage[3], &n_ext, &P);
+    MTG_CUDA(cudaStreamSynchronize(s));
+    NodeRow* rows = static_cast<NodeRow*>(scratch.rows.ensure(std::max<u64>(N, 1) * sizeof(NodeRow)));
+    AdjEntry* ext = static_cast<AdjEntry*>(scratch.ext.ensure(std::max<u64>(n_ext, 1) * sizeof(AdjEntry)));
+    // copied in cache-sized chunks: one big memcpy would use non-temporal stores and leave the rows cold in
+    // DRAM, while the walk is a latency chain that runs ~1.5x faster when the last-level cache holds them
+    auto warm_copy = [](void* dst, const void* src, size_t bytes) {
+        const size_t chunk = 256 << 10;
+        for (size_t o = 0; o < bytes; o += chunk) memcpy((char*)dst + o, (const char*)src + o, std::min(chunk, bytes - o));
+    };
+    warm_copy(rows, rows_stage, N * sizeof(NodeRow));
+    warm_copy(ext, ctx->tail_stage[3].p, n_ext * sizeof(AdjEntry));
+    // dummy weights: matching dummies carry their distance, breaking dummies weigh k
+    TailOutput out;
+    out.dummy_w.resize(2 * P);
+    const u32* tr = ctx->h_triples.data();
+    for (u64 j = 0; j < ctx->n_triples; j++) out.dummy_w[2 * j] = out.dummy_w[2 * j + 1] = tr[3 * j + 2];
+    for (u64 j = ctx->n_triples; j < P; j++) out.dummy_w[2 * j] = out.dummy_w[2 * j + 1] = ctx->k;
+    double t2 = now_ms();
+    WalkInput w{ctx->k, N, E0, E0 + 2 * P, from, to, rows, ext, out.dummy_w.data()};
+    walk_and_break(w, out, scratch);
+    ctx->walk_edges.swap(out.walk_edges);
+    ctx->walk_limits.swap(out.walk_limits);
+    ctx->h_dummy_w.swap(out.dummy_w);
+    ctx->tail_ms[0] = 0;
+    ctx->tail_ms[1] = t1 - t0;
+    ctx->tail_ms[2] = t2 - t1;
     ctx->tail_ms[3] = out.ms_walk;
     ctx->tail_ms[4] = out.ms_break;
     // device copies for the output kernels

@@ -335,21 +335,22 @@ void greedy_match(mtg_ctx* ctx, const u64* d_records_all, const u32* d_meta_all,
     ctx->h_triples.clear();
     ctx->stats.match_rounds = 0;
     ctx->stats.requery_phases = 0;
+    ctx->final_mult.resize(N, s);
+    if (N) MTG_CUDA(cudaMemcpyAsync(ctx->final_mult.p, ctx->imbalance.p, N * sizeof(i32), cudaMemcpyDeviceToDevice, s));
     if (S == 0) {
+        MTG_CUDA(cudaStreamSynchronize(s));
         ctx->have_triples = true;
         ctx->stats.matched = 0;
         return;
     }
     const u64 padded = (S + shard_count - 1) / shard_count;
     MTG_CUDA(cudaEventRecord(ctx->ev0, s));
-    DBuf<i32> mult;
+    DBuf<i32>& mult = ctx->final_mult;  // ends up as the leftover imbalance the tail starts from
     DBuf<u64> list_addr;
     DBuf<u32> list_meta, max_trip, trip_off, trip_cnt, trip_slots, flag, pos, pend, small, work_list, open_bits, pool_meta;
     DBuf<u32> wait_cnt, wait_off, key_a, key_b, val_a, val_b, rev_ptr, cur, done;
     DBuf<unsigned long long> big;  // [0] hand-out counter, [1] retries
     std::vector<DBuf<u64>> pools;
-    mult.resize(N, s);
-    MTG_CUDA(cudaMemcpyAsync(mult.p, ctx->imbalance.p, N * sizeof(i32), cudaMemcpyDeviceToDevice, s));
     list_addr.resize(S, s);
     list_meta.resize(S, s);
     max_trip.resize(S, s);
@@ -494,7 +495,6 @@ void greedy_match(mtg_ctx* ctx, const u64* d_records_all, const u32* d_meta_all,
     ctx->stats.relaxed_edges = h.relaxed;
     ctx->stats.overflow_sources = h.overflow;
     for (auto& p : pools) p.release(s);
-    mult.release(s);
     list_addr.release(s);
     big.release(s);
     for (DBuf<u32>* b : {&list_meta, &max_trip, &trip_off, &trip_cnt, &trip_slots, &flag, &pos, &pend, &small, &work_list, &open_bits,

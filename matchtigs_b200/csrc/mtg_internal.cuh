@@ -100,11 +100,26 @@ struct PinnedBuf {
     }
 };
 
+// Adjacency record of the host Euler walk, built either on the host or on the device (tail_prep.cu).
+struct AdjEntry {
+    u32 edge, to;
+};
+// One 32-byte record per node: row cursor + up to three out-edges inline (newest edge first), so that stepping
+// through a node touches a single cache line.  Rows with more than three edges live in `ext`.
+constexpr u32 ROW_INLINE = 3;
+constexpr u32 ROW_EXT = 0x80000000u;
+struct alignas(32) NodeRow {
+    u32 cur, end;  // next position to inspect / end of the row (ROW_EXT flag: positions refer to `ext`)
+    AdjEntry inl[ROW_INLINE];
+};
+
 // Host arena backed by an anonymous mapping with MADV_HUGEPAGE (host_tail.cpp); grow-only, cached across calls.
 struct HugeBuf {
     void* p = nullptr;
     size_t cap = 0;
+    bool pinned = false;
     void* ensure(size_t bytes);
+    void* ensure_pinned(size_t bytes);  // additionally page-locked (cudaHostRegister) so the GPU can DMA into it
     void release();
     HugeBuf() = default;
     HugeBuf(const HugeBuf&) = delete;
@@ -113,6 +128,12 @@ struct HugeBuf {
 };
 struct TailScratch {
     HugeBuf out_deg, in_deg, diff, rows, ext, used, queue, cyc;
+};
+// Nodes still unbalanced after the matching, ascending node id (device compaction, tail_prep.cu).
+// partner = position of the node's mirror in the opposite list.
+struct TailLeftover {
+    std::vector<u32> self_nodes, out_nodes, out_partner, in_nodes, in_partner;
+    std::vector<i32> out_diff, in_diff;
 };
 
 // Device-side counters of the search / matching kernels.
@@ -162,6 +183,7 @@ struct mtg_ctx {
     bool have_cand = false;
 
     // ---- matching (step 3) ----
+    mtg::DBuf<mtg::i32> final_mult;   // [N] node multiplicities after the matching == leftover imbalance
     mtg::DBuf<mtg::u32> triples;      // [3 * n_triples] device
     uint64_t n_triples = 0;
     std::vector<uint32_t> h_triples;
@@ -179,7 +201,7 @@ struct mtg_ctx {
     mtg::DBuf<mtg::u32> d_dummy_w;    // weights of dummy edges, index = edge id - 2U
 
     mtg::PinnedBuf text_stage[3];     // bitvector / GFA / FASTA bytes, valid until the next call of the same kind
-    mtg::PinnedBuf tail_stage[4];     // edge_from, edge_to, unitig_w, mirror for the host tail
+    mtg::PinnedBuf tail_stage[4];     // edge_from, edge_to, node rows, overflow rows: DMA targets of the host tail
     mtg::TailScratch tail_scratch;    // cached working arrays of the host tail
 
     mtg_search_stats stats{};
@@ -223,7 +245,10 @@ void greedy_match(mtg_ctx* ctx, const u64* d_records_all, const u32* d_meta_all,
 u64 dup_bitvector(mtg_ctx* ctx, char* out, u64 cap, bool size_only, const char** view);
 u64 assemble_tigs(mtg_ctx* ctx, int format, char* out, u64 cap, bool size_only, const char** view);
 
-// ---- host tail (host_tail.cpp) ----
+// ---- host tail (host_tail.cpp) and its device-side preparation (tail_prep.cu) ----
 void finish_walks(mtg_ctx* ctx);
+void tail_leftover(mtg_ctx* ctx, TailLeftover& lo);
+void tail_build_rows(mtg_ctx* ctx, const u32* breaking_pairs, u64 n_break, NodeRow* h_rows, PinnedBuf& ext_stage, u64* n_ext_out,
+                     u64* n_pairs_out);
 
 }  // namespace mtg

@@ -28,3 +28,4 @@ for it in range(4):
     print("iter", it, " ".join(f"{n}={x:.2f}ms" for n, x in zip(names, d)), f"total={d.sum():.2f}ms", ctx.search_stats())
 print(ctx.graph_info(), len(gfa), len(bv))
 print(ctx.diagnostics())
+print([l.strip() for l in open('/proc/self/smaps_rollup') if 'AnonHuge' in l or 'Rss' in l][:3])
