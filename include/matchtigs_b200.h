@@ -61,11 +61,13 @@ typedef struct mtg_search_stats {
     uint64_t candidates;        /* (dst, dist) records emitted */
     uint64_t truncated_sources; /* lists cut at `cap` */
     uint64_t overflow_sources;  /* sources that outgrew the shared-memory table and used the global-memory tier */
-    uint64_t match_rounds;      /* reservation rounds of the matching kernel */
+    uint64_t match_rounds;      /* blocked attempts (spins) of the dataflow matching kernel */
     uint64_t requery_phases;    /* extra search phases for sources whose capped list ran dry */
     uint64_t matched;           /* triples produced */
     float dijkstra_ms;          /* device time of the search kernels (CUDA events) */
-    float match_ms;             /* device time of the matching kernels */
+    float match_ms;             /* device time of the matching step (set-up kernels, sort, dataflow kernel, copies) */
+    float dijkstra_kernel_ms;   /* device time of the tier-0 (thread-per-source) search kernel of the last main search */
+    float match_kernel_ms;      /* device time of the dataflow matching kernel (first phase) */
 } mtg_search_stats;
 
 /* ---- lifecycle ---- */

@@ -42,7 +42,8 @@ class SearchStats(C.Structure):
     _fields_ = [("sources_searched", C.c_uint64), ("settled_nodes", C.c_uint64), ("relaxed_edges", C.c_uint64),
                 ("candidates", C.c_uint64), ("truncated_sources", C.c_uint64), ("overflow_sources", C.c_uint64),
                 ("match_rounds", C.c_uint64), ("requery_phases", C.c_uint64), ("matched", C.c_uint64),
-                ("dijkstra_ms", C.c_float), ("match_ms", C.c_float)]
+                ("dijkstra_ms", C.c_float), ("match_ms", C.c_float), ("dijkstra_kernel_ms", C.c_float),
+                ("match_kernel_ms", C.c_float)]
 
     def as_dict(self) -> dict:
         return {n: (float(getattr(self, n)) if t is C.c_float else int(getattr(self, n))) for n, t in self._fields_}

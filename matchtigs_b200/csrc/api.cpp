@@ -60,6 +60,8 @@ int mtg_ctx_create(mtg_ctx** out, int device) {
         MTG_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
         MTG_CUDA(cudaEventCreate(&ctx->ev0));
         MTG_CUDA(cudaEventCreate(&ctx->ev1));
+        MTG_CUDA(cudaEventCreate(&ctx->ev2));
+        MTG_CUDA(cudaEventCreate(&ctx->ev3));
         cudaDeviceProp prop{};
         MTG_CUDA(cudaGetDeviceProperties(&prop, device));
         ctx->num_sms = prop.multiProcessorCount;
@@ -113,6 +115,8 @@ void mtg_ctx_destroy(mtg_ctx* ctx) {
     }
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev2) cudaEventDestroy(ctx->ev2);
+    if (ctx->ev3) cudaEventDestroy(ctx->ev3);
     delete ctx;
 }
 

@@ -510,10 +510,13 @@ void run_searches(mtg_ctx* ctx, const u32* bitmap, const u32* work_list, u64 n_w
     MTG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dijkstra_thread_kernel, T0_THREADS, 0));
     if (occ < 1) occ = 1;
     u32 grid = (u32)std::min<u64>((n_work + T0_THREADS - 1) / T0_THREADS, (u64)ctx->num_sms * occ);  // persistent CTAs
+    MTG_CUDA(cudaEventRecord(ctx->ev2, s));
     MTG_LAUNCH(ctx, dijkstra_thread_kernel, grid, T0_THREADS, 0, a);
+    MTG_CUDA(cudaEventRecord(ctx->ev3, s));
     u32 h_counts[2] = {0, 0};
     MTG_CUDA(cudaMemcpyAsync(h_counts, counts, sizeof(u32), cudaMemcpyDeviceToHost, s));
     MTG_CUDA(cudaStreamSynchronize(s));
+    MTG_CUDA(cudaEventElapsedTime(&ctx->last_kernel_ms, ctx->ev2, ctx->ev3));
     // ---- tier 1: warp per source, for searches with more than T0_ENTRIES labelled nodes ----
     if (h_counts[0]) {
         const u64 n1 = h_counts[0];
@@ -605,6 +608,7 @@ void dijkstra_candidates(mtg_ctx* ctx, u32 cap, u32 shard_rank, u32 shard_count)
     ctx->stats.truncated_sources = h.truncated;
     ctx->stats.overflow_sources = h.overflow;
     ctx->stats.dijkstra_ms = ms;
+    ctx->stats.dijkstra_kernel_ms = ctx->last_kernel_ms;
     ctx->have_cand = true;
     ctx->have_triples = ctx->have_walks = false;
 }

@@ -197,14 +197,14 @@ void run_tail(const TailInput& in, TailOutput& out, TailScratch& scratch) {
     auto bump = [](u32& x) { return __atomic_fetch_add(&x, 1u, __ATOMIC_RELAXED); };
     u32* od = out_deg.data();
     u32* id = in_deg.data();
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (E0 > (1u << 18))
     for (i64 e = 0; e < (i64)E0; e++) {
         bump(od[in.from[e]]);
         bump(id[in.to[e]]);
     }
     std::vector<Pair> pairs(in.n_triples);
     pairs.reserve(in.n_triples + 1024);
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (E0 > (1u << 18))
     for (i64 j = 0; j < (i64)in.n_triples; j++) {
         const u32 o = in.triples[3 * j], i = in.triples[3 * j + 1];
         pairs[j] = {o, i, in.triples[3 * j + 2]};
@@ -256,7 +256,7 @@ void run_tail(const TailInput& in, TailOutput& out, TailScratch& scratch) {
         if (r.end & ROW_EXT) extp[pos] = a;
         else r.inl[pos] = a;
     };
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (E0 > (1u << 18))
     for (i64 j = 0; j < (i64)pairs.size(); j++) {
         const Pair& p = pairs[j];
         const u32 e = (u32)(E0 + 2 * j);
@@ -264,11 +264,11 @@ void run_tail(const TailInput& in, TailOutput& out, TailScratch& scratch) {
         place(p.out_node, {e, p.in_node});
         out.dummy_w[2 * j] = out.dummy_w[2 * j + 1] = p.w;
     }
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (E0 > (1u << 18))
     for (i64 e = 0; e < (i64)E0; e++) place(in.from[e], {(u32)e, in.to[e]});
     // newest edge first inside every row (descending edge id), and reset the cursors
     const auto newer = [](const AdjEntry& a, const AdjEntry& b) { return a.edge > b.edge; };
-#pragma omp parallel for schedule(dynamic, 4096)
+#pragma omp parallel for schedule(dynamic, 4096) if (E0 > (1u << 18))
     for (i64 v = 0; v < (i64)n; v++) {
         NodeRow& r = rowp[v];
         if (r.end & ROW_EXT) {
@@ -507,15 +507,18 @@ static void eulerise_sparse(u32 k, TailLeftover& lo, std::vector<u32>& breaking)
 static void finish_walks_host_prep(mtg_ctx* ctx) {
     cudaStream_t s = ctx->stream;
     const u64 U = ctx->U, N = ctx->N, E = ctx->E;
-    std::vector<u32> from(E), to(E), uw(U), mirror(N);
+    u32* from = ctx->tail_stage[0].as<u32>(E + 1);  // page-locked staging: full-speed DMA
+    u32* to = ctx->tail_stage[1].as<u32>(E + 1);
+    u32* uw = ctx->tail_stage[2].as<u32>(U + 1);
+    u32* mirror = ctx->tail_stage[3].as<u32>(N + 1);
     if (E) {
-        MTG_CUDA(cudaMemcpyAsync(from.data(), ctx->edge_from.p, E * sizeof(u32), cudaMemcpyDeviceToHost, s));
-        MTG_CUDA(cudaMemcpyAsync(to.data(), ctx->edge_to.p, E * sizeof(u32), cudaMemcpyDeviceToHost, s));
-        MTG_CUDA(cudaMemcpyAsync(uw.data(), ctx->unitig_w.p, U * sizeof(u32), cudaMemcpyDeviceToHost, s));
+        MTG_CUDA(cudaMemcpyAsync(from, ctx->edge_from.p, E * sizeof(u32), cudaMemcpyDeviceToHost, s));
+        MTG_CUDA(cudaMemcpyAsync(to, ctx->edge_to.p, E * sizeof(u32), cudaMemcpyDeviceToHost, s));
+        MTG_CUDA(cudaMemcpyAsync(uw, ctx->unitig_w.p, U * sizeof(u32), cudaMemcpyDeviceToHost, s));
     }
-    if (N) MTG_CUDA(cudaMemcpyAsync(mirror.data(), ctx->mirror.p, N * sizeof(u32), cudaMemcpyDeviceToHost, s));
+    if (N) MTG_CUDA(cudaMemcpyAsync(mirror, ctx->mirror.p, N * sizeof(u32), cudaMemcpyDeviceToHost, s));
     MTG_CUDA(cudaStreamSynchronize(s));
-    TailInput in{ctx->k, N, E, from.data(), to.data(), uw.data(), mirror.data(), ctx->h_triples.data(), ctx->n_triples};
+    TailInput in{ctx->k, N, E, from, to, uw, mirror, ctx->h_triples.data(), ctx->n_triples};
     TailOutput out;
     run_tail(in, out, ctx->tail_scratch);
     ctx->walk_edges.swap(out.walk_edges);
@@ -535,9 +538,11 @@ static void finish_walks_host_prep(mtg_ctx* ctx) {
 
 void finish_walks(mtg_ctx* ctx) {
     MTG_REQUIRE(ctx->have_graph && ctx->have_triples, MTG_ERR_INVALID, "mtg_greedy_match has not run");
-    if (const char* e = getenv("MTG_TAIL_HOST")) {
-        if (*e == '1') return finish_walks_host_prep(ctx);
-    }
+    // Small graphs: the device-side preparation is a dozen launches and four round trips, more than the host needs
+    // to do the same work (MTG_TAIL_HOST=0/1 forces either path for A/B measurements).
+    bool host_prep = ctx->N < (1u << 17);
+    if (const char* e = getenv("MTG_TAIL_HOST")) host_prep = (*e == '1');
+    if (host_prep) return finish_walks_host_prep(ctx);
     cudaStream_t s = ctx->stream;
     const u64 N = ctx->N, E0 = ctx->E;
     TailScratch& scratch = ctx->tail_scratch;

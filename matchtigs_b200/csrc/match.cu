@@ -433,13 +433,16 @@ void greedy_match(mtg_ctx* ctx, const u64* d_records_all, const u32* d_meta_all,
             a.error = small.p + 8;
             a.counter = big.p;
             const u32 grid = (u32)std::min<u64>(((u64)n_pend + TB - 1) / TB, (u64)ctx->num_sms * occ);
+            MTG_CUDA(cudaEventRecord(ctx->ev2, s));
             MTG_LAUNCH(ctx, match_dataflow_kernel, grid, TB, 0, a);
+            MTG_CUDA(cudaEventRecord(ctx->ev3, s));
             u32 h_small[9];
             unsigned long long h_big[2];
             MTG_CUDA(cudaMemcpyAsync(h_small, small.p, sizeof(h_small), cudaMemcpyDeviceToHost, s));
             MTG_CUDA(cudaMemcpyAsync(h_big, big.p, sizeof(h_big), cudaMemcpyDeviceToHost, s));
             MTG_CUDA(cudaStreamSynchronize(s));
             MTG_REQUIRE(h_small[8] == 0, MTG_ERR_INTERNAL, "matching invariant violated (second Dijkstra call for one source)");
+            if (phase == 0) MTG_CUDA(cudaEventElapsedTime(&ctx->stats.match_kernel_ms, ctx->ev2, ctx->ev3));
             min_insuff = h_small[3];
             retries_total += h_big[1];
         }

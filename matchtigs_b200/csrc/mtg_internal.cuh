@@ -151,7 +151,8 @@ struct DevStats {
 struct mtg_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    float last_kernel_ms = 0;  // tier-0 search kernel of the last run_searches call
     std::string err;
     uint64_t launches = 0;
     int num_sms = mtg::NUM_SMS_B200;
