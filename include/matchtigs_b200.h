@@ -97,6 +97,13 @@ int mtg_build_graph_from_links(mtg_ctx* ctx, uint64_t unitigs, const uint64_t* w
                                const uint64_t* link_a, const uint8_t* strand_a, const uint64_t* link_b,
                                const uint8_t* strand_b, uint32_t k, const char* seq_ascii, const uint64_t* offsets);
 
+/* Same two builders fed by the device-side record parser: `text` is the raw FASTA (bcalm == 0, --fa-in semantics) or
+ * bcalm2 FASTA (bcalm != 0, --bcalm-in semantics: ids must equal positions, `L:` fields become links) file content,
+ * < 4 GiB, on the host or (text_on_device != 0) already in HBM.  Line splitting, header/sequence separation,
+ * multi-line records, id validation and link extraction all run as scans on the GPU
+ * (replaces the record parsing of genome-graph's readers, call sites src/bin.rs:896-899, :907-910). */
+int mtg_build_graph_from_text(mtg_ctx* ctx, const char* text, uint64_t len, int bcalm, uint32_t k, int text_on_device);
+
 int mtg_graph_get_info(mtg_ctx* ctx, mtg_graph_info* info);
 /* Copies the graph to host arrays (any pointer may be NULL): edge_from/edge_to [2U] (edge 2u = unitig u forward,
  * 2u+1 = its mirror), mirror [N], imbalance [N], sources [S]. */

@@ -17,7 +17,7 @@ STATUS_NAMES = {0: "MTG_OK", -1: "MTG_ERR_INVALID", -2: "MTG_ERR_CUDA", -3: "MTG
 # every symbol include/matchtigs_b200.h declares (tests check that the library exports all of them)
 EXPORTED_SYMBOLS = [
     "mtg_ctx_create", "mtg_ctx_destroy", "mtg_last_error", "mtg_ctx_stream", "mtg_ctx_kernel_launches",
-    "mtg_build_graph_from_sequences", "mtg_build_graph_from_links", "mtg_graph_get_info", "mtg_graph_export",
+    "mtg_build_graph_from_sequences", "mtg_build_graph_from_links", "mtg_build_graph_from_text", "mtg_graph_get_info", "mtg_graph_export",
     "mtg_dijkstra_candidates", "mtg_candidates_local", "mtg_candidates_export",
     "mtg_greedy_match", "mtg_triples_export",
     "mtg_finish_walks", "mtg_walks_export", "mtg_walks_export_capi", "mtg_host_tail", "mtg_host_free",
@@ -73,6 +73,7 @@ def load() -> C.CDLL:
     l.mtg_ctx_kernel_launches.restype = u64
     l.mtg_build_graph_from_sequences.argtypes = [vp, vp, vp, u64, u32, i32]
     l.mtg_build_graph_from_links.argtypes = [vp, u64, vp, u64, vp, vp, vp, vp, u32, vp, vp]
+    l.mtg_build_graph_from_text.argtypes = [vp, vp, u64, i32, u32, i32]
     l.mtg_graph_get_info.argtypes = [vp, C.POINTER(GraphInfo)]
     l.mtg_graph_export.argtypes = [vp, vp, vp, vp, vp, vp]
     l.mtg_dijkstra_candidates.argtypes = [vp, u32, u32, u32]

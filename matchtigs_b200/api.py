@@ -120,6 +120,14 @@ class Context:
         self._check(self._l.mtg_build_graph_from_links(self._h, len(w), _ptr(w), len(la), _ptr(la), _ptr(sa), _ptr(lb), _ptr(sb),
                                                        k, _ptr(seq), _ptr(offsets)))
 
+    def build_graph_from_text(self, text, k: int, bcalm: bool, device_ptr: int | None = None, length: int | None = None):
+        """Device-side record parsing + graph build.  `text`: bytes / uint8 array on the host, or pass device_ptr + length."""
+        if device_ptr is not None:
+            self._check(self._l.mtg_build_graph_from_text(self._h, C.c_void_p(device_ptr), length, int(bcalm), k, 1))
+            return
+        buf = np.frombuffer(text, dtype=np.uint8) if isinstance(text, (bytes, bytearray, memoryview)) else np.ascontiguousarray(text, np.uint8)
+        self._check(self._l.mtg_build_graph_from_text(self._h, _ptr(buf), len(buf), int(bcalm), k, 0))
+
     def graph_info(self) -> dict:
         info = _lib.GraphInfo()
         self._check(self._l.mtg_graph_get_info(self._h, C.byref(info)))
@@ -260,24 +268,36 @@ class Graph:
         return self.ctx.graph_info()["edges"]
 
 
-def read_bigraph_from_fasta_as_edge_centric(text: bytes, k: int, ctx: Context | None = None) -> Graph:
-    """``--fa-in``: nodes are the distinct (k-1)-mers at unitig ends, numbered in first-seen order."""
+_DEVICE_PARSE_LIMIT = 0xFFFFFFF0  # the device-side record parser indexes bytes with 32 bits
+
+
+def read_bigraph_from_fasta_as_edge_centric(text: bytes, k: int, ctx: Context | None = None, device_parse: bool = True) -> Graph:
+    """``--fa-in``: nodes are the distinct (k-1)-mers at unitig ends, numbered in first-seen order.
+
+    Records are split on the device (``mtg_build_graph_from_text``); ``device_parse=False`` (or a file of 4 GiB and
+    more) uses the host reader + ``mtg_build_graph_from_sequences`` instead -- same graph either way."""
     ctx = ctx or Context()
-    u = Unitigs(text, bcalm=False)
-    ctx.build_graph_from_sequences(u.seq, u.offsets, k)
-    return Graph(ctx, k, u.count)
+    if device_parse and len(text) < _DEVICE_PARSE_LIMIT:
+        ctx.build_graph_from_text(text, k, bcalm=False)
+    else:
+        u = Unitigs(text, bcalm=False)
+        ctx.build_graph_from_sequences(u.seq, u.offsets, k)
+    return Graph(ctx, k, ctx.graph_info()["unitigs"])
 
 
-def read_bigraph_from_bcalm2_as_edge_centric(text: bytes, k: int, ctx: Context | None = None) -> Graph:
+def read_bigraph_from_bcalm2_as_edge_centric(text: bytes, k: int, ctx: Context | None = None, device_parse: bool = True) -> Graph:
     """``--bcalm-in``: topology from the ``L:`` links (union-find numbering of ``src/clib.rs``)."""
     ctx = ctx or Context()
-    u = Unitigs(text, bcalm=True)
-    lens = np.diff(u.offsets.astype(np.int64))
-    if u.count and int(lens.min()) < k:
-        raise MatchtigsError(-3, "sequence shorter than k")
-    weights = (lens + 1 - k).astype(np.uint64)
-    ctx.build_graph_from_links(weights, u.link_a, u.strand_a, u.link_b, u.strand_b, k, u.seq, u.offsets)
-    return Graph(ctx, k, u.count)
+    if device_parse and len(text) < _DEVICE_PARSE_LIMIT:
+        ctx.build_graph_from_text(text, k, bcalm=True)
+    else:
+        u = Unitigs(text, bcalm=True)
+        lens = np.diff(u.offsets.astype(np.int64))
+        if u.count and int(lens.min()) < k:
+            raise MatchtigsError(-3, "sequence shorter than k")
+        weights = (lens + 1 - k).astype(np.uint64)
+        ctx.build_graph_from_links(weights, u.link_a, u.strand_a, u.link_b, u.strand_b, k, u.seq, u.offsets)
+    return Graph(ctx, k, ctx.graph_info()["unitigs"])
 
 
 @dataclass

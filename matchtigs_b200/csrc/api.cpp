@@ -133,8 +133,12 @@ int mtg_build_graph_from_links(mtg_ctx* ctx, uint64_t unitigs, const uint64_t* w
                                const uint8_t* strand_a, const uint64_t* link_b, const uint8_t* strand_b, uint32_t k,
                                const char* seq_ascii, const uint64_t* offsets) {
     return guarded(ctx, [&] {
-        build_graph_from_links(ctx, unitigs, weights, n_links, link_a, strand_a, link_b, strand_b, k, seq_ascii, offsets);
+        build_graph_from_links(ctx, unitigs, weights, n_links, link_a, strand_a, link_b, strand_b, k, seq_ascii, offsets, false);
     });
+}
+
+int mtg_build_graph_from_text(mtg_ctx* ctx, const char* text, uint64_t len, int bcalm, uint32_t k, int text_on_device) {
+    return guarded(ctx, [&] { build_graph_from_text(ctx, text, len, bcalm != 0, k, text_on_device != 0); });
 }
 
 int mtg_graph_get_info(mtg_ctx* ctx, mtg_graph_info* info) {

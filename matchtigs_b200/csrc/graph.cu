@@ -583,7 +583,7 @@ void build_graph_from_sequences(mtg_ctx* ctx, const char* seq, const u64* offset
 }
 
 void build_graph_from_links(mtg_ctx* ctx, u64 U, const u64* weights, u64 n_links, const u64* a, const u8* sa, const u64* b,
-                            const u8* sb, u32 k, const char* seq, const u64* offsets) {
+                            const u8* sb, u32 k, const char* seq, const u64* offsets, bool on_device) {
     MTG_REQUIRE(k >= 2 && k <= 64, MTG_ERR_INVALID, "k must be in [2, 64]");
     MTG_REQUIRE(U < (1ull << 30), MTG_ERR_UNSUPPORTED, "more than 2^30 unitigs");
     MTG_REQUIRE(U == 0 || weights, MTG_ERR_INVALID, "null weights");
@@ -598,15 +598,23 @@ void build_graph_from_links(mtg_ctx* ctx, u64 U, const u64* weights, u64 n_links
     int* d_err = nullptr;
     MTG_CUDA(cudaMallocAsync((void**)&d_err, sizeof(int), s));
     MTG_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), s));
-    if (seq && offsets && U) upload_and_pack(ctx, seq, offsets, U, false, d_err);
+    if (seq && offsets && U) upload_and_pack(ctx, seq, offsets, U, on_device, d_err);
     DBuf<u64> d_w, d_a, d_b;
     DBuf<u8> d_sa, d_sb, rank;
     DBuf<u32> cc, key_a, key_b, op_a, op_b, parent, rep, is_rep, node_of_rep;
-    d_w.upload(weights, U, s);
-    d_a.upload(a, n_links, s);
-    d_b.upload(b, n_links, s);
-    d_sa.upload(sa, n_links, s);
-    d_sb.upload(sb, n_links, s);
+    if (on_device) {  // borrowed device arrays (device-side parser): no copies
+        d_w.p = const_cast<u64*>(weights);
+        d_a.p = const_cast<u64*>(a);
+        d_b.p = const_cast<u64*>(b);
+        d_sa.p = const_cast<u8*>(sa);
+        d_sb.p = const_cast<u8*>(sb);
+    } else {
+        d_w.upload(weights, U, s);
+        d_a.upload(a, n_links, s);
+        d_b.upload(b, n_links, s);
+        d_sa.upload(sa, n_links, s);
+        d_sb.upload(sb, n_links, s);
+    }
     ctx->unitig_w.resize(U, s);
     if (U) MTG_LAUNCH(ctx, weights_to_u32, grid_for(U, TB), TB, 0, d_w.p, U, ctx->unitig_w.p, d_err);
     const u64 nslots = 4 * U, nops = 2 * n_links;
@@ -655,6 +663,7 @@ void build_graph_from_links(mtg_ctx* ctx, u64 U, const u64* weights, u64 n_links
     check_err_flag(ctx, d_err);
     MTG_CUDA(cudaFreeAsync(d_tot, s));
     MTG_CUDA(cudaFreeAsync(d_err, s));
+    if (on_device) d_w.p = d_a.p = d_b.p = nullptr, d_sa.p = d_sb.p = nullptr;
     for (DBuf<u64>* x : {&d_w, &d_a, &d_b}) x->release(s);
     for (DBuf<u8>* x : {&d_sa, &d_sb, &rank}) x->release(s);
     for (DBuf<u32>* x : {&cc, &key_a, &key_b, &op_a, &op_b, &parent, &rep, &is_rep, &node_of_rep}) x->release(s);

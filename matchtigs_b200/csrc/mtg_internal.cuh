@@ -224,6 +224,7 @@ inline dim3 grid_for(size_t n, int block) { return dim3((unsigned)((n + block - 
 // ---- primitives (prims.cu) ----
 // out[i] = sum_{j<i} in[j]; returns nothing; `total` (device pointer, may be null) receives the grand total.
 void exclusive_sum_u32(mtg_ctx* ctx, const u32* in, u32* out, size_t n, u32* d_total);
+void exclusive_sum_u8(mtg_ctx* ctx, const u8* in, u32* out, size_t n, u32* d_total);
 void exclusive_sum_u32_to_u64(mtg_ctx* ctx, const u32* in, u64* out, size_t n, u64* d_total);
 // out[i] = max_{j<=i} in[j]
 void inclusive_max_u32(mtg_ctx* ctx, const u32* in, u32* out, size_t n);
@@ -236,7 +237,9 @@ int radix_sort_pairs_u32(mtg_ctx* ctx, u32* k_a, u32* k_b, u32* v_a, u32* v_b, s
 // ---- graph construction (graph.cu) ----
 void build_graph_from_sequences(mtg_ctx* ctx, const char* seq, const u64* offsets, u64 U, u32 k, bool on_device);
 void build_graph_from_links(mtg_ctx* ctx, u64 U, const u64* weights, u64 n_links, const u64* a, const u8* sa, const u64* b,
-                            const u8* sb, u32 k, const char* seq, const u64* offsets);
+                            const u8* sb, u32 k, const char* seq, const u64* offsets, bool on_device);
+// device-side FASTA / bcalm2 record parser feeding the two builders (parse.cu)
+void build_graph_from_text(mtg_ctx* ctx, const char* text, u64 len, bool bcalm, u32 k, bool text_on_device);
 
 // ---- search + matching (dijkstra.cu, match.cu) ----
 void dijkstra_candidates(mtg_ctx* ctx, u32 cap, u32 shard_rank, u32 shard_count);

@@ -172,6 +172,9 @@ void scan_impl(mtg_ctx* ctx, const TIn* in, TOut* out, size_t n, TOut* d_total) 
 void exclusive_sum_u32(mtg_ctx* ctx, const u32* in, u32* out, size_t n, u32* d_total) {
     scan_impl<u32, u32, OpAdd, false>(ctx, in, out, n, d_total);
 }
+void exclusive_sum_u8(mtg_ctx* ctx, const u8* in, u32* out, size_t n, u32* d_total) {
+    scan_impl<u8, u32, OpAdd, false>(ctx, in, out, n, d_total);
+}
 void exclusive_sum_u32_to_u64(mtg_ctx* ctx, const u32* in, u64* out, size_t n, u64* d_total) {
     scan_impl<u32, u64, OpAdd, false>(ctx, in, out, n, d_total);
 }

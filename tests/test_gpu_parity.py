@@ -36,10 +36,10 @@ def run_oracle(text, k, mode):
     return o.run()
 
 
-def build(mt, ctx, text, k, mode):
+def build(mt, ctx, text, k, mode, device_parse=True):
     if mode == "fasta":
-        return mt.read_bigraph_from_fasta_as_edge_centric(text, k, ctx)
-    return mt.read_bigraph_from_bcalm2_as_edge_centric(text, k, ctx)
+        return mt.read_bigraph_from_fasta_as_edge_centric(text, k, ctx, device_parse=device_parse)
+    return mt.read_bigraph_from_bcalm2_as_edge_centric(text, k, ctx, device_parse=device_parse)
 
 
 def compare_all(mt, ctx, text, k, mode, cap=8, dbg_valid=False, check_props=False):
@@ -190,6 +190,53 @@ def test_input_errors(mt, ctx):
     with pytest.raises(mt.MatchtigsError):
         ctx.build_graph_from_sequences(np.frombuffer(b"ACGT", np.uint8), np.array([0, 4], np.uint64), 99)
     # the context stays usable after errors
+    compare_all(mt, ctx, b">0\nACGTA\n", 5, "fasta")
+
+
+def graph_state(ctx):
+    ex = ctx.graph_export()
+    return ctx.graph_info(), {k: v.copy() for k, v in ex.items()}
+
+
+@pytest.mark.parametrize("bcalm", [False, True])
+def test_device_parser_equals_host_reader(mt, ctx, bcalm):
+    """mtg_build_graph_from_text (records parsed on the device) == host reader + array builders, incl. outputs."""
+    anc = tools.genome(20_000, 31, families=3, copies=3, min_len=50, max_len=300, divergence=0.02)
+    text, _, _ = tools.unitigs(tools.pangenome(anc, 8, 4, snp_site_rate=0.04, indel_site_rate=0.003), 21)
+    # multi-line records, CRLF line ends, blank lines, no trailing newline
+    lines = text.split(b"\n")
+    messy = []
+    for ln in lines:
+        if ln.startswith(b">") or len(ln) < 40:
+            messy.append(ln + b"\r")
+        else:
+            messy.extend([ln[:17], ln[17:33] + b"\r", b"", ln[33:]])
+    variants = [text, b"\n".join(messy).rstrip(b"\n")]
+    for t in variants:
+        o = run_oracle(t, 21, "bcalm" if bcalm else "fasta")
+        build(mt, ctx, t, 21, "bcalm" if bcalm else "fasta", device_parse=False)
+        gi_ref, ex_ref = graph_state(ctx)
+        ctx.build_graph_from_text(t, 21, bcalm)
+        gi, ex = graph_state(ctx)
+        assert gi == gi_ref
+        for name in ex_ref:
+            assert np.array_equal(ex[name], ex_ref[name]), name
+        ctx.dijkstra_candidates(8)
+        ctx.greedy_match()
+        ctx.finish_walks()
+        assert ctx.assemble_tigs("gfa") == o.text("gfa") and ctx.dup_bitvector() == o.text("bitvector")
+
+
+def test_device_parser_errors_and_edge_cases(mt, ctx):
+    for bad, bcalm in ((b"ACGT\n>0\nACGTA\n", False), (b">1 LN:i:5\nACGTA\n", True), (b">0 L:+:x:+\nACGTA\n", True),
+                       (b">0 L:*:1:+\nACGTA\n", True), (b">0 L:+:7:+\nACGTA\n", True), (b">0\nACGNA\n", False), (b">0\nAC\n", True)):
+        with pytest.raises(mt.MatchtigsError) as e:
+            ctx.build_graph_from_text(bad, 5, bcalm)
+        assert e.value.code == -3, bad
+    ctx.build_graph_from_text(b"", 5, False)
+    assert ctx.graph_info()["unitigs"] == 0
+    ctx.build_graph_from_text(b">0 LN:i:5 L:+:0:+ L:+:1\nAAAAA", 5, True)  # short `L:` token is ignored like the host reader does
+    assert ctx.graph_info()["unitigs"] == 1
     compare_all(mt, ctx, b">0\nACGTA\n", 5, "fasta")
 
 
