@@ -6,7 +6,12 @@
 // (dist, node id); the kernel therefore produces, per source, the targets of each level sorted
 // by node id, level after level, until `cap` records exist.
 //
-// Tier 1 -- one warp per source, persistent CTAs pulling work from an atomic counter:
+// Tier 0 -- one THREAD per source (dijkstra_thread_kernel): almost every search labels a few dozen
+//   nodes, so each lane runs its own search over a 48-entry lane-interleaved slice of shared memory
+//   (extract-min = scan for the smallest (dist, node), relaxation = linear search); a warp then
+//   carries 32 independent gather chains instead of one.
+// Tier 1 -- one warp per source for the searches that outgrow tier 0, persistent CTAs pulling
+//   work from an atomic counter:
 //   * distance labels live in a per-warp open-addressing table in shared memory
 //     (key = node id, value = tentative distance, atomicMin relaxations);
 //   * the frontier is the insertion-ordered slot list of that table; a 64-bit mask of
