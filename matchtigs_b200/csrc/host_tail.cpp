@@ -309,16 +309,24 @@ void walk_and_break(const WalkInput& in, TailOutput& out, TailScratch& scratch) 
     };
     HVec<QEntry> queue;
     queue.bind(scratch.queue, E / 2 + 16, 0, false);
+    bool more = false;  // set by first_unused: does the row hold further entries behind the returned one?
     auto first_unused = [&](u32 v) -> const AdjEntry* {
         NodeRow& r = rows[v];
         if (!(r.end & ROW_EXT)) {
             while (r.cur < r.end && is_used(r.inl[r.cur].edge)) r.cur++;
+            more = r.cur + 1 < r.end;
             return r.cur < r.end ? &r.inl[r.cur] : nullptr;
         }
         const u32 end = r.end & ~ROW_EXT;
         while (r.cur < end && is_used(ext[r.cur].edge)) r.cur++;
+        more = r.cur + 1 < end;
         return r.cur < end ? &ext[r.cur] : nullptr;
     };
+    // Positions whose from-node may still own an unused out-edge, in cycle order from the head.  A position is only
+    // recorded if its row had entries left when the walk passed (exhaustion is permanent), which skips about half of
+    // the re-root probes -- each one a cache miss.
+    HVec<u32> cand;
+    cand.bind(scratch.cand, E / 2 + 16, 0, false);
     HVec<u32> cyc;
     cyc.bind(scratch.cyc, E / 2 + 16, 0, false);
     std::vector<std::pair<u32, u32>> stack;  // (next index, block end)
@@ -336,8 +344,9 @@ void walk_and_break(const WalkInput& in, TailOutput& out, TailScratch& scratch) 
     for (u64 e0 = 0; e0 < E; e0++) {
         if (is_used((u32)e0)) continue;
         // one closed walk per component, started at the lowest unused edge id
-        size_t qf = 0;
+        size_t cf = 0;
         queue.clear();
+        cand.clear();
         // every node owns an original edge, so the lowest unused edge of a component is never a dummy
         MTG_REQUIRE(e0 < E0, MTG_ERR_INTERNAL, "closed walk would start at a dummy edge");
         u32 start_edge = (u32)e0, start_from = in.from[e0], start_to = in.to[e0];
@@ -346,11 +355,13 @@ void walk_and_break(const WalkInput& in, TailOutput& out, TailScratch& scratch) 
         bool rooted = false;
         for (;;) {
             mark_pair(start_edge);
+            cand.push_back((u32)queue.size());  // a walk start is always probed again
             queue.push_back({start_edge, start_from, 0, 0});
             u32 cur_node = start_to;
             for (const AdjEntry* a; (a = first_unused(cur_node)) != nullptr;) {
                 __builtin_prefetch(&rows[a->to]);
                 mark_pair(a->edge);
+                if (more) cand.push_back((u32)queue.size());
                 queue.push_back({a->edge, cur_node, 0, 0});
                 cur_node = a->to;
             }
@@ -358,8 +369,9 @@ void walk_and_break(const WalkInput& in, TailOutput& out, TailScratch& scratch) 
             else n0 = queue.size();
             // re-root at the first cycle position (from the head) whose from-node still has an unused out-edge
             bool found = false;
-            while (qf < queue.size()) {
-                if (qf + 12 < queue.size()) __builtin_prefetch(&rows[queue[qf + 12].from]);  // independent misses: overlap them
+            while (cf < cand.size()) {
+                if (cf + 12 < cand.size()) __builtin_prefetch(&rows[queue[cand[cf + 12]].from]);  // independent misses: overlap them
+                const u32 qf = cand[cf];
                 const AdjEntry* a = first_unused(queue[qf].from);
                 if (a) {
                     head_idx = qf;  // rotate_left(position)
@@ -371,7 +383,7 @@ void walk_and_break(const WalkInput& in, TailOutput& out, TailScratch& scratch) 
                     found = true;
                     break;
                 }
-                qf++;  // exhausted for good
+                cf++;  // exhausted for good
             }
             if (!found) break;
         }

@@ -127,7 +127,7 @@ struct HugeBuf {
     ~HugeBuf() { release(); }
 };
 struct TailScratch {
-    HugeBuf out_deg, in_deg, diff, rows, ext, used, queue, cyc;
+    HugeBuf out_deg, in_deg, diff, rows, ext, used, queue, cand, cyc;
 };
 // Nodes still unbalanced after the matching, ascending node id (device compaction, tail_prep.cu).
 // partner = position of the node's mirror in the opposite list.
