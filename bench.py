@@ -258,6 +258,9 @@ def run_ours(args):
         # duration: CUDA events around the tier-0 search kernel on the library's stream, averaged over the timed steps
         djk_ms = stats["dijkstra_kernel_ms"]
         achieved = alg_bytes / world / (djk_ms * 1e-3) / 1e9 if djk_ms > 0 else 0.0
+        # dram__bytes_read.sum + dram__bytes_write.sum of the kernel's main launch from the committed `ncu --set full`
+        # captures (profiles/round1_ncu_full_dijkstra_thread_main_*.txt); only known for the captured workloads at N=1
+        traffic = NCU_DRAM_BYTES.get((args.workload, float(info["scale"]))) if world == 1 else None
         # cpu baseline: the oracle at 1 thread (deterministic reference semantics), whole workload, once
         import oracle
         o = oracle.Oracle(euler_fast=True)
@@ -285,7 +288,7 @@ def run_ours(args):
                          "match_kernel_ms_per_step": stats["match_kernel_ms"], "match_blocked_retries": stats["match_rounds"],
                          "requery_phases": stats["requery_phases"], "overflow_sources": stats["overflow_sources"]},
             "roofline": {"kernel": "dijkstra_thread_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes / world,
                          "note": "random 32-B-sector gathers along dependent chains; the CSR of this workload fits in L2, so the "
                                  "kernel is bound by L2 latency x chain depth, not by HBM bandwidth (see DESIGN.md section 4)"},
@@ -299,6 +302,10 @@ def run_ours(args):
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+# (workload, scale) -> DRAM bytes (read + write) of one main launch of dijkstra_thread_kernel, from ncu --set full
+NCU_DRAM_BYTES = {("ecoli", 1.0): 210432 + 0, ("chr1", 0.3): 19860992 + 9339648}
 
 
 def main():

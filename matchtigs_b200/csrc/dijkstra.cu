@@ -20,9 +20,13 @@
 //     probe + the (col, weight) row per settled node are the only global loads.
 // Tier 2 -- searches that outgrow the shared-memory table (or a level with > 64 targets)
 //   rerun with one CTA per source against dense global-memory labels.
+#include <cooperative_groups.h>
+
 #include <algorithm>
 
 #include "mtg_internal.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace mtg {
 
@@ -116,12 +120,16 @@ __global__ void __launch_bounds__(T0_THREADS) dijkstra_thread_kernel(SearchArgs 
     const unsigned tid = threadIdx.x, lane = tid & 31;
     unsigned long long st_settled = 0, st_relaxed = 0, st_cand = 0, st_searched = 0, st_trunc = 0, st_ovf = 0;
     for (;;) {
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(a.work_counter, 32ull);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= a.n_items) break;
-        const u64 q = base + lane;
-        if (q >= a.n_items) continue;
+        // Every lane fetches its next source as soon as it is done (no waiting for the slowest search of a batch);
+        // the lanes that arrive together share one atomic.
+        u64 q;
+        {
+            cg::coalesced_group g = cg::coalesced_threads();
+            unsigned long long base = 0;
+            if (g.thread_rank() == 0) base = atomicAdd(a.work_counter, (unsigned long long)g.size());
+            q = g.shfl(base, 0) + g.thread_rank();
+        }
+        if (q >= a.n_items) break;
         const u64 t = a.todo ? (u64)a.todo[q] : q;
         const u64 gi = a.work_list ? (u64)a.work_list[t] : t * a.shard_count + a.shard_rank;
         const u32 src = a.sources[gi];
