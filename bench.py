@@ -261,6 +261,8 @@ def run_ours(args):
         # dram__bytes_read.sum + dram__bytes_write.sum of the kernel's main launch from the committed `ncu --set full`
         # captures (profiles/round1_ncu_full_dijkstra_thread_main_*.txt); only known for the captured workloads at N=1
         traffic = NCU_DRAM_BYTES.get((args.workload, float(info["scale"]))) if world == 1 else None
+        sectors = NCU_L2_READ_SECTORS.get((args.workload, float(info["scale"]))) if world == 1 else None
+        sector_gbps = sectors * 32 / (djk_ms * 1e-3) / 1e9 if sectors and djk_ms > 0 else None
         # cpu baseline: the oracle at 1 thread (deterministic reference semantics), whole workload, once
         import oracle
         o = oracle.Oracle(euler_fast=True)
@@ -290,6 +292,12 @@ def run_ours(args):
             "roofline": {"kernel": "dijkstra_thread_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes / world,
+                         "sector_granular": {"l2_read_sectors_per_launch": sectors, "achieved_GBps": sector_gbps,
+                                             "ceilings_GBps": GATHER_CEILING_GBPS,
+                                             "frac_of_l2_resident_ceiling": sector_gbps / GATHER_CEILING_GBPS["l2_resident"]
+                                             if sector_gbps else None,
+                                             "source": "ncu lts__t_sectors_srcunit_tex_op_read.sum of the committed capture x 32 B over "
+                                                       "the live kernel time; ceilings from scripts/micro/gather_ceiling.cu"},
                          "note": "random 32-B-sector gathers along dependent chains; the CSR of this workload fits in L2, so the "
                                  "kernel is bound by L2 latency x chain depth, not by HBM bandwidth (see DESIGN.md section 4)"},
             "cpu_baseline": {"value": U / cpu_s, "unit": "unitigs/s", "cores": 1, "kind": "port",
@@ -306,6 +314,11 @@ def run_ours(args):
 
 # (workload, scale) -> DRAM bytes (read + write) of one main launch of dijkstra_thread_kernel, from ncu --set full
 NCU_DRAM_BYTES = {("ecoli", 1.0): 210432 + 0, ("chr1", 0.3): 19860992 + 9339648}
+# same captures: L2 sectors the kernel read (lts__t_sectors_srcunit_tex_op_read.sum), i.e. the sector-granular traffic
+NCU_L2_READ_SECTORS = {("ecoli", 1.0): 144584, ("chr1", 0.3): 32715339}
+# random 32-byte-sector gather ceilings measured on a B200 of this pool with scripts/micro/gather_ceiling.cu
+# (profiles/round1_gather_ceiling.jsonl): footprint 8 GiB (HBM) and 32 MiB (L2-resident), independent gathers
+GATHER_CEILING_GBPS = {"hbm_random": 1174.8, "l2_resident": 6663.9}
 
 
 def main():

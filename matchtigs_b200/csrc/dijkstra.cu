@@ -119,33 +119,39 @@ __global__ void __launch_bounds__(T0_THREADS) dijkstra_thread_kernel(SearchArgs 
     __shared__ u8 s_dist[T0_ENTRIES][T0_THREADS];
     const unsigned tid = threadIdx.x, lane = tid & 31;
     unsigned long long st_settled = 0, st_relaxed = 0, st_cand = 0, st_searched = 0, st_trunc = 0, st_ovf = 0;
+    // One flat loop: every iteration a lane either fetches its next source or settles ONE node of its current search.
+    // Lanes whose search ends refill on the next iteration instead of idling until the largest search of the warp
+    // is done (a nested search loop would reconverge only after all 32 searches).
+    bool active = false;
+    u64 t = 0;
+    u32 src = 0, n = 0, open = 0, emitted = 0, settled = 0, relaxed = 0;
     for (;;) {
-        // Every lane fetches its next source as soon as it is done (no waiting for the slowest search of a batch);
-        // the lanes that arrive together share one atomic.
-        u64 q;
-        {
-            cg::coalesced_group g = cg::coalesced_threads();
-            unsigned long long base = 0;
-            if (g.thread_rank() == 0) base = atomicAdd(a.work_counter, (unsigned long long)g.size());
-            q = g.shfl(base, 0) + g.thread_rank();
+        if (!active) {
+            u64 q;
+            {
+                cg::coalesced_group g = cg::coalesced_threads();  // the lanes that refill together share one atomic
+                unsigned long long base = 0;
+                if (g.thread_rank() == 0) base = atomicAdd(a.work_counter, (unsigned long long)g.size());
+                q = g.shfl(base, 0) + g.thread_rank();
+            }
+            if (q >= a.n_items) break;
+            t = a.todo ? (u64)a.todo[q] : q;
+            const u64 gi = a.work_list ? (u64)a.work_list[t] : t * a.shard_count + a.shard_rank;
+            src = a.sources[gi];
+            if (a.row_s[src] == a.row_s[src + 1]) {  // no traversable out-edge: the search settles the source only
+                a.meta[t] = 0;
+                st_settled++;
+            } else {
+                st_searched++;
+                n = 1;
+                open = 1;  // labelled, not yet settled
+                emitted = settled = relaxed = 0;
+                s_key[0][tid] = src;
+                s_dist[0][tid] = 0;
+                active = true;
+            }
         }
-        if (q >= a.n_items) break;
-        const u64 t = a.todo ? (u64)a.todo[q] : q;
-        const u64 gi = a.work_list ? (u64)a.work_list[t] : t * a.shard_count + a.shard_rank;
-        const u32 src = a.sources[gi];
-        if (a.row_s[src] == a.row_s[src + 1]) {  // no traversable out-edge: the search settles the source only
-            a.meta[t] = 0;
-            st_settled++;
-            continue;
-        }
-        st_searched++;
-        u32 n = 1, emitted = 0;
-        bool truncated = false, overflow = false;
-        unsigned long long settled = 0, relaxed = 0;
-        s_key[0][tid] = src;
-        s_dist[0][tid] = 0;
-        u64* out = a.records + t * a.cap;
-        for (;;) {
+        if (active) {
             // extract-min over the unsettled labels: total order (dist, node id)
             unsigned long long best = ~0ull;
             u32 bi = 0;
@@ -158,11 +164,12 @@ __global__ void __launch_bounds__(T0_THREADS) dijkstra_thread_kernel(SearchArgs 
                     bi = i;
                 }
             }
-            if (best == ~0ull) break;
             const u32 d = (u32)(best >> 32), v = (u32)best;
             s_dist[bi][tid] = (u8)(d | T0_SETTLED);
             settled++;
-            if (v != src && ((a.bitmap[v >> 5] >> (v & 31)) & 1u)) out[emitted++] = (u64)v | ((u64)d << 32);
+            open--;
+            if (v != src && ((a.bitmap[v >> 5] >> (v & 31)) & 1u)) a.records[t * a.cap + emitted++] = (u64)v | ((u64)d << 32);
+            bool overflow = false;
             const u32 e0 = a.row_s[v], e1 = a.row_s[v + 1];
             for (u32 e = e0; e < e1; e++) {
                 const u32 nw = d + a.w_s[e];
@@ -178,29 +185,28 @@ __global__ void __launch_bounds__(T0_THREADS) dijkstra_thread_kernel(SearchArgs 
                     s_key[n][tid] = u;
                     s_dist[n][tid] = (u8)nw;
                     n++;
+                    open++;
                 } else {
                     overflow = true;
                     break;
                 }
             }
-            if (overflow) break;
-            if (emitted == a.cap) {
-                // the list is full; it is complete only if nothing is left to settle (checked after v's own relaxation,
-                // because the last target may be the only way to further ones)
-                for (u32 i = 0; i < n; i++) truncated |= !(s_dist[i][tid] & T0_SETTLED);
-                break;
+            if (overflow) {
+                a.meta[t] = META_OVERFLOW;
+                a.overflow_list[atomicAdd(a.overflow_count, 1u)] = (u32)t;
+                st_ovf++;
+                active = false;
+            } else if (open == 0 || emitted == a.cap) {
+                // a full list is complete only if nothing is left to settle (checked after v's own relaxation, because
+                // the last target may be the only way to further ones)
+                const bool truncated = open != 0;
+                a.meta[t] = emitted | (truncated ? META_TRUNC : 0u);
+                st_settled += settled;
+                st_relaxed += relaxed;
+                st_cand += emitted;
+                st_trunc += truncated;
+                active = false;
             }
-        }
-        if (overflow) {
-            a.meta[t] = META_OVERFLOW;
-            a.overflow_list[atomicAdd(a.overflow_count, 1u)] = (u32)t;
-            st_ovf++;
-        } else {
-            a.meta[t] = emitted | (truncated ? META_TRUNC : 0u);
-            st_settled += settled;
-            st_relaxed += relaxed;
-            st_cand += emitted;
-            st_trunc += truncated;
         }
     }
     for (int o = 16; o > 0; o >>= 1) {
