@@ -6,9 +6,11 @@ the import of the library / creation of a context raises.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
-SO_PATH = Path(__file__).resolve().parent / "libmatchtigs_b200.so"
+# MTG_LIB_PATH: diagnostic override used to A/B differently compiled builds of the same library
+SO_PATH = Path(os.environ.get("MTG_LIB_PATH") or Path(__file__).resolve().parent / "libmatchtigs_b200.so")
 
 MTG_OK = 0
 STATUS_NAMES = {0: "MTG_OK", -1: "MTG_ERR_INVALID", -2: "MTG_ERR_CUDA", -3: "MTG_ERR_INPUT", -4: "MTG_ERR_INTERNAL",

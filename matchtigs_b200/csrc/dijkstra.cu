@@ -111,7 +111,10 @@ __device__ __forceinline__ u64 warp_or64(u64 v) {
 // and relaxation is a linear search of the few labelled nodes.  32 independent load chains per warp hide the
 // L2 latency that a single chain cannot.  Searches that outgrow T0_ENTRIES labels go to the warp tier.
 constexpr int T0_THREADS = 128;
-constexpr int T0_ENTRIES = 48;
+#ifndef MTG_T0_ENTRIES
+#define MTG_T0_ENTRIES 48
+#endif
+constexpr int T0_ENTRIES = MTG_T0_ENTRIES;
 constexpr u32 T0_SETTLED = 0x80u;
 
 __global__ void __launch_bounds__(T0_THREADS) dijkstra_thread_kernel(SearchArgs a) {

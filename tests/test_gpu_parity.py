@@ -115,6 +115,32 @@ def test_arbitrary_fasta_all_k(mt, ctx, k):
         compare_all(mt, ctx, text, k, "fasta", check_props=(k <= 11))
 
 
+@pytest.mark.parametrize("block", range(4))
+def test_fuzz_tiny_genomes_both_readers(mt, ctx, block):
+    """Many tiny, repeat-rich genomes compacted at small odd k (the unitig builder needs odd k; palindromic (k-1)-mers,
+    hairpins and self-loops are frequent at this size), through both reader semantics, every stage compared."""
+    for i in range(12):
+        rng = random.Random(90_000 + 100 * block + i)
+        k = 2 * rng.randint(1, 8) + 1
+        g = tools.genome(rng.randint(40, 2500), rng.randint(1, 10**6), families=rng.randint(0, 4), copies=rng.randint(2, 6),
+                         min_len=k, max_len=rng.randint(k + 1, 120), divergence=rng.choice([0.0, 0.02, 0.1]),
+                         tandem_arrays=rng.randint(0, 3))
+        text, _, _ = tools.unitigs(g, k)
+        cap = rng.choice([1, 2, 4, 8, 16])
+        for mode in ("fasta", "bcalm"):
+            compare_all(mt, ctx, text, k, mode, cap=cap, dbg_valid=True, check_props=True)
+
+
+@pytest.mark.parametrize("block", range(4))
+def test_fuzz_dense_arbitrary_fasta(mt, ctx, block):
+    """Arbitrary FASTA with record ends drawn from a tiny pool: parallel edges, self-mirrors and long candidate lists."""
+    for i in range(12):
+        rng = random.Random(95_000 + 100 * block + i)
+        k = rng.randint(3, 13)
+        text = random_fasta(rng, rng.randint(1, 600), k, max_extra=rng.choice([0, 2, 8, 30]), pool=rng.choice([2, 3, 5, 9, 40]))
+        compare_all(mt, ctx, text, k, "fasta", cap=rng.choice([1, 3, 16]))
+
+
 @pytest.mark.parametrize("cap", [1, 2, 3, 8, 64])
 def test_cap_independence(mt, ctx, cap):
     # dense graphs with many short edges: small caps force re-query phases, results must not change
