@@ -285,6 +285,8 @@ void run_tail(const TailInput& in, TailOutput& out, TailScratch& scratch) {
             r.cur = 0;
         }
     }
+#pragma omp parallel for schedule(static) if (par)
+    for (i64 v = 0; v < (i64)n; v++) fill_row_hints(rowp, extp, (u32)v);
     double t3 = now_ms();
     out.ms_degrees = t1 - t0;
     out.ms_eulerise = t2 - t1;
@@ -314,19 +316,23 @@ void walk_and_break(const WalkInput& in, TailOutput& out, TailScratch& scratch) 
     };
     HVec<QEntry> queue;
     queue.bind(scratch.queue, E / 2 + 16, 0, false);
-    bool more = false;  // set by first_unused: does the row hold further entries behind the returned one?
+    bool more = false;          // set by first_unused: does the row hold further entries behind the returned one?
+    const u32* hint = nullptr;  // set by first_unused: prefetch hints of the returned entry (inline rows only)
     auto first_unused = [&](u32 v) -> const AdjEntry* {
         NodeRow& r = rows[v];
         if (!(r.end & ROW_EXT)) {
             while (r.cur < r.end && is_used(r.inl[r.cur].edge)) r.cur++;
             more = r.cur + 1 < r.end;
+            hint = r.hint[r.cur < r.end ? r.cur : 0];
             return r.cur < r.end ? &r.inl[r.cur] : nullptr;
         }
         const u32 end = r.end & ~ROW_EXT;
         while (r.cur < end && is_used(ext[r.cur].edge)) r.cur++;
         more = r.cur + 1 < end;
+        hint = nullptr;
         return r.cur < end ? &ext[r.cur] : nullptr;
     };
+    const bool use_hints = !getenv("MTG_TAIL_NOHINT");
     // Positions whose from-node may still own an unused out-edge, in cycle order from the head.  A position is only
     // recorded if its row had entries left when the walk passed (exhaustion is permanent), which skips about half of
     // the re-root probes -- each one a cache miss.
@@ -365,6 +371,10 @@ void walk_and_break(const WalkInput& in, TailOutput& out, TailScratch& scratch) 
             u32 cur_node = start_to;
             for (const AdjEntry* a; (a = first_unused(cur_node)) != nullptr;) {
                 __builtin_prefetch(&rows[a->to]);
+                if (hint && use_hints) {  // two steps ahead: the likely successors of a->to
+                    __builtin_prefetch(&rows[hint[0]]);
+                    __builtin_prefetch(&rows[hint[1]]);
+                }
                 mark_pair(a->edge);
                 if (more) cand.push_back((u32)queue.size());
                 queue.push_back({a->edge, cur_node, 0, 0});

@@ -104,14 +104,42 @@ struct PinnedBuf {
 struct AdjEntry {
     u32 edge, to;
 };
-// One 32-byte record per node: row cursor + up to three out-edges inline (newest edge first), so that stepping
-// through a node touches a single cache line.  Rows with more than three edges live in `ext`.
+// One cache line per node: row cursor + up to three out-edges inline (newest edge first), so that stepping
+// through a node touches a single line.  Rows with more than three edges live in `ext`.
+// hint[i] = targets of the first two out-edges of node inl[i].to: the walk is one dependent cache miss per step, and
+// the hints let it prefetch the line it will most likely need two steps ahead while the next one is still in flight.
 constexpr u32 ROW_INLINE = 3;
 constexpr u32 ROW_EXT = 0x80000000u;
-struct alignas(32) NodeRow {
+struct alignas(64) NodeRow {
     u32 cur, end;  // next position to inspect / end of the row (ROW_EXT flag: positions refer to `ext`)
     AdjEntry inl[ROW_INLINE];
+    u32 hint[ROW_INLINE][2];
+    u32 pad[2];
 };
+static_assert(sizeof(NodeRow) == 64, "one cache line per node");
+
+// Fills the prefetch hints of row v (rows and cursors must be final).  Shared by the device and the host row builders.
+__host__ __device__ inline void fill_row_hints(NodeRow* rows, const AdjEntry* ext, u32 v) {
+    NodeRow& r = rows[v];
+    const u32 n = (r.end & ROW_EXT) ? 0u : r.end;
+    for (u32 i = 0; i < ROW_INLINE; i++) {
+        u32 h0 = v, h1 = v;
+        if (i < n) {
+            const u32 w = r.inl[i].to;
+            const NodeRow& t = rows[w];
+            h0 = h1 = w;
+            if (t.end & ROW_EXT) {  // more than ROW_INLINE entries
+                h0 = ext[t.cur].to;
+                h1 = ext[t.cur + 1].to;
+            } else if (t.end) {
+                h0 = t.inl[0].to;
+                h1 = t.end > 1 ? t.inl[1].to : h0;
+            }
+        }
+        r.hint[i][0] = h0;
+        r.hint[i][1] = h1;
+    }
+}
 
 // Host arena backed by an anonymous mapping with MADV_HUGEPAGE (host_tail.cpp); grow-only, cached across calls.
 struct HugeBuf {

@@ -128,6 +128,13 @@ __global__ void __launch_bounds__(TB) row_headers(const u32* __restrict__ deg, c
     }
 }
 
+// rows and cursors are final: prefetch hints for the host walk (two random gathers per entry, cheap here, a cache miss
+// each on the host)
+__global__ void __launch_bounds__(TB) row_hints(NodeRow* rows, const AdjEntry* __restrict__ ext, u64 N) {
+    u64 v = (u64)blockIdx.x * TB + threadIdx.x;
+    if (v < N) fill_row_hints(rows, ext, (u32)v);
+}
+
 int bits_for(u64 n) {
     int b = 1;
     while (b < 32 && (1ull << b) < n) b++;
@@ -226,6 +233,7 @@ void tail_build_rows(mtg_ctx* ctx, const u32* breaking_pairs, u64 n_break, NodeR
     if (E) MTG_LAUNCH(ctx, fill_rows, grid_for(E, TB), TB, 0, which ? key_b.p : key_a.p, which ? val_b.p : val_a.p, E, E0, ctx->edge_to.p,
                       pair_out.p, pair_in.p, ctx->mirror.p, deg.p, row_ptr.p, ext_off.p, rows.p, ext.p);
     MTG_LAUNCH(ctx, row_headers, grid_for(N, TB), TB, 0, deg.p, ext_off.p, N, rows.p);
+    MTG_LAUNCH(ctx, row_hints, grid_for(N, TB), TB, 0, rows.p, ext.p, N);
     MTG_CUDA(cudaMemcpyAsync(h_rows, rows.p, N * sizeof(NodeRow), cudaMemcpyDeviceToHost, s));
     AdjEntry* h_ext = ext_stage.as<AdjEntry>(std::max<u64>(n_ext, 1));
     if (n_ext) MTG_CUDA(cudaMemcpyAsync(h_ext, ext.p, n_ext * sizeof(AdjEntry), cudaMemcpyDeviceToHost, s));
