@@ -179,6 +179,22 @@ def run_ours(args):
     ext = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
+    def link_gbps(to_device: bool) -> float:
+        """Pinned-memory copy bandwidth of this box's host link (context for the e2e number; boxes differ a lot)."""
+        h = torch.empty(128 << 20, dtype=torch.uint8).pin_memory()
+        d = flush[: h.numel()]
+        best = 0.0
+        for _ in range(3):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            (d.copy_(h, non_blocking=True) if to_device else h.copy_(d, non_blocking=True))
+            b.record()
+            b.synchronize()
+            best = max(best, h.numel() / (a.elapsed_time(b) * 1e-3) / 1e9)
+        return best
+
+    link = {"h2d_GBps": link_gbps(True), "d2h_GBps": link_gbps(False)} if rank == 0 else None
+
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
@@ -210,6 +226,7 @@ def run_ours(args):
             step(resident)
         barrier()
         total_ms, dj_ms, mt_ms, djk_ms, mtk_ms, stats, out = 0.0, 0.0, 0.0, 0.0, 0.0, None, None
+        per_step = []
         launches0 = ctx.kernel_launches
         for _ in range(steps):
             with torch.cuda.stream(ext):
@@ -220,7 +237,8 @@ def run_ours(args):
             out = step(resident)
             e1.record(ext)
             barrier()
-            total_ms += e0.elapsed_time(e1)
+            per_step.append(e0.elapsed_time(e1))
+            total_ms += per_step[-1]
             stats = ctx.search_stats()
             dj_ms += stats["dijkstra_ms"]
             mt_ms += stats["match_ms"]
@@ -231,14 +249,16 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms, dj_ms, mt_ms, djk_ms, mtk_ms = (float(x) for x in t.cpu())
-        stats = dict(stats, dijkstra_kernel_ms=djk_ms / steps, match_kernel_ms=mtk_ms / steps)
+        per_step.sort()
+        stats = dict(stats, dijkstra_kernel_ms=djk_ms / steps, match_kernel_ms=mtk_ms / steps,
+                     spread={"min": per_step[0], "median": per_step[len(per_step) // 2], "max": per_step[-1]})
         return total_ms / steps, dj_ms / steps, mt_ms / steps, stats, launches, out
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     ms_res, dj_ms, match_ms, stats, launches, _ = timed(True, args.steps, args.warmup)
-    ms_e2e, _, _, _, _, out = timed(False, args.steps, max(1, args.warmup // 2))
+    ms_e2e, _, _, stats_e2e, _, out = timed(False, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
 
     # settled / relaxed / candidates summed over ranks for the roofline numerator
@@ -280,8 +300,10 @@ def run_ours(args):
                        "distinct_kmers": info["distinct_kmers"], "input_bp": info["input_bp"], "candidate_cap": CAP,
                        "l2": "flushed between timed iterations (256 MiB memset)", "reader": "fa-in semantics (k-mer join)",
                        "parallelism": f"sources sharded over {world} GPU(s), graph replicated"},
-            "e2e": {"value": U / (ms_e2e * 1e-3), "unit": "unitigs/s", "ms_per_step": ms_e2e,
+            "ms_per_step_spread_rank0": stats["spread"],
+            "e2e": {"value": U / (ms_e2e * 1e-3), "unit": "unitigs/s", "ms_per_step": ms_e2e, "ms_per_step_spread_rank0": stats_e2e["spread"],
                     "h2d_bytes_per_step": int(text_host.numel()), "input": "unitig FASTA text (parsed on the device)",
+                    "host_link": link,
                     "d2h_bytes_per_step": int(len(gfa) + len(bv))},
             "gpu_launches": int(launches),
             "settled_nodes_per_sec": settled / (dj_ms * 1e-3) if dj_ms > 0 else None,

@@ -597,10 +597,16 @@ void finish_walks(mtg_ctx* ctx) {
     NodeRow* rows = static_cast<NodeRow*>(scratch.rows.ensure(std::max<u64>(N, 1) * sizeof(NodeRow)));
     AdjEntry* ext = static_cast<AdjEntry*>(scratch.ext.ensure(std::max<u64>(n_ext, 1) * sizeof(AdjEntry)));
     // copied in cache-sized chunks: one big memcpy would use non-temporal stores and leave the rows cold in
-    // DRAM, while the walk is a latency chain that runs ~1.5x faster when the last-level cache holds them
+    // DRAM, while the walk is a latency chain that runs ~1.5x faster when the last-level cache holds them.
+    // Rows that exceed any last-level cache anyway are copied by a few threads instead.
     auto warm_copy = [](void* dst, const void* src, size_t bytes) {
         const size_t chunk = 256 << 10;
-        for (size_t o = 0; o < bytes; o += chunk) memcpy((char*)dst + o, (const char*)src + o, std::min(chunk, bytes - o));
+        const i64 n_chunks = (i64)((bytes + chunk - 1) / chunk);
+#pragma omp parallel for schedule(static) num_threads(4) if (bytes > (96u << 20))
+        for (i64 c = 0; c < n_chunks; c++) {
+            const size_t o = (size_t)c * chunk;
+            memcpy((char*)dst + o, (const char*)src + o, std::min(chunk, bytes - o));
+        }
     };
     warm_copy(rows, rows_stage, N * sizeof(NodeRow));
     warm_copy(ext, ctx->tail_stage[3].p, n_ext * sizeof(AdjEntry));
