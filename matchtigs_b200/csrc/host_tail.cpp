@@ -345,11 +345,6 @@ void walk_and_break(const WalkInput& in, TailOutput& out, TailScratch& scratch) 
     out.walk_limits.clear();
     out.walk_edges.reserve(E / 2);
     double ms_break = 0;
-    auto emit = [&](const u32* b, const u32* e) {
-        MTG_REQUIRE(*b < E0, MTG_ERR_INTERNAL, "walk starts with a dummy edge");
-        out.walk_edges.insert(out.walk_edges.end(), b, e);
-        out.walk_limits.push_back(out.walk_edges.size());
-    };
     auto is_dummy = [&](u32 e) { return e >= E0; };
     auto dummy_weight = [&](u32 e) { return in.dummy_w[e - E0]; };
     for (u64 e0 = 0; e0 < E; e0++) {
@@ -404,21 +399,36 @@ void walk_and_break(const WalkInput& in, TailOutput& out, TailScratch& scratch) 
         }
         double tb = now_ms();
         const size_t len = queue.size();
-        // in-order expansion; the root block is the initial closed walk [0, n0)
+        // in-order expansion; the root block is the initial closed walk [0, n0).  The reference's cycle vector is `cyc`
+        // rotated left by head_pos; its heaviest dummy (the first one on ties, greedytigs/mod.rs:736-748) is found on the
+        // way: best_pre / best_post are the first heaviest dummies before / from head_pos on.
         cyc.clear();
         stack.clear();
         stack.push_back({0u, (u32)n0});
-        size_t head_pos = 0;
+        size_t head_pos = 0, pre_pos = 0, post_pos = 0;
+        u32 pre_w = 0, post_w = 0;
+        bool head_seen = false;
+        auto place = [&](u32 i) {
+            const u32 x = queue[i].edge;
+            if (i == head_idx) {
+                head_pos = cyc.size();
+                head_seen = true;
+            }
+            if (is_dummy(x)) {
+                const u32 w = dummy_weight(x);
+                if (head_seen) {
+                    if (w > post_w) post_w = w, post_pos = cyc.size();
+                } else if (w > pre_w) {
+                    pre_w = w, pre_pos = cyc.size();
+                }
+            }
+            cyc.push_back(x);
+        };
         while (!stack.empty()) {
             auto& fr = stack.back();
             if (fr.first == fr.second) {
                 stack.pop_back();
-                if (!stack.empty()) {  // the block of element (first) is done: emit the element itself
-                    auto& up = stack.back();
-                    const u32 i = up.first++;
-                    if (i == head_idx) head_pos = cyc.size();
-                    cyc.push_back(queue[i].edge);
-                }
+                if (!stack.empty()) place(stack.back().first++);  // the block of this element is done: the element itself
                 continue;
             }
             const u32 i = fr.first;
@@ -427,41 +437,40 @@ void walk_and_break(const WalkInput& in, TailOutput& out, TailScratch& scratch) 
                 stack.push_back({q.child_begin, q.child_end});
             } else {
                 fr.first++;
-                if (i == head_idx) head_pos = cyc.size();
-                cyc.push_back(q.edge);
+                place(i);
             }
         }
         MTG_REQUIRE(cyc.size() == len, MTG_ERR_INTERNAL, "cycle expansion lost elements");
-        // G. greedytigs/mod.rs:736-788
-        // the reference's cycle vector is `cyc` rotated left by head_pos; the heaviest-dummy rotation is applied on top
-        u32 longest_w = 0;
-        size_t longest_i = 0;
-        for (size_t i = 0; i < len; i++) {
-            size_t j = head_pos + i;
-            if (j >= len) j -= len;
-            const u32 x = cyc[j];
-            if (is_dummy(x) && dummy_weight(x) > longest_w) {  // strict: the first heaviest dummy wins
-                longest_w = dummy_weight(x);
-                longest_i = i;
-            }
-        }
-        size_t rot = head_pos + (longest_w > 0 ? longest_i : 0);
-        if (rot >= len) rot -= len;
-        if (rot) std::rotate(cyc.begin(), cyc.begin() + rot, cyc.end());
-        size_t offset = 0;
+        // G. greedytigs/mod.rs:736-788: start at the heaviest dummy (rotated order = [head_pos, len) then [0, head_pos)),
+        // cut at every dummy of weight >= k and at a dummy in position 0; the rotation is never materialised
+        const size_t rot = (post_w | pre_w) == 0 ? head_pos : (post_w >= pre_w ? post_pos : pre_pos);
+        std::vector<u32>& we = out.walk_edges;
+        size_t piece = we.size();  // start of the piece being collected
+        auto close = [&] {
+            if (we.size() == piece) return;
+            MTG_REQUIRE(we[piece] < E0, MTG_ERR_INTERNAL, "walk starts with a dummy edge");
+            out.walk_limits.push_back(we.size());
+            piece = we.size();
+        };
+        bool first = true;
         const u32* p = cyc.data();
-        for (size_t i = 0; i < len; i++) {
-            const u32 x = cyc[i];
-            if (is_dummy(x) && (dummy_weight(x) >= in.k || i == 0)) {
-                if (offset < i) emit(p + offset, p + i);
-                offset = i + 1;
-                out.breaking++;
+        for (int seg = 0; seg < 2; seg++) {
+            const size_t jb = seg ? 0 : rot, je = seg ? rot : len;
+            size_t run = jb;  // pieces are copied run by run (a piece may continue across the wrap-around)
+            for (size_t j = jb; j < je; j++) {
+                const u32 x = p[j];
+                if (is_dummy(x) && (first || dummy_weight(x) >= in.k)) {
+                    we.insert(we.end(), p + run, p + j);
+                    close();
+                    out.breaking++;
+                    run = j + 1;
+                }
+                first = false;
             }
+            we.insert(we.end(), p + run, p + je);
         }
-        if (offset < len) {
-            if (!is_dummy(cyc[len - 1])) emit(p + offset, p + len);
-            else if (offset < len - 1) emit(p + offset, p + len - 1);
-        }
+        if (we.size() > piece && is_dummy(we.back())) we.pop_back();  // a trailing (light) dummy is dropped
+        close();
         out.cycles++;
         ms_break += now_ms() - tb;
     }
