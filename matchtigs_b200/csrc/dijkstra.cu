@@ -537,7 +537,10 @@ void run_searches(mtg_ctx* ctx, const u32* bitmap, const u32* work_list, u64 n_w
     MTG_CUDA(cudaEventRecord(ctx->ev3, s));
     u32 h_counts[2] = {0, 0};
     MTG_CUDA(cudaMemcpyAsync(h_counts, counts, sizeof(u32), cudaMemcpyDeviceToHost, s));
+    // the counters ride along: if no search left tier 0 (the common case) they are final and nobody has to ask again
+    MTG_CUDA(cudaMemcpyAsync(&ctx->h_dstats, ctx->dstats.p, sizeof(DevStats), cudaMemcpyDeviceToHost, s));
     MTG_CUDA(cudaStreamSynchronize(s));
+    ctx->h_dstats_final = h_counts[0] == 0;
     MTG_CUDA(cudaEventElapsedTime(&ctx->last_kernel_ms, ctx->ev2, ctx->ev3));
     // ---- tier 1: warp per source, for searches with more than T0_ENTRIES labelled nodes ----
     if (h_counts[0]) {
@@ -616,12 +619,19 @@ void dijkstra_candidates(mtg_ctx* ctx, u32 cap, u32 shard_rank, u32 shard_count)
     ctx->dstats.zero(s);
     MTG_CUDA(cudaEventRecord(ctx->ev0, s));
     run_searches(ctx, ctx->target_bits.p, nullptr, ctx->S_local, shard_rank, shard_count, cap, ctx->cand.p, ctx->cand_meta.p);
-    MTG_CUDA(cudaEventRecord(ctx->ev1, s));
-    DevStats h{};
-    MTG_CUDA(cudaMemcpyAsync(&h, ctx->dstats.p, sizeof(h), cudaMemcpyDeviceToHost, s));
-    MTG_CUDA(cudaStreamSynchronize(s));
     float ms = 0;
-    MTG_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    if (ctx->S_local == 0) {
+        ctx->h_dstats = DevStats{};
+        ctx->last_kernel_ms = 0;
+    } else if (ctx->h_dstats_final) {  // tier 0 was everything: its synchronisation already brought the counters back
+        MTG_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev3));
+    } else {
+        MTG_CUDA(cudaEventRecord(ctx->ev1, s));
+        MTG_CUDA(cudaMemcpyAsync(&ctx->h_dstats, ctx->dstats.p, sizeof(DevStats), cudaMemcpyDeviceToHost, s));
+        MTG_CUDA(cudaStreamSynchronize(s));
+        MTG_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    }
+    const DevStats& h = ctx->h_dstats;
     ctx->stats = mtg_search_stats{};
     ctx->stats.sources_searched = h.sources_searched;
     ctx->stats.settled_nodes = h.settled;

@@ -11,6 +11,7 @@
 // the 4U end slots, then one thread per component replays its unions in call order with
 // union-by-rank so that representatives -- and therefore node ids -- equal the reference's.
 #include <algorithm>
+#include <cstdlib>
 #include <memory>
 
 #include "mtg_internal.cuh"
@@ -191,9 +192,9 @@ __global__ void __launch_bounds__(TB)
                    u32* __restrict__ src_flag, u32* __restrict__ target_bits, unsigned long long* __restrict__ counters) {
     u64 v = (u64)blockIdx.x * TB + threadIdx.x;
     bool is_src = false, is_tgt = false, self_unb = false;
+    i32 diff = 0;
     if (v < N) {
         u32 m = mirror[v];
-        i32 diff;
         if (m == (u32)v) {
             diff = (i32)(out_deg[v] & 1u);
             is_src = is_tgt = self_unb = diff != 0;
@@ -212,6 +213,9 @@ __global__ void __launch_bounds__(TB)
         if (tb) atomicAdd(&counters[0], (unsigned long long)__popc(tb));
         if (sb) atomicAdd(&counters[1], (unsigned long long)__popc(sb));
     }
+    // total target multiplicity: an upper bound for the number of matches (sizes the triple buffers without a round trip)
+    const unsigned tm = __reduce_add_sync(0xffffffffu, is_tgt ? (unsigned)diff : 0u);
+    if ((threadIdx.x & 31) == 0 && tm) atomicAdd(&counters[2], (unsigned long long)tm);
 }
 
 __global__ void __launch_bounds__(TB) compact_flagged(const u32* __restrict__ flag, const u32* __restrict__ pos, u64 n, u32* __restrict__ out) {
@@ -396,10 +400,7 @@ int bits_for(u64 n) {
     return b;
 }
 
-void check_err_flag(mtg_ctx* ctx, int* d_err) {
-    int h = 0;
-    MTG_CUDA(cudaMemcpyAsync(&h, d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    MTG_CUDA(cudaStreamSynchronize(ctx->stream));
+void throw_on_err_flag(int h) {
     switch (h) {
         case 0: return;
         case 1: throw Error{MTG_ERR_INPUT, "sequence contains a character other than A, C, G, T"};
@@ -411,13 +412,22 @@ void check_err_flag(mtg_ctx* ctx, int* d_err) {
     }
 }
 
+void check_err_flag(mtg_ctx* ctx, int* d_err) {
+    int h = 0;
+    MTG_CUDA(cudaMemcpyAsync(&h, d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    MTG_CUDA(cudaStreamSynchronize(ctx->stream));
+    throw_on_err_flag(h);
+}
+
 // Packs the sequences into ctx->seq_words / seq_off.  Returns device pointers to the ASCII (for nothing else).
-void upload_and_pack(mtg_ctx* ctx, const char* seq, const u64* offsets, u64 U, bool on_device, int* d_err) {
+void upload_and_pack(mtg_ctx* ctx, const char* seq, const u64* offsets, u64 U, bool on_device, u64 total_known, int* d_err) {
     cudaStream_t s = ctx->stream;
-    u64 total;
+    u64 total = total_known;
     if (on_device) {
-        MTG_CUDA(cudaMemcpyAsync(&total, offsets + U, sizeof(u64), cudaMemcpyDeviceToHost, s));
-        MTG_CUDA(cudaStreamSynchronize(s));
+        if (total == UNKNOWN_TOTAL) {  // device-resident offsets from outside: the last one has to come back
+            MTG_CUDA(cudaMemcpyAsync(&total, offsets + U, sizeof(u64), cudaMemcpyDeviceToHost, s));
+            MTG_CUDA(cudaStreamSynchronize(s));
+        }
         ctx->seq_off.resize(U + 1, s);
         MTG_CUDA(cudaMemcpyAsync(ctx->seq_off.p, offsets, (U + 1) * sizeof(u64), cudaMemcpyDeviceToDevice, s));
     } else {
@@ -447,7 +457,7 @@ void finish_graph(mtg_ctx* ctx) {
     const u32 k = ctx->k;
     ctx->out_deg.resize(N, s);
     ctx->out_deg.zero(s);
-    DBuf<u32> deg_s, short_flag, pos, from_a, from_b, eid_a, eid_b, src_flag;
+    DBuf<u32> deg_s, short_flag, pos, pos_e, from_a, from_b, eid_a, eid_b, src_flag;
     deg_s.resize(N, s);
     deg_s.zero(s);
     short_flag.resize(E, s);
@@ -465,28 +475,29 @@ void finish_graph(mtg_ctx* ctx) {
         MTG_LAUNCH(ctx, classify_nodes, grid_for(padded, TB), TB, 0, ctx->out_deg.p, ctx->mirror.p, N, ctx->imbalance.p, src_flag.p,
                    ctx->target_bits.p, d_counters);
     }
-    pos.resize(std::max(N, E) + 1, s);
+    // source positions, short-edge rows and short-edge positions: three scans, then ONE round trip for all totals
+    pos.resize(N + 1, s);
+    pos_e.resize(E + 1, s);
     u32* d_tot = nullptr;
     MTG_CUDA(cudaMallocAsync((void**)&d_tot, 2 * sizeof(u32), s));
+    MTG_CUDA(cudaMemsetAsync(d_tot, 0, 2 * sizeof(u32), s));
     exclusive_sum_u32(ctx, src_flag.p, pos.p, N, d_tot);
-    u32 h_tot[2] = {0, 0};
-    unsigned long long h_counters[4];
-    MTG_CUDA(cudaMemcpyAsync(h_tot, d_tot, sizeof(u32), cudaMemcpyDeviceToHost, s));
-    MTG_CUDA(cudaMemcpyAsync(h_counters, d_counters, sizeof(h_counters), cudaMemcpyDeviceToHost, s));
-    MTG_CUDA(cudaStreamSynchronize(s));
-    ctx->S = h_tot[0];
-    ctx->T = h_counters[0];
-    ctx->self_mirror_unbalanced = h_counters[1];
-    ctx->sources.resize(ctx->S, s);
-    if (N) MTG_LAUNCH(ctx, compact_flagged, grid_for(N, TB), TB, 0, src_flag.p, pos.p, N, ctx->sources.p);
-    // short-edge CSR
     ctx->row_s.resize(N + 1, s);
     exclusive_sum_u32(ctx, deg_s.p, ctx->row_s.p, N, ctx->row_s.p + N);
     if (N == 0) MTG_CUDA(cudaMemsetAsync(ctx->row_s.p, 0, sizeof(u32), s));
-    exclusive_sum_u32(ctx, short_flag.p, pos.p, E, d_tot + 1);
-    MTG_CUDA(cudaMemcpyAsync(h_tot + 1, d_tot + 1, sizeof(u32), cudaMemcpyDeviceToHost, s));
+    exclusive_sum_u32(ctx, short_flag.p, pos_e.p, E, d_tot + 1);
+    u32 h_tot[2] = {0, 0};
+    unsigned long long h_counters[4];
+    MTG_CUDA(cudaMemcpyAsync(h_tot, d_tot, sizeof(h_tot), cudaMemcpyDeviceToHost, s));
+    MTG_CUDA(cudaMemcpyAsync(h_counters, d_counters, sizeof(h_counters), cudaMemcpyDeviceToHost, s));
     MTG_CUDA(cudaStreamSynchronize(s));
+    ctx->S = h_tot[0];
     ctx->Es = h_tot[1];
+    ctx->T = h_counters[0];
+    ctx->self_mirror_unbalanced = h_counters[1];
+    ctx->target_mult_total = h_counters[2];
+    ctx->sources.resize(ctx->S, s);
+    if (N) MTG_LAUNCH(ctx, compact_flagged, grid_for(N, TB), TB, 0, src_flag.p, pos.p, N, ctx->sources.p);
     const u64 Es = ctx->Es;
     ctx->col_s.resize(Es, s);
     ctx->w_s.resize(Es, s);
@@ -495,21 +506,24 @@ void finish_graph(mtg_ctx* ctx) {
         from_b.resize(Es, s);
         eid_a.resize(Es, s);
         eid_b.resize(Es, s);
-        MTG_LAUNCH(ctx, gather_short_edges, grid_for(E, TB), TB, 0, short_flag.p, pos.p, ctx->edge_from.p, E, from_a.p, eid_a.p);
+        MTG_LAUNCH(ctx, gather_short_edges, grid_for(E, TB), TB, 0, short_flag.p, pos_e.p, ctx->edge_from.p, E, from_a.p, eid_a.p);
         int which = radix_sort_pairs_u32(ctx, from_a.p, from_b.p, eid_a.p, eid_b.p, Es, bits_for(N));
         MTG_LAUNCH(ctx, fill_short_csr, grid_for(Es, TB), TB, 0, which ? eid_b.p : eid_a.p, ctx->edge_to.p, ctx->unitig_w.p, Es,
                    ctx->col_s.p, ctx->w_s.p);
     }
     MTG_CUDA(cudaFreeAsync(d_counters, s));
     MTG_CUDA(cudaFreeAsync(d_tot, s));
-    for (DBuf<u32>* b : {&deg_s, &short_flag, &pos, &from_a, &from_b, &eid_a, &eid_b, &src_flag}) b->release(s);
+    for (DBuf<u32>* b : {&deg_s, &short_flag, &pos, &pos_e, &from_a, &from_b, &eid_a, &eid_b, &src_flag}) b->release(s);
     ctx->have_graph = true;
     ctx->have_cand = ctx->have_triples = ctx->have_walks = false;
+    // small graphs prepare the sequential tail on the host: send it its inputs now, behind the build
+    ctx->tail_inputs_staged = false;
+    if (N < TAIL_HOST_PREP_MAX_NODES && !getenv("MTG_TAIL_HOST")) stage_tail_inputs(ctx);
 }
 
 }  // namespace
 
-void build_graph_from_sequences(mtg_ctx* ctx, const char* seq, const u64* offsets, u64 U, u32 k, bool on_device) {
+void build_graph_from_sequences(mtg_ctx* ctx, const char* seq, const u64* offsets, u64 U, u32 k, bool on_device, u64 total_bases) {
     MTG_REQUIRE(k >= 2 && k <= 64, MTG_ERR_INVALID, "k must be in [2, 64]");
     MTG_REQUIRE(U < (1ull << 30), MTG_ERR_UNSUPPORTED, "more than 2^30 unitigs");
     MTG_REQUIRE(U == 0 || (seq && offsets), MTG_ERR_INVALID, "null sequence input");
@@ -529,7 +543,7 @@ void build_graph_from_sequences(mtg_ctx* ctx, const char* seq, const u64* offset
         ctx->total_bases = 0;
         ctx->have_seqs = true;
     } else {
-        upload_and_pack(ctx, seq, offsets, U, on_device, d_err);
+        upload_and_pack(ctx, seq, offsets, U, on_device, total_bases, d_err);
     }
     const u64 n = 2 * U;
     const u32 L = k - 1;
@@ -547,7 +561,7 @@ void build_graph_from_sequences(mtg_ctx* ctx, const char* seq, const u64* offset
     ctx->unitig_w.resize(U, s);
     if (n) MTG_LAUNCH(ctx, extract_end_keys, grid_for(n, TB), TB, 0, ctx->seq_words.p, ctx->seq_off.p, U, k, klo_a.p, khi_a.p, val_a.p,
                       ctx->unitig_w.p, d_err);
-    check_err_flag(ctx, d_err);
+    // the input error flag is read together with the node count below (sorting garbage keys is harmless)
     int which = radix_sort_pairs(ctx, klo_a.p, klo_b.p, khi_a.p, khi_b.p, val_a.p, val_b.p, n, nwords, 2 * (int)L);
     const u64* klo = which ? klo_b.p : klo_a.p;
     const u64* khi = nwords == 2 ? (which ? khi_b.p : khi_a.p) : nullptr;
@@ -568,22 +582,25 @@ void build_graph_from_sequences(mtg_ctx* ctx, const char* seq, const u64* offset
         MTG_LAUNCH(ctx, assign_nodes, grid_for(n, TB), TB, 0, val, head_idx.p, created.p, base.p, n, node_ep.p, mirror_ep.p);
     }
     u32 h_n = 0;
+    int h_err = 0;
     MTG_CUDA(cudaMemcpyAsync(&h_n, d_tot, sizeof(u32), cudaMemcpyDeviceToHost, s));
+    MTG_CUDA(cudaMemcpyAsync(&h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, s));
     MTG_CUDA(cudaStreamSynchronize(s));
+    MTG_CUDA(cudaFreeAsync(d_tot, s));
+    MTG_CUDA(cudaFreeAsync(d_err, s));
+    throw_on_err_flag(h_err);
     ctx->N = h_n;
     ctx->edge_from.resize(n, s);
     ctx->edge_to.resize(n, s);
     ctx->mirror.resize(ctx->N, s);
     if (U) MTG_LAUNCH(ctx, make_edges, grid_for(U, TB), TB, 0, node_ep.p, mirror_ep.p, U, ctx->edge_from.p, ctx->edge_to.p, ctx->mirror.p);
-    MTG_CUDA(cudaFreeAsync(d_tot, s));
-    MTG_CUDA(cudaFreeAsync(d_err, s));
     for (DBuf<u64>* b : {&klo_a, &klo_b, &khi_a, &khi_b}) b->release(s);
     for (DBuf<u32>* b : {&val_a, &val_b, &head_idx, &created, &base, &node_ep, &mirror_ep}) b->release(s);
     finish_graph(ctx);
 }
 
 void build_graph_from_links(mtg_ctx* ctx, u64 U, const u64* weights, u64 n_links, const u64* a, const u8* sa, const u64* b,
-                            const u8* sb, u32 k, const char* seq, const u64* offsets, bool on_device) {
+                            const u8* sb, u32 k, const char* seq, const u64* offsets, bool on_device, u64 total_bases) {
     MTG_REQUIRE(k >= 2 && k <= 64, MTG_ERR_INVALID, "k must be in [2, 64]");
     MTG_REQUIRE(U < (1ull << 30), MTG_ERR_UNSUPPORTED, "more than 2^30 unitigs");
     MTG_REQUIRE(U == 0 || weights, MTG_ERR_INVALID, "null weights");
@@ -598,7 +615,7 @@ void build_graph_from_links(mtg_ctx* ctx, u64 U, const u64* weights, u64 n_links
     int* d_err = nullptr;
     MTG_CUDA(cudaMallocAsync((void**)&d_err, sizeof(int), s));
     MTG_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), s));
-    if (seq && offsets && U) upload_and_pack(ctx, seq, offsets, U, on_device, d_err);
+    if (seq && offsets && U) upload_and_pack(ctx, seq, offsets, U, on_device, total_bases, d_err);
     DBuf<u64> d_w, d_a, d_b;
     DBuf<u8> d_sa, d_sb, rank;
     DBuf<u32> cc, key_a, key_b, op_a, op_b, parent, rep, is_rep, node_of_rep;

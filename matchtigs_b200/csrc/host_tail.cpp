@@ -178,6 +178,7 @@ struct WalkInput {
     NodeRow* rows;
     const AdjEntry* ext;
     const u32* dummy_w;  // weight of dummy edge e at [e - E0]
+    bool hints;          // the rows carry prefetch hints (not worth building while everything is cache-resident)
 };
 
 void walk_and_break(const WalkInput& w, TailOutput& out, TailScratch& scratch);
@@ -285,13 +286,16 @@ void run_tail(const TailInput& in, TailOutput& out, TailScratch& scratch) {
             r.cur = 0;
         }
     }
+    const bool hints = n >= TAIL_HOST_PREP_MAX_NODES;
+    if (hints) {
 #pragma omp parallel for schedule(static) if (par)
-    for (i64 v = 0; v < (i64)n; v++) fill_row_hints(rowp, extp, (u32)v);
+        for (i64 v = 0; v < (i64)n; v++) fill_row_hints(rowp, extp, (u32)v);
+    }
     double t3 = now_ms();
     out.ms_degrees = t1 - t0;
     out.ms_eulerise = t2 - t1;
     out.ms_csr = t3 - t2;
-    WalkInput w{in.k, in.n_nodes, E0, E, in.from, in.to, rows.data(), ext.data(), out.dummy_w.data()};
+    WalkInput w{in.k, in.n_nodes, E0, E, in.from, in.to, rows.data(), ext.data(), out.dummy_w.data(), hints};
     walk_and_break(w, out, scratch);
 }
 
@@ -332,7 +336,7 @@ void walk_and_break(const WalkInput& in, TailOutput& out, TailScratch& scratch) 
         hint = nullptr;
         return r.cur < end ? &ext[r.cur] : nullptr;
     };
-    const bool use_hints = !getenv("MTG_TAIL_NOHINT");
+    const bool use_hints = in.hints && !getenv("MTG_TAIL_NOHINT");
     // Positions whose from-node may still own an unused out-edge, in cycle order from the head.  A position is only
     // recorded if its row had entries left when the walk passed (exhaustion is permanent), which skips about half of
     // the re-root probes -- each one a cache miss.
@@ -540,10 +544,12 @@ static void eulerise_sparse(u32 k, TailLeftover& lo, std::vector<u32>& breaking)
 }
 
 // Variant kept for A/B measurements (MTG_TAIL_HOST=1): everything after the matching on the host.
-static void finish_walks_host_prep(mtg_ctx* ctx) {
+// Copies of the graph arrays the host-side preparation reads, into page-locked staging.  Issued right behind the graph
+// build for graphs that will take the host path, so that they have long arrived when the tail starts.
+void stage_tail_inputs(mtg_ctx* ctx) {
     cudaStream_t s = ctx->stream;
     const u64 U = ctx->U, N = ctx->N, E = ctx->E;
-    u32* from = ctx->tail_stage[0].as<u32>(E + 1);  // page-locked staging: full-speed DMA
+    u32* from = ctx->tail_stage[0].as<u32>(E + 1);
     u32* to = ctx->tail_stage[1].as<u32>(E + 1);
     u32* uw = ctx->tail_stage[2].as<u32>(U + 1);
     u32* mirror = ctx->tail_stage[3].as<u32>(N + 1);
@@ -553,7 +559,20 @@ static void finish_walks_host_prep(mtg_ctx* ctx) {
         MTG_CUDA(cudaMemcpyAsync(uw, ctx->unitig_w.p, U * sizeof(u32), cudaMemcpyDeviceToHost, s));
     }
     if (N) MTG_CUDA(cudaMemcpyAsync(mirror, ctx->mirror.p, N * sizeof(u32), cudaMemcpyDeviceToHost, s));
-    MTG_CUDA(cudaStreamSynchronize(s));
+    ctx->tail_inputs_staged = true;
+}
+
+static void finish_walks_host_prep(mtg_ctx* ctx) {
+    cudaStream_t s = ctx->stream;
+    const u64 U = ctx->U, N = ctx->N, E = ctx->E;
+    u32* from = ctx->tail_stage[0].as<u32>(E + 1);  // page-locked staging: full-speed DMA
+    u32* to = ctx->tail_stage[1].as<u32>(E + 1);
+    u32* uw = ctx->tail_stage[2].as<u32>(U + 1);
+    u32* mirror = ctx->tail_stage[3].as<u32>(N + 1);
+    if (!ctx->tail_inputs_staged) {  // small graphs: stage_tail_inputs already ran behind the graph build
+        stage_tail_inputs(ctx);
+        MTG_CUDA(cudaStreamSynchronize(s));
+    }
     TailInput in{ctx->k, N, E, from, to, uw, mirror, ctx->h_triples.data(), ctx->n_triples};
     TailOutput out;
     run_tail(in, out, ctx->tail_scratch);
@@ -567,8 +586,7 @@ static void finish_walks_host_prep(mtg_ctx* ctx) {
     ctx->tail_ms[4] = out.ms_break;
     ctx->d_walk_edges.upload(ctx->walk_edges.data(), ctx->walk_edges.size(), s);
     ctx->d_walk_limits.upload(ctx->walk_limits.data(), ctx->walk_limits.size(), s);
-    ctx->d_dummy_w.upload(ctx->h_dummy_w.data(), ctx->h_dummy_w.size(), s);
-    MTG_CUDA(cudaStreamSynchronize(s));
+    ctx->d_dummy_w.upload(ctx->h_dummy_w.data(), ctx->h_dummy_w.size(), s);  // pageable sources: staged before the call returns
     ctx->have_walks = true;
 }
 
@@ -576,9 +594,10 @@ void finish_walks(mtg_ctx* ctx) {
     MTG_REQUIRE(ctx->have_graph && ctx->have_triples, MTG_ERR_INVALID, "mtg_greedy_match has not run");
     // Small graphs: the device-side preparation is a dozen launches and four round trips, more than the host needs
     // to do the same work (MTG_TAIL_HOST=0/1 forces either path for A/B measurements).
-    bool host_prep = ctx->N < (1u << 17);
+    bool host_prep = ctx->N < TAIL_HOST_PREP_MAX_NODES;
     if (const char* e = getenv("MTG_TAIL_HOST")) host_prep = (*e == '1');
     if (host_prep) return finish_walks_host_prep(ctx);
+    ctx->tail_inputs_staged = false;  // this path reuses the staging buffers
     cudaStream_t s = ctx->stream;
     const u64 N = ctx->N, E0 = ctx->E;
     TailScratch& scratch = ctx->tail_scratch;
@@ -626,7 +645,7 @@ void finish_walks(mtg_ctx* ctx) {
     for (u64 j = 0; j < ctx->n_triples; j++) out.dummy_w[2 * j] = out.dummy_w[2 * j + 1] = tr[3 * j + 2];
     for (u64 j = ctx->n_triples; j < P; j++) out.dummy_w[2 * j] = out.dummy_w[2 * j + 1] = ctx->k;
     double t2 = now_ms();
-    WalkInput w{ctx->k, N, E0, E0 + 2 * P, from, to, rows, ext, out.dummy_w.data()};
+    WalkInput w{ctx->k, N, E0, E0 + 2 * P, from, to, rows, ext, out.dummy_w.data(), true};
     walk_and_break(w, out, scratch);
     ctx->walk_edges.swap(out.walk_edges);
     ctx->walk_limits.swap(out.walk_limits);

@@ -224,10 +224,14 @@ __global__ void __launch_bounds__(TB) compact_indices(const u32* __restrict__ fl
 }
 // wait-list entries of a pending source: mirror(src) + every entry that is open at the start of the phase
 __global__ void __launch_bounds__(TB)
-    count_waits(const u32* __restrict__ pend, u32 n_pend, const u64* __restrict__ list_addr, const u32* __restrict__ list_meta,
-                const i32* __restrict__ mult, u32* __restrict__ cnt) {
+    count_waits(const u32* __restrict__ pend, const u32* __restrict__ n_pend_dev, u64 S, const u64* __restrict__ list_addr,
+                const u32* __restrict__ list_meta, const i32* __restrict__ mult, u32* __restrict__ cnt) {
     u32 r = blockIdx.x * TB + threadIdx.x;
-    if (r >= n_pend) return;
+    if (r >= S) return;
+    if (r >= *n_pend_dev) {  // launched over all S slots: the host learns n_pend together with the wait-list total
+        cnt[r] = 0;
+        return;
+    }
     const u32 i = pend[r];
     const u64* list = reinterpret_cast<const u64*>(list_addr[i]);
     const u32 count = list_meta[i] & META_COUNT;
@@ -370,35 +374,34 @@ void greedy_match(mtg_ctx* ctx, const u64* d_records_all, const u32* d_meta_all,
     MTG_LAUNCH(ctx, init_lists, grid_for(S, TB), TB, 0, ctx->sources.p, ctx->mirror.p, ctx->imbalance.p, d_records_all, d_meta_all, S,
                shard_count, padded, cap, list_addr.p, list_meta.p, max_trip.p);
     exclusive_sum_u32(ctx, max_trip.p, trip_off.p, S, small.p + 5);
-    u32 total_slots = 0;
-    MTG_CUDA(cudaMemcpyAsync(&total_slots, small.p + 5, sizeof(u32), cudaMemcpyDeviceToHost, s));
-    MTG_CUDA(cudaStreamSynchronize(s));
-    trip_slots.resize(3ull * std::max<u32>(total_slots, 1), s);
-    ctx->triples.resize(3ull * std::max<u32>(total_slots, 1), s);
+    // every match closes one unit of some target's multiplicity: the graph build's total bounds the triple slots
+    const u64 slot_bound = std::max<u64>(ctx->target_mult_total, 1);
+    MTG_REQUIRE(slot_bound < 0xFFFFFFFFull / 3, MTG_ERR_UNSUPPORTED, "too many potential matches");
+    trip_slots.resize(3 * slot_bound, s);
+    ctx->triples.resize(3 * slot_bound, s);
 
     int occ = 0;
     MTG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, match_dataflow_kernel, TB, 0));
     if (occ < 1) occ = 1;
 
     u64 lo = 0, n_final = 0, retries_total = 0;
+    bool copied_out = false;  // triples + counters already fetched with the last phase's round trip
     for (int phase = 0;; phase++) {
         MTG_REQUIRE(phase < 16, MTG_ERR_INTERNAL, "matching did not converge");
         // pending = sources >= lo with a non-empty list, ascending
         MTG_LAUNCH(ctx, flag_pending, grid_for(S, TB), TB, 0, list_meta.p, S, lo, flag.p);
         exclusive_sum_u32(ctx, flag.p, pos.p, S, small.p + 0);
         MTG_LAUNCH(ctx, compact_indices, grid_for(S, TB), TB, 0, flag.p, pos.p, S, pend.p);
-        u32 n_pend = 0;
-        MTG_CUDA(cudaMemcpyAsync(&n_pend, small.p + 0, sizeof(u32), cudaMemcpyDeviceToHost, s));
+        // wait lists: (node, source) pairs written in source order, stable sort by node => ascending sources per node
+        MTG_LAUNCH(ctx, count_waits, grid_for(S, TB), TB, 0, pend.p, small.p + 0, S, list_addr.p, list_meta.p, mult.p, wait_cnt.p);
+        exclusive_sum_u32(ctx, wait_cnt.p, wait_off.p, S, small.p + 6);
+        u32 h_np[7];
+        MTG_CUDA(cudaMemcpyAsync(h_np, small.p, sizeof(h_np), cudaMemcpyDeviceToHost, s));
         MTG_CUDA(cudaStreamSynchronize(s));
+        const u32 n_pend = h_np[0], P = h_np[6];
         trip_cnt.zero(s);
         u32 min_insuff = NO_INDEX;
         if (n_pend) {
-            // wait lists: (node, source) pairs written in source order, stable sort by node => ascending sources per node
-            MTG_LAUNCH(ctx, count_waits, grid_for(n_pend, TB), TB, 0, pend.p, n_pend, list_addr.p, list_meta.p, mult.p, wait_cnt.p);
-            exclusive_sum_u32(ctx, wait_cnt.p, wait_off.p, n_pend, small.p + 6);
-            u32 P = 0;
-            MTG_CUDA(cudaMemcpyAsync(&P, small.p + 6, sizeof(u32), cudaMemcpyDeviceToHost, s));
-            MTG_CUDA(cudaStreamSynchronize(s));
             key_a.resize(P, s);
             key_b.resize(P, s);
             val_a.resize(P, s);
@@ -453,6 +456,14 @@ void greedy_match(mtg_ctx* ctx, const u64* d_records_all, const u32* d_meta_all,
         MTG_LAUNCH(ctx, copy_final, grid_for(S, TB), TB, 0, flag.p, pos.p, trip_off.p, trip_slots.p, S, n_final, ctx->triples.p);
         u32 added = 0;
         MTG_CUDA(cudaMemcpyAsync(&added, small.p + 5, sizeof(u32), cudaMemcpyDeviceToHost, s));
+        if (jstar >= S && slot_bound <= (1u << 20)) {
+            // last phase of a small job: the triples (up to their bound), the counters and the count share one round trip
+            ctx->h_triples.resize(3 * slot_bound);
+            MTG_CUDA(cudaMemcpyAsync(ctx->h_triples.data(), ctx->triples.p, 3 * slot_bound * sizeof(u32), cudaMemcpyDeviceToHost, s));
+            MTG_CUDA(cudaMemcpyAsync(&ctx->h_dstats, ctx->dstats.p, sizeof(DevStats), cudaMemcpyDeviceToHost, s));
+            MTG_CUDA(cudaEventRecord(ctx->ev1, s));
+            copied_out = true;
+        }
         MTG_CUDA(cudaStreamSynchronize(s));
         n_final += added;
         if (jstar >= S) break;
@@ -484,16 +495,17 @@ void greedy_match(mtg_ctx* ctx, const u64* d_records_all, const u32* d_meta_all,
     ctx->stats.matched = n_final;
     ctx->stats.match_rounds = retries_total;
     ctx->h_triples.resize(3 * n_final);
-    if (n_final) MTG_CUDA(cudaMemcpyAsync(ctx->h_triples.data(), ctx->triples.p, 3 * n_final * sizeof(u32), cudaMemcpyDeviceToHost, s));
-    MTG_CUDA(cudaEventRecord(ctx->ev1, s));
-    MTG_CUDA(cudaStreamSynchronize(s));
+    if (!copied_out) {
+        if (n_final) MTG_CUDA(cudaMemcpyAsync(ctx->h_triples.data(), ctx->triples.p, 3 * n_final * sizeof(u32), cudaMemcpyDeviceToHost, s));
+        // searches of requery phases added to the device counters
+        MTG_CUDA(cudaMemcpyAsync(&ctx->h_dstats, ctx->dstats.p, sizeof(DevStats), cudaMemcpyDeviceToHost, s));
+        MTG_CUDA(cudaEventRecord(ctx->ev1, s));
+        MTG_CUDA(cudaStreamSynchronize(s));
+    }
     float ms = 0;
     MTG_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     ctx->stats.match_ms = ms;
-    // searches of requery phases added to the device counters
-    DevStats h{};
-    MTG_CUDA(cudaMemcpyAsync(&h, ctx->dstats.p, sizeof(h), cudaMemcpyDeviceToHost, s));
-    MTG_CUDA(cudaStreamSynchronize(s));
+    const DevStats& h = ctx->h_dstats;
     ctx->stats.settled_nodes = h.settled;
     ctx->stats.relaxed_edges = h.relaxed;
     ctx->stats.overflow_sources = h.overflow;

@@ -181,6 +181,8 @@ struct mtg_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     float last_kernel_ms = 0;  // tier-0 search kernel of the last run_searches call
+    mtg::DevStats h_dstats{};   // host copy of the search counters taken by the last run_searches call ...
+    bool h_dstats_final = false;  // ... and whether nothing ran after that copy
     std::string err;
     uint64_t launches = 0;
     int num_sms = mtg::NUM_SMS_B200;
@@ -188,6 +190,8 @@ struct mtg_ctx {
     // ---- resident graph (step 1) ----
     uint32_t k = 0;
     uint64_t U = 0, N = 0, E = 0, Es = 0, S = 0, T = 0, self_mirror_unbalanced = 0;
+    bool tail_inputs_staged = false;  // host copies of edge_from/edge_to/unitig_w/mirror are in tail_stage[0..3]
+    uint64_t target_mult_total = 0;  // sum of the targets' multiplicities = upper bound for the number of matches
     bool have_graph = false, have_seqs = false;
     mtg::DBuf<mtg::u64> seq_words;    // 2-bit store: base i at bits [2(i%32), 2(i%32)+1] of word i/32; A0 C1 T2 G3
     mtg::DBuf<mtg::u64> seq_off;      // [U+1] base offsets
@@ -263,11 +267,19 @@ int radix_sort_pairs(mtg_ctx* ctx, u64* k0_a, u64* k0_b, u64* k1_a, u64* k1_b, u
 int radix_sort_pairs_u32(mtg_ctx* ctx, u32* k_a, u32* k_b, u32* v_a, u32* v_b, size_t n, int key_bits);
 
 // ---- graph construction (graph.cu) ----
-void build_graph_from_sequences(mtg_ctx* ctx, const char* seq, const u64* offsets, u64 U, u32 k, bool on_device);
+// total_bases: offsets[U] if the caller already knows it (saves a round trip when the offsets live on the device)
+constexpr u64 UNKNOWN_TOTAL = ~0ull;
+void build_graph_from_sequences(mtg_ctx* ctx, const char* seq, const u64* offsets, u64 U, u32 k, bool on_device,
+                                u64 total_bases = UNKNOWN_TOTAL);
 void build_graph_from_links(mtg_ctx* ctx, u64 U, const u64* weights, u64 n_links, const u64* a, const u8* sa, const u64* b,
-                            const u8* sb, u32 k, const char* seq, const u64* offsets, bool on_device);
+                            const u8* sb, u32 k, const char* seq, const u64* offsets, bool on_device,
+                            u64 total_bases = UNKNOWN_TOTAL);
 // device-side FASTA / bcalm2 record parser feeding the two builders (parse.cu)
 void build_graph_from_text(mtg_ctx* ctx, const char* text, u64 len, bool bcalm, u32 k, bool text_on_device);
+
+// Graphs below this node count prepare the sequential tail on the host (fewer round trips than launches).
+constexpr u64 TAIL_HOST_PREP_MAX_NODES = 1u << 17;
+void stage_tail_inputs(mtg_ctx* ctx);  // host_tail.cpp
 
 // ---- search + matching (dijkstra.cu, match.cu) ----
 void dijkstra_candidates(mtg_ctx* ctx, u32 cap, u32 shard_rank, u32 shard_count);

@@ -182,8 +182,8 @@ void build_graph_from_text(mtg_ctx* ctx, const char* text, u64 L, bool bcalm, u3
         }
     }
     try {
-        if (bcalm) build_graph_from_links(ctx, U, weights.p, NL, link_a.p, strand_a.p, link_b.p, strand_b.p, k, seq.p, offsets.p, true);
-        else build_graph_from_sequences(ctx, seq.p, offsets.p, U, k, true);
+        if (bcalm) build_graph_from_links(ctx, U, weights.p, NL, link_a.p, strand_a.p, link_b.p, strand_b.p, k, seq.p, offsets.p, true, B);
+        else build_graph_from_sequences(ctx, seq.p, offsets.p, U, k, true, B);
     } catch (...) {
         cleanup();
         throw;
