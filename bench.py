@@ -201,24 +201,32 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    phase_s = {}  # host wall time per library call, summed over the timed steps of the current leg (every call blocks)
+
+    def call(name, fn, *a, **kw):
+        t0 = time.perf_counter()
+        r = fn(*a, **kw)
+        phase_s[name] = phase_s.get(name, 0.0) + time.perf_counter() - t0
+        return r
+
     def step(resident: bool):
         """One pass of the hot path.  Returns (gfa, bitvector) on rank 0."""
         if resident:
-            ctx.build_graph_from_device_sequences(seq_dev.data_ptr(), off_dev.data_ptr(), U, k)
+            call("graph_build", ctx.build_graph_from_device_sequences, seq_dev.data_ptr(), off_dev.data_ptr(), U, k)
         else:
             # end to end: raw FASTA bytes in page-locked host memory -> H2D -> records parsed on the device -> graph
-            ctx.build_graph_from_text(text_host.numpy(), k, bcalm=False)
+            call("parse+graph_build", ctx.build_graph_from_text, text_host.numpy(), k, bcalm=False)
         if world == 1:
-            ctx.dijkstra_candidates(CAP, 0, 1)
-            ctx.greedy_match()
+            call("dijkstra", ctx.dijkstra_candidates, CAP, 0, 1)
+            call("match", ctx.greedy_match)
         else:
-            ctx.dijkstra_candidates(CAP, rank, world)
-            rec_all, meta_all = sharding.all_gather_candidates(ctx, dist, torch, world)  # NCCL over NVLink
-            ctx.greedy_match(rec_all.data_ptr(), meta_all.data_ptr(), world)
+            call("dijkstra", ctx.dijkstra_candidates, CAP, rank, world)
+            rec_all, meta_all = call("all_gather", sharding.all_gather_candidates, ctx, dist, torch, world)  # NCCL over NVLink
+            call("match", ctx.greedy_match, rec_all.data_ptr(), meta_all.data_ptr(), world)
         if rank == 0:
-            ctx.finish_walks()
+            call("tail", ctx.finish_walks)
             # results land in page-locked host memory owned by the context (zero-copy views)
-            return ctx.assemble_tigs_view("gfa"), ctx.dup_bitvector_view()
+            return call("emit_gfa", ctx.assemble_tigs_view, "gfa"), call("emit_bitvector", ctx.dup_bitvector_view)
         return None, None
 
     def timed(resident: bool, steps: int, warmup: int):
@@ -228,6 +236,7 @@ def run_ours(args):
         total_ms, dj_ms, mt_ms, djk_ms, mtk_ms, stats, out = 0.0, 0.0, 0.0, 0.0, 0.0, None, None
         per_step = []
         launches0 = ctx.kernel_launches
+        phase_s.clear()
         for _ in range(steps):
             with torch.cuda.stream(ext):
                 flush.zero_()  # evict L2 between timed iterations (outside the event pair)
@@ -251,7 +260,8 @@ def run_ours(args):
         total_ms, dj_ms, mt_ms, djk_ms, mtk_ms = (float(x) for x in t.cpu())
         per_step.sort()
         stats = dict(stats, dijkstra_kernel_ms=djk_ms / steps, match_kernel_ms=mtk_ms / steps,
-                     spread={"min": per_step[0], "median": per_step[len(per_step) // 2], "max": per_step[-1]})
+                     spread={"min": per_step[0], "median": per_step[len(per_step) // 2], "max": per_step[-1]},
+                     phases_ms={n: 1e3 * v / steps for n, v in phase_s.items()})
         return total_ms / steps, dj_ms / steps, mt_ms / steps, stats, launches, out
 
     sampler = ClockSampler(local_rank)
@@ -301,7 +311,9 @@ def run_ours(args):
                        "l2": "flushed between timed iterations (256 MiB memset)", "reader": "fa-in semantics (k-mer join)",
                        "parallelism": f"sources sharded over {world} GPU(s), graph replicated"},
             "ms_per_step_spread_rank0": stats["spread"],
+            "phases_ms_rank0": stats["phases_ms"],  # host wall time per library call (each one blocks), mean per step
             "e2e": {"value": U / (ms_e2e * 1e-3), "unit": "unitigs/s", "ms_per_step": ms_e2e, "ms_per_step_spread_rank0": stats_e2e["spread"],
+                    "phases_ms_rank0": stats_e2e["phases_ms"],
                     "h2d_bytes_per_step": int(text_host.numel()), "input": "unitig FASTA text (parsed on the device)",
                     "host_link": link,
                     "d2h_bytes_per_step": int(len(gfa) + len(bv))},
@@ -335,9 +347,9 @@ def run_ours(args):
 
 
 # (workload, scale) -> DRAM bytes (read + write) of one main launch of dijkstra_thread_kernel, from ncu --set full
-NCU_DRAM_BYTES = {("ecoli", 1.0): 210432 + 0, ("chr1", 0.3): 19860992 + 9339648}
+NCU_DRAM_BYTES = {("ecoli", 1.0): 208896 + 0, ("chr1", 0.3): 27804160 + 17134592}
 # same captures: L2 sectors the kernel read (lts__t_sectors_srcunit_tex_op_read.sum), i.e. the sector-granular traffic
-NCU_L2_READ_SECTORS = {("ecoli", 1.0): 144584, ("chr1", 0.3): 32715339}
+NCU_L2_READ_SECTORS = {("ecoli", 1.0): 144437, ("chr1", 0.3): 33546649}
 # random 32-byte-sector gather ceilings measured on a B200 of this pool with scripts/micro/gather_ceiling.cu
 # (profiles/round1_gather_ceiling.jsonl): footprint 8 GiB (HBM) and 32 MiB (L2-resident), independent gathers
 GATHER_CEILING_GBPS = {"hbm_random": 1174.8, "l2_resident": 6663.9}

@@ -197,6 +197,7 @@ constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_ROWS = 8;
 constexpr int RS_TILE = RS_THREADS * RS_ROWS;
+constexpr u32 RS_RAW_TILES = 64;  // up to this many tiles (128 K elements) the scatter CTAs scan the count matrix themselves
 
 template <class KW>
 __global__ void __launch_bounds__(RS_THREADS) radix_hist(const KW* __restrict__ keyword, u32* __restrict__ hist, size_t n, int shift,
@@ -214,14 +215,42 @@ __global__ void __launch_bounds__(RS_THREADS) radix_hist(const KW* __restrict__ 
     hist[(size_t)threadIdx.x * tiles + blockIdx.x] = h[threadIdx.x];
 }
 
-template <class KW, int NW>
+// RAW: `base_of` still holds the per-(digit, tile) counts of radix_hist; every CTA derives its own bases from them
+// (used while the count matrix is small: saves the scan launch of the pass).
+template <class KW, int NW, bool RAW>
 __global__ void __launch_bounds__(RS_THREADS)
     radix_scatter(const KW* __restrict__ k0_in, KW* __restrict__ k0_out, const KW* __restrict__ k1_in, KW* __restrict__ k1_out,
                   const u32* __restrict__ v_in, u32* __restrict__ v_out, const u32* __restrict__ base_of, size_t n, int word,
                   int shift, u32 tiles) {
     __shared__ u32 cnt[RS_WARPS][256];
+    __shared__ u32 warp_sum[RS_WARPS];
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&cnt[0][0])[i] = 0;
+    u32 my_base = 0;  // global base of (digit == threadIdx.x, this tile)
+    if (RAW) {
+        static_assert(RS_THREADS == 256, "one thread per digit");
+        const u32* row = base_of + (size_t)threadIdx.x * tiles;
+        u32 tot = 0, before = 0;
+        for (u32 t = 0; t < tiles; t++) {
+            const u32 c = row[t];
+            if (t < blockIdx.x) before += c;
+            tot += c;
+        }
+        // exclusive scan of the digit totals over the 256 threads
+        u32 inc = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            u32 up = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= (unsigned)o) inc += up;
+        }
+        if (lane == 31) warp_sum[warp] = inc;
+        __syncthreads();
+        u32 pre = 0;
+        for (unsigned w = 0; w < warp; w++) pre += warp_sum[w];
+        my_base = pre + inc - tot + before;
+    } else {
+        my_base = base_of[(size_t)threadIdx.x * tiles + blockIdx.x];
+    }
     __syncthreads();
     const size_t chunk = (size_t)blockIdx.x * RS_TILE + (size_t)warp * (RS_ROWS * 32);
     KW k0[RS_ROWS], k1[RS_ROWS];
@@ -259,7 +288,7 @@ __global__ void __launch_bounds__(RS_THREADS)
     }
     __syncthreads();
     {  // exclusive prefix over warps for digit == threadIdx.x, seeded with the global base of (digit, tile)
-        u32 run = base_of[(size_t)threadIdx.x * tiles + blockIdx.x];
+        u32 run = my_base;
 #pragma unroll
         for (int w = 0; w < RS_WARPS; w++) {
             u32 c = cnt[w][threadIdx.x];
@@ -296,8 +325,12 @@ int radix_sort_impl(mtg_ctx* ctx, KW* k0_a, KW* k0_b, KW* k1_a, KW* k1_b, u32* v
         u32 *vi = cur ? v_b : v_a, *vo = cur ? v_a : v_b;
         const KW* digit_src = (NW == 2 && word == 1) ? ki1 : ki0;
         MTG_LAUNCH(ctx, (radix_hist<KW>), tiles, RS_THREADS, 0, digit_src, hist, n, shift, tiles);
-        exclusive_sum_u32(ctx, hist, hist, (size_t)256 * tiles, nullptr);
-        MTG_LAUNCH(ctx, (radix_scatter<KW, NW>), tiles, RS_THREADS, 0, ki0, ko0, ki1, ko1, vi, vo, hist, n, word, shift, tiles);
+        if (tiles <= RS_RAW_TILES) {
+            MTG_LAUNCH(ctx, (radix_scatter<KW, NW, true>), tiles, RS_THREADS, 0, ki0, ko0, ki1, ko1, vi, vo, hist, n, word, shift, tiles);
+        } else {
+            exclusive_sum_u32(ctx, hist, hist, (size_t)256 * tiles, nullptr);
+            MTG_LAUNCH(ctx, (radix_scatter<KW, NW, false>), tiles, RS_THREADS, 0, ki0, ko0, ki1, ko1, vi, vo, hist, n, word, shift, tiles);
+        }
         cur ^= 1;
     }
     MTG_CUDA(cudaFreeAsync(hist, ctx->stream));
