@@ -256,34 +256,49 @@ void run_tail(const TailInput& in, TailOutput& out, TailScratch& scratch) {
     ext.bind(scratch.ext, n_ext, n_ext, false);
     NodeRow* rowp = rows.data();
     AdjEntry* extp = ext.data();
-    auto place = [&](u32 v, AdjEntry a) {  // any order: every row is sorted afterwards
+    auto place = [&](u32 v, AdjEntry a) {
         NodeRow& r = rowp[v];
         const u32 pos = par ? __atomic_fetch_add(&r.cur, 1u, __ATOMIC_RELAXED) : r.cur++;
         if (r.end & ROW_EXT) extp[pos] = a;
         else r.inl[pos] = a;
     };
-#pragma omp parallel for schedule(static) if (par)
-    for (i64 j = 0; j < (i64)pairs.size(); j++) {
-        const Pair& p = pairs[j];
-        const u32 e = (u32)(E0 + 2 * j);
-        place(in.mirror[p.in_node], {e + 1, in.mirror[p.out_node]});
-        place(p.out_node, {e, p.in_node});
-        out.dummy_w[2 * j] = out.dummy_w[2 * j + 1] = p.w;
-    }
-#pragma omp parallel for schedule(static) if (par)
-    for (i64 e = 0; e < (i64)E0; e++) place(in.from[e], {(u32)e, in.to[e]});
-    // newest edge first inside every row (descending edge id), and reset the cursors
-    const auto newer = [](const AdjEntry& a, const AdjEntry& b) { return a.edge > b.edge; };
-#pragma omp parallel for schedule(dynamic, 4096) if (par)
-    for (i64 v = 0; v < (i64)n; v++) {
-        NodeRow& r = rowp[v];
-        if (r.end & ROW_EXT) {
-            const u32 end = r.end & ~ROW_EXT, begin = end - od[v];
-            std::sort(extp + begin, extp + end, newer);
-            r.cur = begin;
-        } else {
-            if (r.end > 1) std::sort(r.inl, r.inl + r.end, newer);
-            r.cur = 0;
+    for (size_t j = 0; j < pairs.size(); j++) out.dummy_w[2 * j] = out.dummy_w[2 * j + 1] = pairs[j].w;
+    if (!par) {
+        // one thread: placing the edges in descending id order leaves every row sorted (newest edge first)
+        for (size_t j = pairs.size(); j-- > 0;) {
+            const Pair& p = pairs[j];
+            const u32 e = (u32)(E0 + 2 * j);
+            place(in.mirror[p.in_node], {e + 1, in.mirror[p.out_node]});
+            place(p.out_node, {e, p.in_node});
+        }
+        for (u64 e = E0; e-- > 0;) place(in.from[e], {(u32)e, in.to[e]});
+        for (u32 v = 0; v < n; v++) {
+            NodeRow& r = rowp[v];
+            r.cur = (r.end & ROW_EXT) ? (r.end & ~ROW_EXT) - od[v] : 0u;
+        }
+    } else {
+#pragma omp parallel for schedule(static)
+        for (i64 j = 0; j < (i64)pairs.size(); j++) {
+            const Pair& p = pairs[j];
+            const u32 e = (u32)(E0 + 2 * j);
+            place(in.mirror[p.in_node], {e + 1, in.mirror[p.out_node]});
+            place(p.out_node, {e, p.in_node});
+        }
+#pragma omp parallel for schedule(static)
+        for (i64 e = 0; e < (i64)E0; e++) place(in.from[e], {(u32)e, in.to[e]});
+        // newest edge first inside every row (descending edge id), and reset the cursors
+        const auto newer = [](const AdjEntry& a, const AdjEntry& b) { return a.edge > b.edge; };
+#pragma omp parallel for schedule(dynamic, 4096)
+        for (i64 v = 0; v < (i64)n; v++) {
+            NodeRow& r = rowp[v];
+            if (r.end & ROW_EXT) {
+                const u32 end = r.end & ~ROW_EXT, begin = end - od[v];
+                std::sort(extp + begin, extp + end, newer);
+                r.cur = begin;
+            } else {
+                if (r.end > 1) std::sort(r.inl, r.inl + r.end, newer);
+                r.cur = 0;
+            }
         }
     }
     const bool hints = n >= TAIL_HOST_PREP_MAX_NODES;
