@@ -5,8 +5,8 @@
 //     make_graph_eulerian_with_breaking_edges, src/implementation/mod.rs:408-427) are a compaction of the
 //     final multiplicity array -- three flag scans;
 //   * the adjacency the walk iterates (petgraph order: newest edge first) is a stable radix sort of
-//     (from-node, edge id) over all original and dummy edges, written straight into the 32-byte node records
-//     the walk uses and DMA'd into its page-locked huge-page arena.
+//     (from-node, edge id) over all original and dummy edges, written straight into the one-line node records
+//     (with their prefetch hints) the walk uses, DMA'd to the host.
 // Only the pairing loop of eulerise (sequential by definition) runs on the host in between.
 #include <algorithm>
 
