@@ -59,8 +59,8 @@ def test_reader_fasta_and_bcalm(mt):
     assert np.array_equal((np.diff(u.offsets.astype(np.int64)) + 1 - 21).astype(np.uint64), o.array("edge_weight")[::2])
 
 
-def oracle_inputs(text, k, mode):
-    o = oracle.Oracle()
+def oracle_inputs(text, k, mode, euler_fast=False):
+    o = oracle.Oracle(euler_fast=euler_fast)
     (o.load_fasta if mode == "fasta" else o.load_bcalm)(text, k)
     o.run()
     U = o.num("unitigs")
@@ -68,8 +68,8 @@ def oracle_inputs(text, k, mode):
                o.array("mirror"), o.array("triples"))
 
 
-def check_tail(mt, text, k, mode):
-    o, (ef, et, uw, mi, tr) = oracle_inputs(text, k, mode)
+def check_tail(mt, text, k, mode, euler_fast=False):
+    o, (ef, et, uw, mi, tr) = oracle_inputs(text, k, mode, euler_fast)
     walks, dummy_w, ms = mt.api.host_tail(k, ef, et, uw, mi, tr)
     ow = o.walks()
     assert len(walks) == len(ow)
@@ -92,6 +92,15 @@ def test_host_tail_equals_oracle_dbg(mt, mode):
     anc = tools.genome(15_000, 8, families=3, copies=3, min_len=50, max_len=300, divergence=0.02)
     text, _, _ = tools.unitigs(tools.pangenome(anc, 10, 5, snp_site_rate=0.04, indel_site_rate=0.003), 15)
     check_tail(mt, text, 15, mode)
+
+
+def test_host_tail_threaded_preparation_with_hints(mt):
+    """Above 2^18 edges / 2^17 nodes the host preparation runs on all cores (atomic placement + per-row sort) and builds
+    the walk's prefetch hints; the walks must not change.  (The oracle's linear-time Euler variant is used: its faithful
+    Vec::rotate_left one is quadratic; the two are compared with each other in test_oracle.py.)"""
+    text, k, info = tools.config_unitigs("chr1", 0.05)
+    assert info["unitigs"] > (1 << 17)
+    check_tail(mt, text, k, "fasta", euler_fast=True)
 
 
 def test_host_tail_empty(mt):
