@@ -179,6 +179,8 @@ struct WalkInput {
     const AdjEntry* ext;
     const u32* dummy_w;  // weight of dummy edge e at [e - E0]
     bool hints;          // the rows carry prefetch hints (not worth building while everything is cache-resident)
+    u64 n_matching;      // dummy pairs [0, n_matching) come from the matching, the rest are breaking pairs of weight k
+    bool matching_light; // every matching dummy weighs less than k (always true behind the GPU matching)
 };
 
 void walk_and_break(const WalkInput& w, TailOutput& out, TailScratch& scratch);
@@ -262,7 +264,11 @@ void run_tail(const TailInput& in, TailOutput& out, TailScratch& scratch) {
         if (r.end & ROW_EXT) extp[pos] = a;
         else r.inl[pos] = a;
     };
-    for (size_t j = 0; j < pairs.size(); j++) out.dummy_w[2 * j] = out.dummy_w[2 * j + 1] = pairs[j].w;
+    u32 max_matching_w = 0;
+    for (size_t j = 0; j < pairs.size(); j++) {
+        out.dummy_w[2 * j] = out.dummy_w[2 * j + 1] = pairs[j].w;
+        if (j < in.n_triples) max_matching_w = std::max(max_matching_w, pairs[j].w);
+    }
     if (!par) {
         // one thread: placing the edges in descending id order leaves every row sorted (newest edge first)
         for (size_t j = pairs.size(); j-- > 0;) {
@@ -310,7 +316,7 @@ void run_tail(const TailInput& in, TailOutput& out, TailScratch& scratch) {
     out.ms_degrees = t1 - t0;
     out.ms_eulerise = t2 - t1;
     out.ms_csr = t3 - t2;
-    WalkInput w{in.k, in.n_nodes, E0, E, in.from, in.to, rows.data(), ext.data(), out.dummy_w.data(), hints};
+    WalkInput w{in.k, in.n_nodes, E0, E, in.from, in.to, rows.data(), ext.data(), out.dummy_w.data(), hints, in.n_triples, max_matching_w < in.k};
     walk_and_break(w, out, scratch);
 }
 
@@ -324,17 +330,28 @@ void walk_and_break(const WalkInput& in, TailOutput& out, TailScratch& scratch) 
     used.bind(scratch.used, (E + 63) / 64 + 1, (E + 63) / 64 + 1, true);
     auto is_used = [&](u32 e) { return (used[e >> 6] >> (e & 63)) & 1ull; };
     auto mark_pair = [&](u32 e) { used[e >> 6] |= 3ull << (e & 62); };  // e and e^1 share a word
-    // The cycle under construction.  Every extension appends a contiguous run of elements to `queue`
-    // (creation order == the order in which positions are scanned for leftover out-edges).  A run created
-    // while position i was the head sits, in cycle order, immediately before element i ("push_back on the
-    // rotated vector"); all runs created at i are consecutive in `queue`, so element i only needs the
-    // range [child_begin, child_end) of its block.  Cycle order == in-order expansion of this tree.
-    struct QEntry {
-        u32 edge, from;
-        u32 child_begin, child_end;
+    // The cycle under construction: element i = (q_edge[i], q_from[i]).  Every extension appends a contiguous run
+    // (creation order == the order in which positions are scanned for leftover out-edges).  A run created while
+    // position i was the head sits, in cycle order, immediately before element i ("push_back on the rotated
+    // vector"); all runs created at i are consecutive, so i owns one block [begin, end) of later elements.  Heads are
+    // visited in ascending position, so `children` stays sorted.  Cycle order == in-order expansion of this tree --
+    // a short list of slices of q_edge, because re-roots are rare (about 100 per million steps).
+    HVec<u32> q_edge, q_from;
+    q_edge.bind(scratch.queue, E / 2 + 16, 0, false);
+    q_from.bind(scratch.cyc, E / 2 + 16, 0, false);
+    struct Child {
+        u32 pos, begin, end;
     };
-    HVec<QEntry> queue;
-    queue.bind(scratch.queue, E / 2 + 16, 0, false);
+    std::vector<Child> children;
+    struct Slice {
+        u32 b, e;
+    };
+    std::vector<Slice> rope, order;
+    struct Frame {
+        u32 next, end;   // pending slice start / end of the block
+        size_t ci, ce;   // children of this block: children[ci, ce)
+    };
+    std::vector<Frame> stack;
     bool more = false;          // set by first_unused: does the row hold further entries behind the returned one?
     const u32* hint = nullptr;  // set by first_unused: prefetch hints of the returned entry (inline rows only)
     auto first_unused = [&](u32 v) -> const AdjEntry* {
@@ -357,31 +374,36 @@ void walk_and_break(const WalkInput& in, TailOutput& out, TailScratch& scratch) 
     // the re-root probes -- each one a cache miss.
     HVec<u32> cand;
     cand.bind(scratch.cand, E / 2 + 16, 0, false);
-    HVec<u32> cyc;
-    cyc.bind(scratch.cyc, E / 2 + 16, 0, false);
-    std::vector<std::pair<u32, u32>> stack;  // (next index, block end)
     out.walk_edges.clear();
     out.walk_limits.clear();
     out.walk_edges.reserve(E / 2);
     double ms_break = 0;
+    // Dummy weights without a lookup: breaking dummies (pairs >= n_matching) weigh exactly k; matching dummies weigh
+    // their distance, which is below k unless a caller of the host-only entry supplied something else (`light`).
+    const u32 brk_lo = (u32)(E0 + 2 * in.n_matching);
+    const bool light = in.matching_light;
     auto is_dummy = [&](u32 e) { return e >= E0; };
-    auto dummy_weight = [&](u32 e) { return in.dummy_w[e - E0]; };
+    auto weight_of = [&](u32 e) { return e >= brk_lo ? in.k : in.dummy_w[e - E0]; };
+    auto breaks = [&](u32 e) { return e >= brk_lo || (!light && in.dummy_w[e - E0] >= in.k); };  // e is a dummy
     for (u64 e0 = 0; e0 < E; e0++) {
         if (is_used((u32)e0)) continue;
         // one closed walk per component, started at the lowest unused edge id
         size_t cf = 0;
-        queue.clear();
+        q_edge.clear();
+        q_from.clear();
         cand.clear();
+        children.clear();
         // every node owns an original edge, so the lowest unused edge of a component is never a dummy
         MTG_REQUIRE(e0 < E0, MTG_ERR_INTERNAL, "closed walk would start at a dummy edge");
         u32 start_edge = (u32)e0, start_from = in.from[e0], start_to = in.to[e0];
-        size_t head_idx = 0;  // queue index of the element the (rotated) cycle vector currently starts with
-        size_t n0 = 0;        // length of the initial closed walk == the root block [0, n0)
+        u32 head_idx = 0;  // position of the element the (rotated) cycle vector currently starts with
+        u32 n0 = 0;        // length of the initial closed walk == the root block [0, n0)
         bool rooted = false;
         for (;;) {
             mark_pair(start_edge);
-            cand.push_back((u32)queue.size());  // a walk start is always probed again
-            queue.push_back({start_edge, start_from, 0, 0});
+            cand.push_back((u32)q_edge.size());  // a walk start is always probed again
+            q_edge.push_back(start_edge);
+            q_from.push_back(start_from);
             u32 cur_node = start_to;
             for (const AdjEntry* a; (a = first_unused(cur_node)) != nullptr;) {
                 __builtin_prefetch(&rows[a->to]);
@@ -390,24 +412,26 @@ void walk_and_break(const WalkInput& in, TailOutput& out, TailScratch& scratch) 
                     __builtin_prefetch(&rows[hint[1]]);
                 }
                 mark_pair(a->edge);
-                if (more) cand.push_back((u32)queue.size());
-                queue.push_back({a->edge, cur_node, 0, 0});
+                if (more) cand.push_back((u32)q_edge.size());
+                q_edge.push_back(a->edge);
+                q_from.push_back(cur_node);
                 cur_node = a->to;
             }
-            if (rooted) queue[head_idx].child_end = (u32)queue.size();  // the run just appended belongs to the head's block
-            else n0 = queue.size();
+            if (rooted) children.back().end = (u32)q_edge.size();  // the run just appended belongs to the head's block
+            else n0 = (u32)q_edge.size();
             // re-root at the first cycle position (from the head) whose from-node still has an unused out-edge
             bool found = false;
             while (cf < cand.size()) {
-                if (cf + 12 < cand.size()) __builtin_prefetch(&rows[queue[cand[cf + 12]].from]);  // independent misses: overlap them
+                if (cf + 12 < cand.size()) __builtin_prefetch(&rows[q_from[cand[cf + 12]]]);  // independent misses: overlap them
                 const u32 qf = cand[cf];
-                const AdjEntry* a = first_unused(queue[qf].from);
+                const AdjEntry* a = first_unused(q_from[qf]);
                 if (a) {
                     head_idx = qf;  // rotate_left(position)
                     rooted = true;
-                    if (!queue[qf].child_end) queue[qf].child_begin = (u32)queue.size();  // first run spliced before qf
+                    if (children.empty() || children.back().pos != qf)  // first run spliced before qf
+                        children.push_back({qf, (u32)q_edge.size(), (u32)q_edge.size()});
                     start_edge = a->edge;
-                    start_from = queue[qf].from;
+                    start_from = q_from[qf];
                     start_to = a->to;
                     found = true;
                     break;
@@ -417,52 +441,67 @@ void walk_and_break(const WalkInput& in, TailOutput& out, TailScratch& scratch) 
             if (!found) break;
         }
         double tb = now_ms();
-        const size_t len = queue.size();
-        // in-order expansion; the root block is the initial closed walk [0, n0).  The reference's cycle vector is `cyc`
-        // rotated left by head_pos; its heaviest dummy (the first one on ties, greedytigs/mod.rs:736-748) is found on the
-        // way: best_pre / best_post are the first heaviest dummies before / from head_pos on.
-        cyc.clear();
-        stack.clear();
-        stack.push_back({0u, (u32)n0});
-        size_t head_pos = 0, pre_pos = 0, post_pos = 0;
-        u32 pre_w = 0, post_w = 0;
-        bool head_seen = false;
-        auto place = [&](u32 i) {
-            const u32 x = queue[i].edge;
-            if (i == head_idx) {
-                head_pos = cyc.size();
-                head_seen = true;
-            }
-            if (is_dummy(x)) {
-                const u32 w = dummy_weight(x);
-                if (head_seen) {
-                    if (w > post_w) post_w = w, post_pos = cyc.size();
-                } else if (w > pre_w) {
-                    pre_w = w, pre_pos = cyc.size();
-                }
-            }
-            cyc.push_back(x);
+        const size_t len = q_edge.size();
+        // in-order expansion of the block tree into slices of q_edge; the root block is the initial closed walk [0, n0)
+        const auto child_range = [&](u32 b, u32 e, size_t* ci, size_t* ce) {
+            const auto lt = [](const Child& c, u32 v) { return c.pos < v; };
+            *ci = std::lower_bound(children.begin(), children.end(), b, lt) - children.begin();
+            *ce = std::lower_bound(children.begin(), children.end(), e, lt) - children.begin();
         };
+        rope.clear();
+        stack.clear();
+        {
+            Frame f{0u, n0, 0, 0};
+            child_range(0u, n0, &f.ci, &f.ce);
+            stack.push_back(f);
+        }
+        size_t total = 0;
         while (!stack.empty()) {
-            auto& fr = stack.back();
-            if (fr.first == fr.second) {
+            Frame& f = stack.back();
+            if (f.ci == f.ce) {
+                if (f.next < f.end) rope.push_back({f.next, f.end}), total += f.end - f.next;
                 stack.pop_back();
-                if (!stack.empty()) place(stack.back().first++);  // the block of this element is done: the element itself
                 continue;
             }
-            const u32 i = fr.first;
-            const QEntry& q = queue[i];
-            if (q.child_end > q.child_begin) {
-                stack.push_back({q.child_begin, q.child_end});
-            } else {
-                fr.first++;
-                place(i);
-            }
+            const Child c = children[f.ci++];
+            if (f.next < c.pos) rope.push_back({f.next, c.pos}), total += c.pos - f.next;
+            f.next = c.pos;  // the element itself follows its block
+            Frame g{c.begin, c.end, 0, 0};
+            child_range(c.begin, c.end, &g.ci, &g.ce);
+            stack.push_back(g);  // invalidates f
         }
-        MTG_REQUIRE(cyc.size() == len, MTG_ERR_INTERNAL, "cycle expansion lost elements");
-        // G. greedytigs/mod.rs:736-788: start at the heaviest dummy (rotated order = [head_pos, len) then [0, head_pos)),
-        // cut at every dummy of weight >= k and at a dummy in position 0; the rotation is never materialised
-        const size_t rot = (post_w | pre_w) == 0 ? head_pos : (post_w >= pre_w ? post_pos : pre_pos);
+        MTG_REQUIRE(total == len, MTG_ERR_INTERNAL, "cycle expansion lost elements");
+        // the reference's cycle vector starts at the head element: rotate the slice list accordingly
+        size_t s0 = 0;
+        while (s0 < rope.size() && rope[s0].b != head_idx) s0++;
+        MTG_REQUIRE(s0 < rope.size(), MTG_ERR_INTERNAL, "head element is not at a slice start");
+        order.assign(rope.begin() + s0, rope.end());
+        order.insert(order.end(), rope.begin(), rope.begin() + s0);
+        // G. greedytigs/mod.rs:736-788: start at the heaviest dummy (the first one on ties, strict `>`), cut at every dummy
+        // of weight >= k and at a dummy in position 0.  Nothing is rotated or copied: pieces go straight from the slices
+        // to the output.
+        const u32* qe = q_edge.data();
+        size_t rot_s = 0;
+        u32 rot_o = 0, best_w = 0;
+        for (size_t si = 0; si < order.size(); si++) {
+            const Slice sl = order[si];
+            bool done = false;
+            for (u32 j = sl.b; j < sl.e; j++) {
+                const u32 x = qe[j];
+                if (!is_dummy(x)) continue;
+                const u32 w = weight_of(x);
+                if (w > best_w) {
+                    best_w = w;
+                    rot_s = si;
+                    rot_o = j - sl.b;
+                    if (light && w == in.k) {  // nothing is heavier than a breaking dummy
+                        done = true;
+                        break;
+                    }
+                }
+            }
+            if (done) break;
+        }
         std::vector<u32>& we = out.walk_edges;
         size_t piece = we.size();  // start of the piece being collected
         auto close = [&] {
@@ -472,22 +511,24 @@ void walk_and_break(const WalkInput& in, TailOutput& out, TailScratch& scratch) 
             piece = we.size();
         };
         bool first = true;
-        const u32* p = cyc.data();
-        for (int seg = 0; seg < 2; seg++) {
-            const size_t jb = seg ? 0 : rot, je = seg ? rot : len;
-            size_t run = jb;  // pieces are copied run by run (a piece may continue across the wrap-around)
-            for (size_t j = jb; j < je; j++) {
-                const u32 x = p[j];
-                if (is_dummy(x) && (first || dummy_weight(x) >= in.k)) {
-                    we.insert(we.end(), p + run, p + j);
+        auto emit_range = [&](u32 b, u32 e) {  // pieces are copied run by run (a piece may continue across slices)
+            u32 run = b;
+            for (u32 j = b; j < e; j++) {
+                const u32 x = qe[j];
+                if (is_dummy(x) && (first || breaks(x))) {
+                    we.insert(we.end(), qe + run, qe + j);
                     close();
                     out.breaking++;
                     run = j + 1;
                 }
                 first = false;
             }
-            we.insert(we.end(), p + run, p + je);
-        }
+            we.insert(we.end(), qe + run, qe + e);
+        };
+        emit_range(order[rot_s].b + rot_o, order[rot_s].e);
+        for (size_t si = rot_s + 1; si < order.size(); si++) emit_range(order[si].b, order[si].e);
+        for (size_t si = 0; si < rot_s; si++) emit_range(order[si].b, order[si].e);
+        emit_range(order[rot_s].b, order[rot_s].b + rot_o);
         if (we.size() > piece && is_dummy(we.back())) we.pop_back();  // a trailing (light) dummy is dropped
         close();
         out.cycles++;
@@ -657,10 +698,14 @@ void finish_walks(mtg_ctx* ctx) {
     TailOutput out;
     out.dummy_w.resize(2 * P);
     const u32* tr = ctx->h_triples.data();
-    for (u64 j = 0; j < ctx->n_triples; j++) out.dummy_w[2 * j] = out.dummy_w[2 * j + 1] = tr[3 * j + 2];
+    u32 max_matching_w = 0;
+    for (u64 j = 0; j < ctx->n_triples; j++) {
+        out.dummy_w[2 * j] = out.dummy_w[2 * j + 1] = tr[3 * j + 2];
+        max_matching_w = std::max(max_matching_w, tr[3 * j + 2]);
+    }
     for (u64 j = ctx->n_triples; j < P; j++) out.dummy_w[2 * j] = out.dummy_w[2 * j + 1] = ctx->k;
     double t2 = now_ms();
-    WalkInput w{ctx->k, N, E0, E0 + 2 * P, from, to, rows, ext, out.dummy_w.data(), true};
+    WalkInput w{ctx->k, N, E0, E0 + 2 * P, from, to, rows, ext, out.dummy_w.data(), true, ctx->n_triples, max_matching_w < ctx->k};
     walk_and_break(w, out, scratch);
     ctx->walk_edges.swap(out.walk_edges);
     ctx->walk_limits.swap(out.walk_limits);
