@@ -110,15 +110,16 @@ void build_graph_from_text(mtg_ctx* ctx, const char* text, u64 L, bool bcalm, u3
     MTG_REQUIRE(L == 0 || text, MTG_ERR_INVALID, "null text");
     MTG_REQUIRE(L < 0xFFFFFFF0ull, MTG_ERR_UNSUPPORTED, "text of 4 GiB or more: parse it in pieces with the host reader");
     cudaStream_t s = ctx->stream;
+    auto& ws = ctx->parse_ws;
+    DBuf<u32>&ls = ws.ls, &rscan = ws.rscan, &sscan = ws.sscan, &lscan = ws.lscan, &totals = ws.totals;
+    DBuf<u8>&rec_flag = ws.rec_flag, &seq_flag = ws.seq_flag, &link_flag = ws.link_flag;
     const char* d_text = text;
-    char* staged = nullptr;
     if (!text_on_device && L) {
-        MTG_CUDA(cudaMallocAsync((void**)&staged, L, s));
-        MTG_CUDA(cudaMemcpyAsync(staged, text, L, cudaMemcpyHostToDevice, s));
-        d_text = staged;
+        ws.text.resize(L, s);
+        MTG_CUDA(cudaMemcpyAsync(ws.text.p, text, L, cudaMemcpyHostToDevice, s));
+        d_text = ws.text.p;
     }
-    DBuf<u32> ls, rscan, sscan, lscan, totals;
-    DBuf<u8> rec_flag, seq_flag, link_flag, strand_a, strand_b;
+    DBuf<u8> strand_a, strand_b;
     DBuf<char> seq;
     DBuf<u64> offsets, link_a, link_b, weights;
     DBuf<int> err;
@@ -158,9 +159,6 @@ void build_graph_from_text(mtg_ctx* ctx, const char* text, u64 L, bool bcalm, u3
     int h_err = 0;
     MTG_CUDA(cudaMemcpyAsync(&h_err, err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
     MTG_CUDA(cudaStreamSynchronize(s));
-    for (DBuf<u32>* b : {&ls, &rscan, &sscan, &lscan, &totals}) b->release(s);
-    for (DBuf<u8>* b : {&rec_flag, &seq_flag, &link_flag}) b->release(s);
-    if (staged) MTG_CUDA(cudaFreeAsync(staged, s));
     auto cleanup = [&] {
         seq.release(s);
         offsets.release(s);
