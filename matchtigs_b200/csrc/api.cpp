@@ -107,9 +107,9 @@ void mtg_ctx_destroy(mtg_ctx* ctx) {
     ctx->d_dummy_w.release(s);
     ctx->scratch_a.release(s);
     ctx->scratch_b.release(s);
-    for (mtg::DBuf<mtg::u32>* b : {&ctx->parse_ws.ls, &ctx->parse_ws.rscan, &ctx->parse_ws.sscan, &ctx->parse_ws.lscan, &ctx->parse_ws.totals})
+    for (mtg::DBuf<mtg::u32>* b : {&ctx->parse_ws.key, &ctx->parse_ws.n_rec, &ctx->parse_ws.n_seq, &ctx->parse_ws.n_link, &ctx->parse_ws.rbase,
+                                   &ctx->parse_ws.sbase, &ctx->parse_ws.lbase, &ctx->parse_ws.totals})
         b->release(s);
-    for (mtg::DBuf<mtg::u8>* b : {&ctx->parse_ws.rec_flag, &ctx->parse_ws.seq_flag, &ctx->parse_ws.link_flag}) b->release(s);
     ctx->parse_ws.text.release(s);
     for (auto& b : ctx->text_stage) b.release();
     for (auto& b : ctx->tail_stage) b.release();

@@ -190,11 +190,10 @@ struct mtg_ctx {
     // ---- resident graph (step 1) ----
     uint32_t k = 0;
     uint64_t U = 0, N = 0, E = 0, Es = 0, S = 0, T = 0, self_mirror_unbalanced = 0;
-    // Work space of the device-side text parser (parse.cu), kept across calls: ~19 bytes per text byte would otherwise be
-    // allocated and returned to the pool on every job, and a fragmented pool occasionally takes >100 ms to satisfy that.
+    // Work space of the device-side text parser (parse.cu), kept across calls (~1 byte per text byte): per 32-byte chunk
+    // its line-state key, its record / sequence-byte / link counts and their exclusive sums; plus the staged text.
     struct ParseScratch {
-        mtg::DBuf<mtg::u32> ls, rscan, sscan, lscan, totals;
-        mtg::DBuf<mtg::u8> rec_flag, seq_flag, link_flag;
+        mtg::DBuf<mtg::u32> key, n_rec, n_seq, n_link, rbase, sbase, lbase, totals;
         mtg::DBuf<char> text;
     } parse_ws;
     bool tail_inputs_staged = false;  // host copies of edge_from/edge_to/unitig_w/mirror are in tail_stage[0..3]
