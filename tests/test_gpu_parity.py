@@ -354,6 +354,30 @@ def test_other_configs_scaled(mt, ctx, name, scale):
     compare_all(mt, ctx, text, k, "bcalm", cap=4)
 
 
+def test_alternating_job_sizes_in_one_context(mt):
+    """One context, jobs of very different sizes back to back (host-prepared tail below 2^17 nodes, device-prepared above;
+    text parsed on the device): grow-only buffers, staged tail inputs and cached work space must never leak between jobs."""
+    small, ks, _ = tools.config_unitigs("ecoli", 0.05)
+    big, kb, info = tools.config_unitigs("chr1", 0.06)
+    expected = {}
+    for name, (text, k) in {"small": (small, ks), "big": (big, kb)}.items():
+        o = oracle.Oracle(euler_fast=True)
+        o.load_fasta(text, k)
+        o.run()
+        expected[name] = (o.text("gfa"), o.text("bitvector"), o.num("nodes"))
+    assert expected["small"][2] < (1 << 17) <= expected["big"][2]
+    c = mt.Context(0)
+    try:
+        for name in ["small", "big", "small", "small", "big", "small"]:
+            text, k = (small, ks) if name == "small" else (big, kb)
+            g = mt.read_bigraph_from_fasta_as_edge_centric(text, k, c, device_parse=True)
+            mt.GreedytigAlgorithm.compute_tigs(g, mt.GreedytigAlgorithmConfiguration(k=k))
+            assert mt.write_walks_gfa(g) == expected[name][0], name
+            assert mt.write_duplication_bitvector(g) == expected[name][1], name
+    finally:
+        c.close()
+
+
 def test_ecoli_scale_properties(mt, ctx):
     """BASELINE config 2 at 1/4 scale: byte identity + the size-independent properties."""
     text, k, info = tools.config_unitigs("ecoli", 0.25)
