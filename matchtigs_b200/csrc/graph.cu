@@ -620,11 +620,11 @@ void build_graph_from_links(mtg_ctx* ctx, u64 U, const u64* weights, u64 n_links
     DBuf<u8> d_sa, d_sb, rank;
     DBuf<u32> cc, key_a, key_b, op_a, op_b, parent, rep, is_rep, node_of_rep;
     if (on_device) {  // borrowed device arrays (device-side parser): no copies
-        d_w.p = const_cast<u64*>(weights);
-        d_a.p = const_cast<u64*>(a);
-        d_b.p = const_cast<u64*>(b);
-        d_sa.p = const_cast<u8*>(sa);
-        d_sb.p = const_cast<u8*>(sb);
+        d_w.borrow(const_cast<u64*>(weights), U);
+        d_a.borrow(const_cast<u64*>(a), n_links);
+        d_b.borrow(const_cast<u64*>(b), n_links);
+        d_sa.borrow(const_cast<u8*>(sa), n_links);
+        d_sb.borrow(const_cast<u8*>(sb), n_links);
     } else {
         d_w.upload(weights, U, s);
         d_a.upload(a, n_links, s);
@@ -680,7 +680,6 @@ void build_graph_from_links(mtg_ctx* ctx, u64 U, const u64* weights, u64 n_links
     check_err_flag(ctx, d_err);
     MTG_CUDA(cudaFreeAsync(d_tot, s));
     MTG_CUDA(cudaFreeAsync(d_err, s));
-    if (on_device) d_w.p = d_a.p = d_b.p = nullptr, d_sa.p = d_sb.p = nullptr;
     for (DBuf<u64>* x : {&d_w, &d_a, &d_b}) x->release(s);
     for (DBuf<u8>* x : {&d_sa, &d_sb, &rank}) x->release(s);
     for (DBuf<u32>* x : {&cc, &key_a, &key_b, &op_a, &op_b, &parent, &rep, &is_rep, &node_of_rep}) x->release(s);

@@ -41,20 +41,41 @@ struct Error {
 
 // Stream-ordered device array that only ever grows; memory comes from the device's default
 // pool (cudaMallocAsync) whose release threshold the context raises, so repeated runs reuse it.
+// Owning and move-only: a buffer that goes out of scope -- normally or because an MTG_REQUIRE / MTG_CUDA threw --
+// returns its memory on the stream it was last sized on.  borrow() wraps memory owned by somebody else.
 template <class T>
 struct DBuf {
     T* p = nullptr;
     size_t cap = 0;
     size_t n = 0;
+    cudaStream_t st = nullptr;
+    bool owned = true;
+    DBuf() = default;
+    DBuf(const DBuf&) = delete;
+    DBuf& operator=(const DBuf&) = delete;
+    DBuf(DBuf&& o) noexcept : p(o.p), cap(o.cap), n(o.n), st(o.st), owned(o.owned) { o.p = nullptr, o.cap = o.n = 0; }
+    DBuf& operator=(DBuf&& o) noexcept {
+        if (this != &o) {
+            release(st);
+            p = o.p, cap = o.cap, n = o.n, st = o.st, owned = o.owned;
+            o.p = nullptr, o.cap = o.n = 0;
+        }
+        return *this;
+    }
+    ~DBuf() { release(st); }
     void resize(size_t count, cudaStream_t s) {
-        if (count > cap) {
-            if (p) MTG_CUDA(cudaFreeAsync(p, s));
-            p = nullptr;
+        st = s;
+        if (count > cap || !owned) {
+            release(s);
             size_t want = count + count / 16 + 64;
             MTG_CUDA(cudaMallocAsync((void**)&p, want * sizeof(T), s));
             cap = want;
         }
         n = count;
+    }
+    void borrow(T* q, size_t count) {
+        release(st);
+        p = q, n = count, cap = 0, owned = false;
     }
     void zero(cudaStream_t s) {
         if (n) MTG_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s));
@@ -63,9 +84,10 @@ struct DBuf {
         if (n) MTG_CUDA(cudaMemsetAsync(p, 0xFF, n * sizeof(T), s));
     }
     void release(cudaStream_t s) {
-        if (p) cudaFreeAsync(p, s);
+        if (p && owned) cudaFreeAsync(p, s);
         p = nullptr;
         cap = n = 0;
+        owned = true;
     }
     void upload(const T* h, size_t count, cudaStream_t s) {
         resize(count, s);
