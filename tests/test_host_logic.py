@@ -103,6 +103,39 @@ def test_host_tail_threaded_preparation_with_hints(mt):
     check_tail(mt, text, k, "fasta", euler_fast=True)
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_host_tail_heavy_matching_dummies_take_the_generic_breaking_path(mt, seed):
+    """Behind the GPU matching a matching dummy always weighs less than k, and the tail recognises breaking dummies by edge
+    id.  The host-only entry accepts arbitrary triples: with weights >= k every dummy breaks (greedytigs/mod.rs:767-777),
+    found through the weight lookup.  The Euler cycle itself does not depend on the weights, so the walks must be exactly
+    the dummy-free runs of the light result (same multiset: only the rotation start may move)."""
+    rng = random.Random(4200 + seed)
+    k = rng.choice([5, 7, 8])
+    text = random_fasta(rng, rng.randint(40, 250), k, max_extra=8, pool=rng.choice([4, 9, 20]))
+    o, (ef, et, uw, mi, tr) = oracle_inputs(text, k, "fasta")
+    E0 = len(ef)
+    light, _, _ = mt.api.host_tail(k, ef, et, uw, mi, tr)
+    runs = []
+    for w in light:
+        cur = []
+        for e in w.tolist():
+            if e >= E0:
+                if cur:
+                    runs.append(tuple(cur))
+                cur = []
+            else:
+                cur.append(e)
+        if cur:
+            runs.append(tuple(cur))
+    heavy_tr = np.array(tr, dtype=np.uint32).reshape(-1, 3).copy()
+    if len(heavy_tr):
+        heavy_tr[:, 2] = k + rng.randint(0, 3)
+    heavy, dummy_w, _ = mt.api.host_tail(k, ef, et, uw, mi, heavy_tr.reshape(-1))
+    assert all((w < E0).all() for w in heavy), "a dummy of weight >= k survived inside a walk"
+    assert sorted(tuple(w.tolist()) for w in heavy) == sorted(runs)
+    assert (dummy_w >= k).all()
+
+
 def test_host_tail_empty(mt):
     walks, dummy_w, _ = mt.api.host_tail(5, [], [], [], [], [])
     assert walks == [] and len(dummy_w) == 0
