@@ -42,3 +42,57 @@ def test_cuda_matches_hand_derived(case):
         assert mt.write_duplication_bitvector(g).decode() == case["bitvector"]
     finally:
         ctx.close()
+
+
+# ---- outputs of the real reference binary, if somebody generated them (tests/golden/make_reference_goldens.sh) ----
+REF_DIR = Path(__file__).parent / "golden" / "reference"
+REF_CASES = json.loads((REF_DIR / "manifest.json").read_text())
+
+
+def _reference_outputs(case):
+    paths = {kind: REF_DIR / case[kind] for kind in ("gfa", "fasta", "bitvector")}
+    if not all(p.exists() for p in paths.values()):
+        pytest.skip("no output of the real matchtigs binary for this case (needs a Rust toolchain: "
+                    "tests/golden/make_reference_goldens.sh); parity with the reference stays unpinned")
+    return {kind: p.read_bytes() for kind, p in paths.items()}
+
+
+def test_reference_inputs_are_reproducible():
+    """The committed inputs are exactly what tests/golden/export_inputs.py generates (so the goldens can be regenerated)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("export_inputs", REF_DIR.parent / "export_inputs.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    names = set()
+    for name, text, k, modes in mod.cases():
+        assert (REF_DIR / "inputs" / f"{name}.fa").read_bytes() == text, name
+        names |= {f"{name}.{m}" for m in modes}
+    assert names == {c["name"] for c in REF_CASES}
+
+
+@pytest.mark.parametrize("case", REF_CASES, ids=[c["name"] for c in REF_CASES])
+def test_oracle_matches_reference_binary(case):
+    want = _reference_outputs(case)
+    o = oracle.Oracle()
+    text = (REF_DIR / case["input"]).read_bytes()
+    (o.load_fasta if case["mode"] == "fasta" else o.load_bcalm)(text, case["k"])
+    o.run()
+    for kind in ("gfa", "fasta", "bitvector"):
+        assert o.text(kind) == want[kind], kind
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", REF_CASES, ids=[c["name"] for c in REF_CASES])
+def test_cuda_matches_reference_binary(case):
+    want = _reference_outputs(case)
+    import matchtigs_b200 as mt
+    ctx = mt.Context(0)
+    try:
+        reader = mt.read_bigraph_from_fasta_as_edge_centric if case["mode"] == "fasta" else mt.read_bigraph_from_bcalm2_as_edge_centric
+        g = reader((REF_DIR / case["input"]).read_bytes(), case["k"], ctx)
+        mt.GreedytigAlgorithm.compute_tigs(g, mt.GreedytigAlgorithmConfiguration(k=case["k"]))
+        assert mt.write_walks_gfa(g) == want["gfa"]
+        assert mt.write_walks_fasta(g) == want["fasta"]
+        assert mt.write_duplication_bitvector(g) == want["bitvector"]
+    finally:
+        ctx.close()
