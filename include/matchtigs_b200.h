@@ -137,7 +137,8 @@ int mtg_triples_export(mtg_ctx* ctx, uint32_t* triples /* 3 * n_triples */);
  * (src/implementation/mod.rs:392-649), Euler decomposition (greedytigs/mod.rs:722) and cycle breaking
  * (greedytigs/mod.rs:726-789).  Produces walks over edge ids: original edge e < 2U, dummy edges >= 2U. */
 int mtg_finish_walks(mtg_ctx* ctx, uint64_t* n_walks, uint64_t* n_walk_edges);
-/* walk_edges [n_walk_edges], walk_limits [n_walks] (end offsets), per-edge weight of dummies via mtg_edge_weight. */
+/* walk_edges [n_walk_edges], walk_limits [n_walks] (end offsets).  Edge ids >= 2 * unitigs are dummy edges in insertion
+ * order; their weights are what mtg_walks_export_capi reports in tigs_insert_out. */
 int mtg_walks_export(mtg_ctx* ctx, uint32_t* walk_edges, uint64_t* walk_limits);
 /* C-API encoding of the walks (src/clib.rs:393-407). */
 int mtg_walks_export_capi(mtg_ctx* ctx, ptrdiff_t* tigs_edge_out, size_t* tigs_insert_out, size_t* tigs_out_limits);
@@ -169,8 +170,8 @@ int mtg_assemble_tigs_view(mtg_ctx* ctx, int format, const char** out, uint64_t*
 int mtg_compute_greedytigs_from_sequences(mtg_ctx* ctx, const char* seq_ascii, const uint64_t* offsets,
                                           uint64_t unitigs, uint32_t k, uint32_t cap);
 int mtg_get_search_stats(mtg_ctx* ctx, mtg_search_stats* stats);
-/* Diagnostics of the last run: host-tail phases in ms (degrees, eulerise, adjacency, Euler walk, breaking) and the
- * number of pending sources at the start of each of the first 48 matching rounds. */
+/* Diagnostics of the last run: host-tail phases in ms (degrees, eulerise, adjacency, Euler walk, breaking).
+ * match_pending is kept for layout compatibility and stays zero: the matching is one dataflow kernel without rounds. */
 int mtg_get_diagnostics(mtg_ctx* ctx, double tail_ms[5], uint32_t match_pending[48]);
 
 /* ---- host-side record reader ----
