@@ -502,35 +502,38 @@ void walk_and_break(const WalkInput& in, TailOutput& out, TailScratch& scratch) 
             }
             if (done) break;
         }
+        // one streaming copy: every element except the cutting dummies goes to the output, in order
         std::vector<u32>& we = out.walk_edges;
-        size_t piece = we.size();  // start of the piece being collected
+        const size_t base = we.size();
+        we.resize(base + len);
+        u32* wp = we.data() + base;
+        u32* piece = wp;  // start of the piece being collected
         auto close = [&] {
-            if (we.size() == piece) return;
-            MTG_REQUIRE(we[piece] < E0, MTG_ERR_INTERNAL, "walk starts with a dummy edge");
-            out.walk_limits.push_back(we.size());
-            piece = we.size();
+            if (wp == piece) return;
+            MTG_REQUIRE(*piece < E0, MTG_ERR_INTERNAL, "walk starts with a dummy edge");
+            out.walk_limits.push_back((u64)(wp - we.data()));
+            piece = wp;
         };
         bool first = true;
-        auto emit_range = [&](u32 b, u32 e) {  // pieces are copied run by run (a piece may continue across slices)
-            u32 run = b;
+        auto emit_range = [&](u32 b, u32 e) {
             for (u32 j = b; j < e; j++) {
                 const u32 x = qe[j];
                 if (is_dummy(x) && (first || breaks(x))) {
-                    we.insert(we.end(), qe + run, qe + j);
                     close();
                     out.breaking++;
-                    run = j + 1;
+                } else {
+                    *wp++ = x;
                 }
                 first = false;
             }
-            we.insert(we.end(), qe + run, qe + e);
         };
         emit_range(order[rot_s].b + rot_o, order[rot_s].e);
         for (size_t si = rot_s + 1; si < order.size(); si++) emit_range(order[si].b, order[si].e);
         for (size_t si = 0; si < rot_s; si++) emit_range(order[si].b, order[si].e);
         emit_range(order[rot_s].b, order[rot_s].b + rot_o);
-        if (we.size() > piece && is_dummy(we.back())) we.pop_back();  // a trailing (light) dummy is dropped
+        if (wp != piece && is_dummy(wp[-1])) wp--;  // a trailing (light) dummy is dropped
         close();
+        we.resize((size_t)(wp - we.data()));
         out.cycles++;
         ms_break += now_ms() - tb;
     }
@@ -745,7 +748,7 @@ extern "C" int mtg_host_tail(uint32_t k, uint64_t nodes, uint64_t unitigs, const
     try {
         TailInput in{k, nodes, 2 * unitigs, edge_from, edge_to, unitig_w, mirror, triples, n_triples};
         TailOutput out;
-        TailScratch scratch;
+        static thread_local TailScratch scratch;  // arenas are reused across calls, like the context does
         run_tail(in, out, scratch);
         auto dup = [](const auto& v) {
             using T = typename std::decay<decltype(v)>::type::value_type;
