@@ -37,14 +37,31 @@ if str(ROOT) not in sys.path:
 import numpy as np  # noqa: E402
 
 WORKLOADS = {
-    # name -> (tools.config_unitigs name, default scale, description)
-    "ecoli": ("ecoli", 1.0, "config[1]: synthetic 4.6 Mbp E. coli-sized genome with injected repeats, k=31, "
-                            "unitigs -> greedy matchtigs GFA + duplicate-kmer bitvector"),
-    "pangenome": ("pangenome", 0.25, "config[3] (scaled): synthetic pangenome, 100 strains with SNP/indel variation, k=31"),
-    "chr1": ("chr1", 0.1, "config[2] (scaled): synthetic chr1-like genome with repeat families, k=31"),
-    "human": ("human", 0.01, "config[4] (scaled): synthetic human-like genome, k=51"),
+    # name -> recipe of tools.config_unitigs, default scale, reader the BASELINE config names, sample scale of the reference arm
+    "ecoli": {"cfg": "ecoli", "scale": 1.0, "bcalm": False, "ref_scale": 1.0,
+              "desc": "configs[1]: synthetic 4.6 Mbp E. coli-sized genome with injected repeats, k=31, --fa-in"},
+    "pangenome": {"cfg": "pangenome", "scale": 1.0, "bcalm": False, "ref_scale": 0.25,
+                  "desc": "configs[3]: synthetic pangenome, 100 E. coli-like strains with SNP/indel variation, k=31, --fa-in"},
+    "chr1": {"cfg": "chr1", "scale": 1.0, "bcalm": True, "ref_scale": 0.1,
+             "desc": "configs[2]: synthetic 250 Mbp chr1-sized genome with repeat families, k=31, --bcalm-in"},
+    "human": {"cfg": "human", "scale": 0.2, "bcalm": True, "ref_scale": 0.02,
+              "desc": "configs[4] (scaled: the synthetic unitig builder needs ~34 B of host RAM per distinct k-mer): "
+                      "synthetic human-like genome, k=51, --bcalm-in"},
 }
+DEFAULT_WORKLOAD = "chr1"  # the largest BASELINE config that fits one GPU and whose input this box can build
 CAP = 16
+OUTPUTS = "GFA + duplicate-kmer bitvector"
+
+
+def config_of(args, world: int) -> dict:
+    """The `config` object: recipe-level keys only, so that both arms print the same one."""
+    w = WORKLOADS[args.workload]
+    scale = w["scale"] if args.scale is None else args.scale
+    return {"workload": args.workload, "description": w["desc"], "k": 51 if w["cfg"] == "human" else 31, "scale": scale,
+            "reader": "--bcalm-in (links -> union-find numbering)" if w["bcalm"] else "--fa-in (k-mer join)",
+            "outputs": OUTPUTS, "candidate_cap": CAP,
+            "l2": "flushed between timed iterations (256 MiB memset); the workload's text alone exceeds L2",
+            "parallelism": f"sources sharded over {world} GPU(s), graph replicated"}
 
 
 def load_peaks() -> tuple[float, str]:
@@ -99,50 +116,77 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_workload(name: str, scale: float | None):
+def make_workload(name: str, scale: float | None, rank: int = 0):
+    """Unitigs of the named recipe (bcalm2-style FASTA text).  Built once per box and cached on disk (tools.cache_dir());
+    under torchrun rank 0 builds and the other ranks wait for the file."""
     import tools
-    cfg, dscale, desc = WORKLOADS[name]
-    scale = dscale if scale is None else scale
+    w = WORKLOADS[name]
+    scale = w["scale"] if scale is None else scale
     t0 = time.time()
-    text, k, info = tools.config_unitigs(cfg, scale)
+    text, k, info = tools.cached_config_unitigs(w["cfg"], scale, wait_for_other=rank != 0)
     info["generate_s"] = round(time.time() - t0, 2)
-    info["description"] = desc
+    info["description"] = w["desc"]
     return text, k, info
 
 
 # ----------------------------------------------------------------------------------------------
 # reference arm: the CPU oracle with every host thread (C++ restatement, not the Rust binary)
 # ----------------------------------------------------------------------------------------------
+ORACLE_PHASES = ("parse", "build", "scan", "dijkstra", "insert", "eulerise", "euler", "break", "bitvector", "write")
+ORACLE_COMPUTE = ("build", "scan", "dijkstra", "insert", "eulerise", "euler", "break", "bitvector")  # SURVEY.md 8d: T_compute
+
+
+def oracle_pass(text: bytes, k: int, bcalm: bool, threads: int):
+    """One whole CPU pass producing exactly the GPU arm's outputs (GFA + bitvector, no FASTA, no C-API arrays).
+    Returns (oracle, wall seconds, phase seconds)."""
+    import oracle
+    o = oracle.Oracle(euler_fast=True, outputs=oracle.Oracle.OUT_GFA | oracle.Oracle.OUT_BITVECTOR)
+    t0 = time.perf_counter()
+    (o.load_bcalm if bcalm else o.load_fasta)(text, k)
+    o.run(threads=threads)
+    wall = time.perf_counter() - t0
+    return o, wall, {n: o.time(n) for n in ORACLE_PHASES}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return  # other ranks exit 0 without work
-    import oracle
-    text, k, info = make_workload(args.workload, args.scale)
+    w = WORKLOADS[args.workload]
+    scale = w["scale"] if args.scale is None else args.scale
+    # bounded sample: the same recipe at a reduced genome length, so that warmup + steps whole passes end within minutes
+    # (a chr1-size pass of the restatement takes ~17 s on 8-16 cores: 25 of them would take 7 minutes)
+    sample_scale = min(scale, w["ref_scale"]) if args.ref_scale is None else args.ref_scale
+    text, k, info = make_workload(args.workload, sample_scale)
     cores = os.cpu_count() or 1
     U = info["unitigs"]
-    times, settled = [], 0
+    times, phases, settled, dj = [], {}, 0, 0.0
     for it in range(args.warmup + args.steps):
-        o = oracle.Oracle(euler_fast=True)
-        t0 = time.perf_counter()
-        o.load_fasta(text, k)
-        o.run(threads=cores)
-        dt = time.perf_counter() - t0
+        o, dt, ph = oracle_pass(text, k, w["bcalm"], cores)
         if it >= args.warmup:
             times.append(dt)
-            settled = o.num("settled")
-            dj = o.time("dijkstra")
+            for n, v in ph.items():
+                phases[n] = phases.get(n, 0.0) + v / args.steps
+            settled, dj = o.num("settled"), o.time("dijkstra")
+        del o
     ms = 1e3 * float(np.mean(times))
     value = U / (ms / 1e3)
+    t_compute = sum(phases[n] for n in ORACLE_COMPUTE)
+    sample = (f"each step = one whole pass (parse -> {OUTPUTS}) over the {args.workload} recipe at scale {sample_scale:g} "
+              f"({U} unitigs, {info['input_bp']} bp); C++ restatement of matchtigs 2.1.9 greedy with the reference's worker scheme "
+              f"on {cores} threads (not the Rust binary, which cannot be built in this image)")
     line = {
         "impl": "reference", "metric": "greedy_matchtig_unitigs_per_sec", "value": value, "unit": "unitigs/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": args.workload, "k": k, **{k_: info[k_] for k_ in ("scale", "unitigs", "distinct_kmers", "input_bp")}},
-        "cpu_baseline": {"value": value, "unit": "unitigs/s", "cores": cores, "kind": "port",
-                         "sample": "whole workload per step; C++ restatement of matchtigs 2.1.9 greedy with the reference's "
-                                   "worker scheme (not the Rust binary, which cannot be built in this image)"},
+        "config": config_of(args, args.gpus),
+        "cpu_baseline": {"value": value, "unit": "unitigs/s", "cores": cores, "kind": "port", "sample": sample,
+                         "sample_scale": sample_scale, "sample_unitigs": U},
         "e2e": {"value": value, "unit": "unitigs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "t_wall_ms": ms, "t_compute_ms": 1e3 * t_compute,
+        "unitigs_per_sec_compute": U / t_compute if t_compute > 0 else None,
+        "phases_ms": {n: 1e3 * v for n, v in phases.items()},
+        "settled_nodes": {"reference_semantics": settled},
         "settled_nodes_per_sec": settled / dj if dj > 0 else None,
     }
     print(json.dumps(line), flush=True)
@@ -166,15 +210,14 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(minutes=40))
 
-    text, k, info = make_workload(args.workload, args.scale)
-    units = mt.Unitigs(text, bcalm=False)
-    U = units.count
-    seq_host = torch.from_numpy(units.seq.copy()).pin_memory()
-    off_host = torch.from_numpy(units.offsets.astype(np.int64)).pin_memory()
-    seq_dev, off_dev = seq_host.cuda(), off_host.cuda()
-    text_host = torch.frombuffer(bytearray(text), dtype=torch.uint8).pin_memory()  # the unitig FASTA file content
+    w = WORKLOADS[args.workload]
+    bcalm = w["bcalm"]
+    text, k, info = make_workload(args.workload, args.scale, rank)
+    text_host = torch.frombuffer(bytearray(text), dtype=torch.uint8).pin_memory()  # the unitig file content, page-locked
+    text_dev = text_host.cuda()                                                   # ... and resident in HBM
     ctx = mt.Context(local_rank)
     ext = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
@@ -212,10 +255,14 @@ def run_ours(args):
     def step(resident: bool):
         """One pass of the hot path.  Returns (gfa, bitvector) on rank 0."""
         if resident:
-            call("graph_build", ctx.build_graph_from_device_sequences, seq_dev.data_ptr(), off_dev.data_ptr(), U, k)
+            # the file content already in HBM: records parsed on the device -> graph
+            call("parse+graph_build", ctx.build_graph_from_text, None, k, bcalm=bcalm, device_ptr=text_dev.data_ptr(),
+                 length=text_dev.numel())
         else:
-            # end to end: raw FASTA bytes in page-locked host memory -> H2D -> records parsed on the device -> graph
-            call("parse+graph_build", ctx.build_graph_from_text, text_host.numpy(), k, bcalm=False)
+            # end to end: raw file bytes in page-locked host memory -> H2D -> parsed on the device -> graph
+            call("parse+graph_build", ctx.build_graph_from_text, text_host.numpy(), k, bcalm=bcalm)
+        dg = ctx.diagnostics()
+        phase_s["(parse, device)"] = phase_s.get("(parse, device)", 0.0) + dg["build_ms"]["parse"] * 1e-3
         if world == 1:
             call("dijkstra", ctx.dijkstra_candidates, CAP, 0, 1)
             call("match", ctx.greedy_match)
@@ -226,7 +273,8 @@ def run_ours(args):
         if rank == 0:
             call("tail", ctx.finish_walks)
             # results land in page-locked host memory owned by the context (zero-copy views)
-            return call("emit_gfa", ctx.assemble_tigs_view, "gfa"), call("emit_bitvector", ctx.dup_bitvector_view)
+            bv = call("emit_bitvector", ctx.dup_bitvector_view)
+            return call("emit_gfa", ctx.assemble_tigs_view, "gfa"), bv
         return None, None
 
     def timed(resident: bool, steps: int, warmup: int):
@@ -234,7 +282,7 @@ def run_ours(args):
             step(resident)
         barrier()
         total_ms, dj_ms, mt_ms, djk_ms, mtk_ms, stats, out = 0.0, 0.0, 0.0, 0.0, 0.0, None, None
-        per_step = []
+        per_step, tail = [], {}
         launches0 = ctx.kernel_launches
         phase_s.clear()
         for _ in range(steps):
@@ -253,6 +301,9 @@ def run_ours(args):
             mt_ms += stats["match_ms"]
             djk_ms += stats["dijkstra_kernel_ms"]
             mtk_ms += stats["match_kernel_ms"]
+            if rank == 0:
+                for n, v in ctx.diagnostics()["tail_ms"].items():
+                    tail[n] = tail.get(n, 0.0) + v / steps
         launches = ctx.kernel_launches - launches0
         t = torch.tensor([total_ms, dj_ms, mt_ms, djk_ms, mtk_ms], dtype=torch.float64, device="cuda")
         if world > 1:
@@ -261,7 +312,7 @@ def run_ours(args):
         per_step.sort()
         stats = dict(stats, dijkstra_kernel_ms=djk_ms / steps, match_kernel_ms=mtk_ms / steps,
                      spread={"min": per_step[0], "median": per_step[len(per_step) // 2], "max": per_step[-1]},
-                     phases_ms={n: 1e3 * v / steps for n, v in phase_s.items()})
+                     phases_ms={n: 1e3 * v / steps for n, v in phase_s.items()}, tail_ms=tail)
         return total_ms / steps, dj_ms / steps, mt_ms / steps, stats, launches, out
 
     sampler = ClockSampler(local_rank)
@@ -280,50 +331,57 @@ def run_ours(args):
 
     if rank == 0:
         gi = ctx.graph_info()
+        U = gi["unitigs"]
         gfa, bv = (x.tobytes() for x in out)
         peak, peak_src = load_peaks()
         # algorithmic bytes of the Dijkstra kernel: 12 B per settled node (row_ptr pair + target probe),
         # 5 B per relaxed short edge (col + weight), 8 B per emitted candidate
         alg_bytes = 12.0 * settled + 5.0 * relaxed + 8.0 * cands
-        # duration: CUDA events around the tier-0 search kernel on the library's stream, averaged over the timed steps
+        # duration: CUDA events around the main search kernel on the library's stream, averaged over the timed steps
         djk_ms = stats["dijkstra_kernel_ms"]
         achieved = alg_bytes / world / (djk_ms * 1e-3) / 1e9 if djk_ms > 0 else 0.0
-        # dram__bytes_read.sum + dram__bytes_write.sum of the kernel's main launch from the committed `ncu --set full`
-        # captures (profiles/round1_ncu_full_dijkstra_thread_main_*.txt); only known for the captured workloads at N=1
-        traffic = NCU_DRAM_BYTES.get((args.workload, float(info["scale"]))) if world == 1 else None
-        sectors = NCU_L2_READ_SECTORS.get((args.workload, float(info["scale"]))) if world == 1 else None
+        key = (args.workload, float(info["scale"]))
+        traffic = NCU_DRAM_BYTES.get(key) if world == 1 else None
+        sectors = NCU_L2_READ_SECTORS.get(key) if world == 1 else None
         sector_gbps = sectors * 32 / (djk_ms * 1e-3) / 1e9 if sectors and djk_ms > 0 else None
-        # cpu baseline: the oracle at 1 thread (deterministic reference semantics), whole workload, once
-        import oracle
-        o = oracle.Oracle(euler_fast=True)
-        t0 = time.perf_counter()
-        o.load_fasta(text, k)
-        o.run(1)
-        cpu_s = time.perf_counter() - t0
+        # cpu baseline: the oracle at 1 thread (deterministic reference semantics), whole workload, once; its outputs are
+        # also what the GPU arm's bytes are compared with
+        o, cpu_s, cpu_ph = oracle_pass(text, k, bcalm, 1)
         identical = (gfa == o.text("gfa")) and (bv == o.text("bitvector"))
+        ref_settled, ref_dj_s = o.num("settled"), o.time("dijkstra")
+        del o
+        # T_compute: graph build from parsed records .. bitvector; T_wall adds parse, H2D/D2H and the GFA
+        ph = stats["phases_ms"]
+        t_compute = ms_res - ph.get("(parse, device)", 0.0) - ph.get("emit_gfa", 0.0)
         line = {
             "metric": "greedy_matchtig_unitigs_per_sec", "value": U / (ms_res * 1e-3), "unit": "unitigs/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_res,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": args.workload, "description": info["description"], "k": k, "scale": info["scale"],
-                       "unitigs": U, "nodes": gi["nodes"], "sources": gi["sources"], "short_edges": gi["short_edges"],
-                       "distinct_kmers": info["distinct_kmers"], "input_bp": info["input_bp"], "candidate_cap": CAP,
-                       "l2": "flushed between timed iterations (256 MiB memset)", "reader": "fa-in semantics (k-mer join)",
-                       "parallelism": f"sources sharded over {world} GPU(s), graph replicated"},
+            "config": config_of(args, world),
+            "workload_sizes": {"unitigs": U, "nodes": gi["nodes"], "sources": gi["sources"], "short_edges": gi["short_edges"],
+                               "distinct_kmers": info["distinct_kmers"], "input_bp": info["input_bp"], "text_bytes": len(text),
+                               "generate_s": info["generate_s"], "cache": info.get("cache")},
+            "t_compute_ms": t_compute, "t_wall_ms": ms_e2e,
+            "unitigs_per_sec_compute": U / (t_compute * 1e-3), "unitigs_per_sec_wall": U / (ms_e2e * 1e-3),
             "ms_per_step_spread_rank0": stats["spread"],
             "phases_ms_rank0": stats["phases_ms"],  # host wall time per library call (each one blocks), mean per step
+            "tail_ms_rank0": stats["tail_ms"],
             "e2e": {"value": U / (ms_e2e * 1e-3), "unit": "unitigs/s", "ms_per_step": ms_e2e, "ms_per_step_spread_rank0": stats_e2e["spread"],
-                    "phases_ms_rank0": stats_e2e["phases_ms"],
-                    "h2d_bytes_per_step": int(text_host.numel()), "input": "unitig FASTA text (parsed on the device)",
+                    "phases_ms_rank0": stats_e2e["phases_ms"], "tail_ms_rank0": stats_e2e["tail_ms"],
+                    "h2d_bytes_per_step": int(text_host.numel()), "input": "unitig file content (parsed on the device)",
                     "host_link": link,
                     "d2h_bytes_per_step": int(len(gfa) + len(bv))},
             "gpu_launches": int(launches),
+            "settled_nodes": {"gpu_kernel": settled, "reference_semantics": ref_settled,
+                              "note": "the GPU searches every source to the candidate cap up front; the reference stops each "
+                                      "search after m+1 targets and skips satisfied sources (SURVEY.md 8d)"},
             "settled_nodes_per_sec": settled / (dj_ms * 1e-3) if dj_ms > 0 else None,
+            "settled_nodes_per_sec_cpu_1thread": ref_settled / ref_dj_s if ref_dj_s > 0 else None,
             "dijkstra": {"ms_per_step": dj_ms, "settled_nodes": settled, "relaxed_edges": relaxed, "candidates": cands,
                          "sources_searched": searched, "kernel_ms_per_step": djk_ms, "match_ms_per_step": match_ms,
                          "match_kernel_ms_per_step": stats["match_kernel_ms"], "match_blocked_retries": stats["match_rounds"],
                          "requery_phases": stats["requery_phases"], "overflow_sources": stats["overflow_sources"]},
-            "roofline": {"kernel": "dijkstra_thread_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"kernel": SEARCH_KERNEL, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes / world,
                          "sector_granular": {"l2_read_sectors_per_launch": sectors, "achieved_GBps": sector_gbps,
@@ -332,11 +390,11 @@ def run_ours(args):
                                              if sector_gbps else None,
                                              "source": "ncu lts__t_sectors_srcunit_tex_op_read.sum of the committed capture x 32 B over "
                                                        "the live kernel time; ceilings from scripts/micro/gather_ceiling.cu"},
-                         "note": "random 32-B-sector gathers along dependent chains; the CSR of this workload fits in L2, so the "
-                                 "kernel is bound by L2 latency x chain depth, not by HBM bandwidth (see DESIGN.md section 4)"},
+                         "note": "random 32-B-sector gathers along dependent chains (see DESIGN.md section 4)"},
             "cpu_baseline": {"value": U / cpu_s, "unit": "unitigs/s", "cores": 1, "kind": "port",
-                             "sample": "whole workload, one run; C++ restatement of matchtigs 2.1.9 greedy at --threads 1 "
-                                       "(not the Rust binary)", "seconds": cpu_s},
+                             "sample": f"whole workload, one pass (parse -> {OUTPUTS}); C++ restatement of matchtigs 2.1.9 greedy at "
+                                       "--threads 1 (not the Rust binary)", "seconds": cpu_s,
+                             "t_compute_ms": 1e3 * sum(cpu_ph[n] for n in ORACLE_COMPUTE), "phases_ms": {n: 1e3 * v for n, v in cpu_ph.items()}},
             "byte_identical_to_oracle": bool(identical),
             "clocks": clocks,
         }
@@ -346,6 +404,7 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+SEARCH_KERNEL = "dijkstra_thread_kernel"
 # (workload, scale) -> DRAM bytes (read + write) of one main launch of dijkstra_thread_kernel, from ncu --set full
 NCU_DRAM_BYTES = {("ecoli", 1.0): 208896 + 0, ("chr1", 0.3): 27804160 + 17134592}
 # same captures: L2 sectors the kernel read (lts__t_sectors_srcunit_tex_op_read.sum), i.e. the sector-granular traffic
@@ -358,11 +417,12 @@ GATHER_CEILING_GBPS = {"hbm_random": 1174.8, "l2_resident": 6663.9}
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="ecoli", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--scale", type=float, default=None)
+    ap.add_argument("--ref-scale", type=float, default=None, help="--impl reference: recipe scale of the timed sample")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -170,9 +170,10 @@ int mtg_assemble_tigs_view(mtg_ctx* ctx, int format, const char** out, uint64_t*
 int mtg_compute_greedytigs_from_sequences(mtg_ctx* ctx, const char* seq_ascii, const uint64_t* offsets,
                                           uint64_t unitigs, uint32_t k, uint32_t cap);
 int mtg_get_search_stats(mtg_ctx* ctx, mtg_search_stats* stats);
-/* Diagnostics of the last run: host-tail phases in ms (degrees, eulerise, adjacency, Euler walk, breaking).
- * match_pending is kept for layout compatibility and stays zero: the matching is one dataflow kernel without rounds. */
-int mtg_get_diagnostics(mtg_ctx* ctx, double tail_ms[5], uint32_t match_pending[48]);
+/* Diagnostics of the last run (either pointer may be NULL): host-tail phases in ms (degrees, eulerise, adjacency,
+ * Euler walk, breaking) and device time of the last graph build in ms: build_ms[0] = H2D copy + record parsing
+ * (mtg_build_graph_from_text only, else 0), build_ms[1] = graph construction proper (pack .. CSR). */
+int mtg_get_diagnostics(mtg_ctx* ctx, double tail_ms[5], double build_ms[2]);
 
 /* ---- host-side record reader ----
  * Splits FASTA / bcalm2 text into the arrays the step API takes; stands where genome-graph's readers stand

@@ -18,6 +18,8 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 CSRC = ROOT / "matchtigs_b200" / "csrc"
 PRODUCT_SO = ROOT / "matchtigs_b200" / "libmatchtigs_b200.so"
+PRODUCT_A = ROOT / "matchtigs_b200" / "libmatchtigs_b200.a"
+NCCL_LINK: list[str] = []  # filled in below if the library is built with its NCCL entry points
 ORACLE_SO = ROOT / "oracle" / "libmtg_oracle.so"
 SYNTH_SO = ROOT / "tools" / "libmtg_synth.so"
 
@@ -80,14 +82,33 @@ def product_sources() -> list[Path]:
 
 
 def build_product(force: bool = False, verbose: bool = False, ptxas_info: bool = False) -> Path:
+    """Compiles every source to an object under build/ (only the stale ones), then links the shared library the
+    Python mirror and the tests load, and archives the same objects into the static library north_star names
+    (``libmatchtigs_b200.a``: what a Rust host links with ``cargo:rustc-link-lib=static=matchtigs_b200``)."""
+    from concurrent.futures import ThreadPoolExecutor
     srcs = product_sources()
-    deps = srcs + sorted(CSRC.glob("*.h")) + sorted(CSRC.glob("*.cuh")) + sorted((ROOT / "include").glob("*.h"))
-    if force or _stale(PRODUCT_SO, deps):
-        cmd = [_nvcc(), *NVCC_FLAGS, "-ccbin", _gxx(), "-I", str(ROOT / "include"), "-I", str(CSRC),
-               "-shared", "-o", str(PRODUCT_SO), *[str(s) for s in srcs], "-lcudart", "-lgomp"]
-        if ptxas_info:
-            cmd[1:1] = ["-Xptxas", "-v"]
-        _run(cmd, verbose or ptxas_info)
+    hdrs = sorted(CSRC.glob("*.h")) + sorted(CSRC.glob("*.cuh")) + sorted((ROOT / "include").glob("*.h"))
+    objdir = ROOT / "build" / "obj"
+    objdir.mkdir(parents=True, exist_ok=True)
+    jobs, objs = [], []
+    for src in srcs:
+        obj = objdir / (src.name + ".o")
+        objs.append(obj)
+        if force or ptxas_info or _stale(obj, [src] + hdrs):
+            cmd = [_nvcc(), *NVCC_FLAGS, "-ccbin", _gxx(), "-I", str(ROOT / "include"), "-I", str(CSRC), "-c", "-o", str(obj), str(src)]
+            if ptxas_info:
+                cmd[1:1] = ["-Xptxas", "-v"]
+            jobs.append(cmd)
+    if jobs:
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
+            list(ex.map(lambda c: _run(c, verbose or ptxas_info), jobs))
+    if jobs or not PRODUCT_SO.exists() or not PRODUCT_A.exists():
+        cuda_lib = str(Path(_nvcc()).resolve().parent.parent / "lib64")
+        _run([_gxx(), "-shared", "-o", str(PRODUCT_SO), *[str(o) for o in objs], "-L", cuda_lib, f"-Wl,-rpath,{cuda_lib}",
+              "-lcudart", "-lgomp", "-lpthread", *NCCL_LINK], verbose)
+        if PRODUCT_A.exists():
+            PRODUCT_A.unlink()
+        _run(["ar", "rcs", str(PRODUCT_A), *[str(o) for o in objs]], verbose)
     return PRODUCT_SO
 
 

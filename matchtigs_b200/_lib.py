@@ -96,7 +96,7 @@ def load() -> C.CDLL:
     l.mtg_assemble_tigs_view.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(u64)]
     l.mtg_compute_greedytigs_from_sequences.argtypes = [vp, vp, vp, u64, u32, u32]
     l.mtg_get_search_stats.argtypes = [vp, C.POINTER(SearchStats)]
-    l.mtg_get_diagnostics.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint32)]
+    l.mtg_get_diagnostics.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     l.mtg_unitigs_parse.argtypes = [C.c_char_p, C.c_size_t, i32, C.POINTER(vp), C.c_char_p, C.c_size_t]
     l.mtg_unitigs_free.argtypes = [vp]
     l.mtg_unitigs_free.restype = None

@@ -211,10 +211,11 @@ class Context:
         return st.as_dict()
 
     def diagnostics(self) -> dict:
-        ms, hist = (C.c_double * 5)(), (C.c_uint32 * 48)()
-        self._check(self._l.mtg_get_diagnostics(self._h, ms, hist))
+        ms, bms = (C.c_double * 5)(), (C.c_double * 2)()
+        self._check(self._l.mtg_get_diagnostics(self._h, ms, bms))
         names = ["degrees", "eulerise", "adjacency", "euler_walk", "breaking"]
-        return {"tail_ms": {n: round(float(v), 3) for n, v in zip(names, ms)}, "match_pending": [int(x) for x in hist if x]}
+        return {"tail_ms": {n: round(float(v), 3) for n, v in zip(names, ms)},
+                "build_ms": {"parse": float(bms[0]), "graph": float(bms[1])}}
 
     @property
     def kernel_launches(self) -> int:

@@ -62,6 +62,7 @@ int mtg_ctx_create(mtg_ctx** out, int device) {
         MTG_CUDA(cudaEventCreate(&ctx->ev1));
         MTG_CUDA(cudaEventCreate(&ctx->ev2));
         MTG_CUDA(cudaEventCreate(&ctx->ev3));
+        for (auto& e : ctx->ev_build) MTG_CUDA(cudaEventCreate(&e));
         cudaDeviceProp prop{};
         MTG_CUDA(cudaGetDeviceProperties(&prop, device));
         ctx->num_sms = prop.multiProcessorCount;
@@ -73,7 +74,7 @@ int mtg_ctx_create(mtg_ctx** out, int device) {
     });
     if (rc != MTG_OK) {
         fprintf(stderr, "matchtigs_b200: context creation failed: %s\n", ctx->err.c_str());
-        delete ctx;
+        mtg_ctx_destroy(ctx);  // also releases the stream and the events created so far
         return rc;
     }
     *out = ctx;
@@ -121,6 +122,8 @@ void mtg_ctx_destroy(mtg_ctx* ctx) {
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ev2) cudaEventDestroy(ctx->ev2);
     if (ctx->ev3) cudaEventDestroy(ctx->ev3);
+    for (auto& e : ctx->ev_build)
+        if (e) cudaEventDestroy(e);
     delete ctx;
 }
 
@@ -299,10 +302,19 @@ int mtg_get_search_stats(mtg_ctx* ctx, mtg_search_stats* stats) {
     });
 }
 
-int mtg_get_diagnostics(mtg_ctx* ctx, double tail_ms[5], uint32_t match_pending[48]) {
+int mtg_get_diagnostics(mtg_ctx* ctx, double tail_ms[5], double build_ms[2]) {
     return guarded(ctx, [&] {
         if (tail_ms) memcpy(tail_ms, ctx->tail_ms, sizeof(ctx->tail_ms));
-        if (match_pending) memcpy(match_pending, ctx->match_hist, sizeof(ctx->match_hist));
+        if (build_ms) {
+            build_ms[0] = build_ms[1] = 0;
+            if (ctx->build_timed) {
+                float a = 0, b = 0;
+                MTG_CUDA(cudaEventSynchronize(ctx->ev_build[2]));
+                MTG_CUDA(cudaEventElapsedTime(&a, ctx->ev_build[0], ctx->ev_build[1]));
+                MTG_CUDA(cudaEventElapsedTime(&b, ctx->ev_build[1], ctx->ev_build[2]));
+                build_ms[0] = a, build_ms[1] = b;
+            }
+        }
     });
 }
 

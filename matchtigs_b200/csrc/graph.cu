@@ -514,6 +514,8 @@ void finish_graph(mtg_ctx* ctx) {
     MTG_CUDA(cudaFreeAsync(d_counters, s));
     MTG_CUDA(cudaFreeAsync(d_tot, s));
     for (DBuf<u32>* b : {&deg_s, &short_flag, &pos, &pos_e, &from_a, &from_b, &eid_a, &eid_b, &src_flag}) b->release(s);
+    MTG_CUDA(cudaEventRecord(ctx->ev_build[2], s));
+    ctx->build_timed = true;
     ctx->have_graph = true;
     ctx->have_cand = ctx->have_triples = ctx->have_walks = false;
     // small graphs prepare the sequential tail on the host: send it its inputs now, behind the build
@@ -529,6 +531,11 @@ void build_graph_from_sequences(mtg_ctx* ctx, const char* seq, const u64* offset
     MTG_REQUIRE(U == 0 || (seq && offsets), MTG_ERR_INVALID, "null sequence input");
     cudaStream_t s = ctx->stream;
     ctx->have_graph = false;
+    ctx->build_timed = false;
+    if (!ctx->in_text_build) {  // no parsing in front of this build
+        MTG_CUDA(cudaEventRecord(ctx->ev_build[0], s));
+        MTG_CUDA(cudaEventRecord(ctx->ev_build[1], s));
+    }
     ctx->k = k;
     ctx->U = U;
     ctx->E = 2 * U;
@@ -608,6 +615,11 @@ void build_graph_from_links(mtg_ctx* ctx, u64 U, const u64* weights, u64 n_links
     MTG_REQUIRE(2 * n_links < 0xFFFFFFFFull, MTG_ERR_UNSUPPORTED, "too many links");
     cudaStream_t s = ctx->stream;
     ctx->have_graph = false;
+    ctx->build_timed = false;
+    if (!ctx->in_text_build) {  // no parsing in front of this build
+        MTG_CUDA(cudaEventRecord(ctx->ev_build[0], s));
+        MTG_CUDA(cudaEventRecord(ctx->ev_build[1], s));
+    }
     ctx->have_seqs = false;
     ctx->k = k;
     ctx->U = U;

@@ -202,6 +202,8 @@ struct mtg_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    cudaEvent_t ev_build[3] = {nullptr, nullptr, nullptr};  // start of the last graph build, end of its parsing, end of the build
+    bool build_timed = false, in_text_build = false;
     float last_kernel_ms = 0;  // tier-0 search kernel of the last run_searches call
     mtg::DevStats h_dstats{};   // host copy of the search counters taken by the last run_searches call ...
     bool h_dstats_final = false;  // ... and whether nothing ran after that copy
@@ -253,7 +255,6 @@ struct mtg_ctx {
     // ---- host tail ----
     std::vector<uint32_t> h_dummy_w;  // weight of dummy edge e at [e - 2U]
     double tail_ms[5] = {0, 0, 0, 0, 0};  // degrees, eulerise, csr, walk, break
-    uint32_t match_hist[48] = {0};        // pending sources per matching round (first phase)
     std::vector<uint32_t> walk_edges;
     std::vector<uint64_t> walk_limits;
     bool have_walks = false;

@@ -175,6 +175,7 @@ void build_graph_from_text(mtg_ctx* ctx, const char* text, u64 L, bool bcalm, u3
     MTG_REQUIRE(L == 0 || text, MTG_ERR_INVALID, "null text");
     MTG_REQUIRE(L < 0xFFFFFFF0ull, MTG_ERR_UNSUPPORTED, "text of 4 GiB or more: parse it in pieces with the host reader");
     cudaStream_t s = ctx->stream;
+    MTG_CUDA(cudaEventRecord(ctx->ev_build[0], s));
     auto& ws = ctx->parse_ws;
     DBuf<u32>& totals = ws.totals;
     const char* d_text = text;
@@ -244,13 +245,17 @@ void build_graph_from_text(mtg_ctx* ctx, const char* text, u64 L, bool bcalm, u3
             default: throw Error{MTG_ERR_INPUT, "sequence shorter than k"};
         }
     }
+    MTG_CUDA(cudaEventRecord(ctx->ev_build[1], s));
+    ctx->in_text_build = true;
     try {
         if (bcalm) build_graph_from_links(ctx, U, weights.p, NL, link_a.p, strand_a.p, link_b.p, strand_b.p, k, seq.p, offsets.p, true, B);
         else build_graph_from_sequences(ctx, seq.p, offsets.p, U, k, true, B);
     } catch (...) {
+        ctx->in_text_build = false;
         cleanup();
         throw;
     }
+    ctx->in_text_build = false;
     cleanup();
 }
 

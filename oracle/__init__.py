@@ -60,10 +60,21 @@ class OracleError(RuntimeError):
 class Oracle:
     """One greedy-matchtig computation on the CPU, following the reference's ``--threads 1`` semantics."""
 
-    def __init__(self, euler_fast: bool = False):
+    OUT_GFA, OUT_FASTA, OUT_BITVECTOR, OUT_CAPI = 1, 2, 4, 8
+
+    def __init__(self, euler_fast: bool = False, outputs: int = 15, **options: int):
+        """`outputs`: which outputs ``run`` produces (bit mask of OUT_*).  `options`: named switches of
+        ``mto_set_option`` (the parity assumptions P1..P7, see the .cpp header)."""
         self._l = lib()
         self._h = C.c_void_p(self._l.mto_create())
-        self._l.mto_set_option(self._h, b"euler_fast", int(euler_fast))
+        self.set_option("euler_fast", int(euler_fast))
+        self.set_option("outputs", int(outputs))
+        for name, value in options.items():
+            self.set_option(name, int(value))
+
+    def set_option(self, name: str, value: int) -> None:
+        if self._l.mto_set_option(self._h, name.encode(), int(value)) != 0:
+            raise KeyError(f"unknown oracle option {name!r}")
 
     def __del__(self):
         if getattr(self, "_h", None):

@@ -228,7 +228,7 @@ struct Stats {
     u64 dijkstra_calls = 0, settled = 0, relaxed = 0, heap_pops = 0, candidates = 0;
     u64 sources = 0, in_nodes = 0, self_mirror_unbalanced = 0;
     u64 breaking_edges = 0, cycles = 0;
-    double t_build = 0, t_scan = 0, t_dijkstra = 0, t_insert = 0, t_eulerise = 0, t_euler = 0, t_break = 0, t_write = 0;
+    double t_parse = 0, t_build = 0, t_scan = 0, t_dijkstra = 0, t_insert = 0, t_eulerise = 0, t_euler = 0, t_break = 0, t_write = 0, t_bitvector = 0;
 };
 
 struct Oracle {
@@ -250,6 +250,8 @@ struct Oracle {
     Stats st;
     std::string err;
     int euler_fast = 0;
+    // which outputs run_greedy produces (bench arms produce exactly what the GPU arm produces): 1 GFA, 2 FASTA, 4 bitvector, 8 C API
+    int outputs = 15;
 };
 
 double now_s() {
@@ -947,13 +949,14 @@ void run_greedy(Oracle& o, u32 threads) {
     o.gfa.clear();
     o.fasta.clear();
     o.bitvec.clear();
-    if (o.have_seqs) {
-        assemble(o, o.gfa, true);
-        assemble(o, o.fasta, false);
-    }
-    bitvector(o, o.bitvec);
-    encode_capi(o);
-    o.st.t_write += now_s() - t1;
+    if (o.have_seqs && (o.outputs & 1)) assemble(o, o.gfa, true);
+    if (o.have_seqs && (o.outputs & 2)) assemble(o, o.fasta, false);
+    double t2 = now_s();
+    if (o.outputs & 4) bitvector(o, o.bitvec);
+    double t3 = now_s();
+    if (o.outputs & 8) encode_capi(o);
+    o.st.t_write += (t2 - t1) + (now_s() - t3);
+    o.st.t_bitvector += t3 - t2;
 }
 
 // L(src): every initially-open in-node within distance k-1 of `src`, in settle order
@@ -988,16 +991,23 @@ const char* mto_error(void* h) { return ((Oracle*)h)->err.c_str(); }
         return -1;                       \
     }
 
+static void reset_keep_options(Oracle& o) {
+    const int ef = o.euler_fast, outs = o.outputs;
+    o = Oracle();
+    o.euler_fast = ef;
+    o.outputs = outs;
+}
+
 // mode 0: --fa-in semantics (k-mer hashing); mode 1: --bcalm-in semantics (links, P6).
 int mto_load_text(void* h, const char* text, size_t len, int k, int mode) {
     MTO_TRY({
         double t0 = now_s();
-        int ef = o.euler_fast;
-        o = Oracle();
-        o.euler_fast = ef;
+        reset_keep_options(o);
         o.k = (u32)k;
         if (k < 2) fail("k must be >= 2");
         ParsedFasta pf = parse_fasta(text, len, mode == 1);
+        o.st.t_parse = now_s() - t0;
+        t0 = now_s();
         o.seqs = std::move(pf.seqs);
         o.have_seqs = true;
         if (mode == 0) {
@@ -1019,9 +1029,7 @@ int mto_load_links(void* h, size_t U, const size_t* weights, size_t n_links, con
                    const size_t* b, const uint8_t* sb, int k) {
     MTO_TRY({
         double t0 = now_s();
-        int ef = o.euler_fast;
-        o = Oracle();
-        o.euler_fast = ef;
+        reset_keep_options(o);
         o.k = (u32)k;
         std::vector<Link> links(n_links);
         for (size_t i = 0; i < n_links; i++) links[i] = Link{(u32)a[i], sa[i], (u32)b[i], sb[i]};
@@ -1035,6 +1043,10 @@ int mto_set_option(void* h, const char* name, int value) {
     Oracle& o = *(Oracle*)h;
     if (!std::strcmp(name, "euler_fast")) {
         o.euler_fast = value;
+        return 0;
+    }
+    if (!std::strcmp(name, "outputs")) {
+        o.outputs = value;
         return 0;
     }
     return -1;
@@ -1094,7 +1106,9 @@ size_t mto_num(void* h, const char* name) {
 double mto_time(void* h, const char* name) {
     Oracle& o = *(Oracle*)h;
     std::string n(name);
+    if (n == "parse") return o.st.t_parse;
     if (n == "build") return o.st.t_build;
+    if (n == "bitvector") return o.st.t_bitvector;
     if (n == "scan") return o.st.t_scan;
     if (n == "dijkstra") return o.st.t_dijkstra;
     if (n == "insert") return o.st.t_insert;

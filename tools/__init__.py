@@ -100,3 +100,52 @@ def config_unitigs(name: str, scale: float = 1.0, threads: int = 0) -> tuple[byt
     text, nk, nu = unitigs(seqs, k, threads)
     return text, k, {"config": name, "scale": scale, "k": k, "distinct_kmers": nk, "unitigs": nu,
                      "input_bp": sum(len(s) for s in seqs)}
+
+
+# ---- on-disk cache of generated unitigs ("write the unitig FASTA once, reuse") ----
+def cache_dir() -> Path:
+    import os
+    d = os.environ.get("MTG_CACHE_DIR")
+    cands = [Path(d)] if d else [Path(__file__).resolve().parent.parent / ".cache", Path("/tmp/mtg_cache")]
+    for c in cands:
+        try:
+            c.mkdir(parents=True, exist_ok=True)
+            probe = c / f".probe{os.getpid()}"
+            probe.write_bytes(b"x")
+            probe.unlink()
+            return c
+        except OSError:
+            continue
+    raise RuntimeError("no writable cache directory")
+
+
+def cached_config_unitigs(name: str, scale: float = 1.0, wait_for_other: bool = False, timeout_s: float = 1800.0):
+    """config_unitigs() behind a disk cache, so that arms / ranks / repeated runs on one box pay for the
+    synthetic compacted-dBG construction once.  With `wait_for_other` the caller does not generate but polls
+    for the file another process (rank 0) is writing."""
+    import json
+    import os
+    import time
+    d = cache_dir()
+    stem = f"{name}_s{scale:g}"
+    fa, meta = d / f"{stem}.unitigs.fa", d / f"{stem}.json"
+    t0 = time.time()
+    while wait_for_other and not meta.exists():
+        if time.time() - t0 > timeout_s:
+            raise TimeoutError(f"waited {timeout_s}s for {meta}")
+        time.sleep(0.5)
+    if meta.exists() and fa.exists():
+        info = json.loads(meta.read_text())
+        if fa.stat().st_size == info.get("text_bytes"):
+            info["cache"] = "hit"
+            return fa.read_bytes(), int(info["k"]), info
+    text, k, info = config_unitigs(name, scale)
+    info["text_bytes"] = len(text)
+    tmp = d / f".{stem}.{os.getpid()}.tmp"
+    tmp.write_bytes(text)
+    os.replace(tmp, fa)
+    tmpm = d / f".{stem}.{os.getpid()}.json.tmp"
+    tmpm.write_text(json.dumps(info))
+    os.replace(tmpm, meta)  # the meta file appears last: its presence means the text is complete
+    info = dict(info, cache="miss")
+    return text, k, info
