@@ -12,8 +12,8 @@
 // before any adjacency exists; the adjacency is then built once as a CSR whose rows are ordered
 // newest edge first (petgraph's iteration order); F keeps the cycle as a circular
 // doubly linked list (rotate == move the head), a FIFO of not-yet-exhausted positions instead of
-// rescanning the cycle, per-node row cursors and a used-edge bitset, which makes it linear in the
-// number of edges with ~4 cache lines touched per edge.
+// rescanning the cycle, and per-edge walk records with a used-slot bitset (WalkRec, mtg_internal.cuh), which makes it
+// linear in the number of edges with one record line touched per step -- prefetched WALK_DEPTH steps ahead.
 #include <sys/mman.h>
 
 #include <algorithm>
@@ -169,21 +169,93 @@ void eulerise(const TailInput& in, const u32* out_deg, const u32* in_deg, HVec<i
     MTG_REQUIRE(ip == ins.size(), MTG_ERR_INTERNAL, "eulerise: in-nodes left over");
 }
 
-// What the walk needs: the row records (mutable cursors), the overflow rows, the endpoints of the original edges
-// (a closed walk always starts at an original edge: every node owns one) and the dummy weights.
+// What the walk needs (see WalkRec in mtg_internal.cuh): the records, the initial used-slot bitset (padding slots and
+// headers of big nodes are marked from the start; the walk marks the rest), node handles and the two slot tables.
 struct WalkInput {
     u32 k;
-    u64 n_nodes, E0, E;
-    const u32 *from, *to;
-    NodeRow* rows;
-    const AdjEntry* ext;
-    const u32* dummy_w;  // weight of dummy edge e at [e - E0]
-    bool hints;          // the rows carry prefetch hints (not worth building while everything is cache-resident)
-    u64 n_matching;      // dummy pairs [0, n_matching) come from the matching, the rest are breaking pairs of weight k
-    bool matching_light; // every matching dummy weighs less than k (always true behind the GPU matching)
+    u64 n_nodes, E0, E, n_slots;
+    const WalkRec* recs;
+    u64* used;               // bitset over slots, 8 spare bytes behind the last slot
+    const u32* handle;       // [N] (host-prepared path; else null and start_handle is set)
+    const u32* slot_edge;    // [n_slots] edge id (NONE32 for padding / headers)
+    const u32* slot_of_edge; // [E0] slot of every original edge (walk starts)
+    const u32* from;         // [E0] from-node of every original edge (host-prepared path)
+    const u32* start_handle; // [E0] handle of the from-node of every original edge (device-prepared path)
+    const u32* dummy_w;      // weight of dummy edge e at [e - E0]
+    bool matching_light;     // every matching dummy weighs less than k (always true behind the GPU matching)
 };
 
 void walk_and_break(const WalkInput& w, TailOutput& out, TailScratch& scratch);
+
+// Host-side record builder (small graphs, the host-only entry, tests): same records as tail_prep.cu builds on the device.
+// `edge_end(e, &from, &to)` yields the end nodes of any original or dummy edge.
+template <class EdgeEnds>
+void build_walk_records(u32 n, u64 E0, u64 E, u32 k, const u32* out_deg, const u32* dummy_w, EdgeEnds&& edge_ends, TailScratch& scratch,
+                        WalkInput& w) {
+    u32* handle = static_cast<u32*>(scratch.handle.ensure(std::max<size_t>(n, 1) * sizeof(u32)));
+    u64 n_slots = 0;
+    for (u32 v = 0; v < n; v++) {
+        handle[v] = walk_handle((u32)n_slots, out_deg[v]);
+        n_slots += walk_cap(out_deg[v]);
+    }
+    MTG_REQUIRE(n_slots < SLOT_MASK, MTG_ERR_UNSUPPORTED, "more than 2^30 edge slots");
+    WalkRec* recs = static_cast<WalkRec*>(scratch.recs.ensure(std::max<u64>(n_slots, 1) * sizeof(WalkRec)));
+    u32* slot_edge = static_cast<u32*>(scratch.slot_edge.ensure(std::max<u64>(n_slots, 1) * sizeof(u32)));
+    u32* slot_of_edge = static_cast<u32*>(scratch.slot_of_edge.ensure(std::max<u64>(E, 1) * sizeof(u32)));
+    const size_t used_words = n_slots / 64 + 2;
+    u64* used = static_cast<u64*>(scratch.used.ensure(used_words * sizeof(u64)));
+    memset(used, 0, used_words * sizeof(u64));
+    memset(slot_edge, 0xFF, n_slots * sizeof(u32));
+    auto mark = [&](u64 s) { used[s >> 6] |= 1ull << (s & 63); };
+    // placing the edges in descending id order leaves every node's slots in iteration order (newest edge first);
+    // `fill` = next free entry slot per node, kept in the (not yet needed) record array of the node's first slot
+    std::vector<u32> fill(n);
+    for (u32 v = 0; v < n; v++) {
+        const u32 d = out_deg[v], base = handle[v] & H_BASE, cap = walk_cap(d);
+        fill[v] = walk_first_slot(handle[v]);
+        if (d > 4) {
+            recs[base].to = d;  // header of a big node
+            mark(base), mark(base + 1);
+        }
+        for (u32 j = fill[v] - base + d; j < cap; j++) mark(base + j);  // padding
+    }
+    for (u64 e = E; e-- > 0;) {
+        u32 f, t;
+        edge_ends((u32)e, &f, &t);
+        const u32 sl = fill[f]++;
+        slot_edge[sl] = (u32)e;
+        slot_of_edge[e] = sl;
+        recs[sl].to = handle[t];
+    }
+    const bool par = n_slots > (1u << 18);
+#pragma omp parallel for schedule(static) if (par)
+    for (i64 sl = 0; sl < (i64)n_slots; sl++) {
+        const u32 e = slot_edge[sl];
+        if (e == NONE32) continue;
+        u32 m = slot_of_edge[e ^ 1u];
+        if (e >= E0) m |= SLOT_DUMMY | (dummy_w[e - E0] >= k ? SLOT_BREAK : 0u);
+        recs[sl].mslot = m;
+    }
+    // hint levels, one after the other; degree of the target = what its handle and header say
+    auto deg_of_handle = [&](u32 h) -> u32 {
+        if (h & H_BIG) return recs[h & H_BASE].to;
+        const u32 base = h & H_BASE, cap = (h & H_FOUR) ? 4u : 2u;
+        u32 d = 0;
+        for (u32 j = 0; j < cap; j++) d += slot_edge[base + j] != NONE32;
+        return d;
+    };
+    for (u32 level = 2; level <= WALK_DEPTH; level++) {
+#pragma omp parallel for schedule(static) if (par)
+        for (i64 sl = 0; sl < (i64)n_slots; sl++)
+            if (slot_edge[sl] != NONE32) walk_fill_hints(recs, (u32)sl, deg_of_handle(recs[sl].to), level);
+    }
+    w.n_slots = n_slots;
+    w.recs = recs;
+    w.used = used;
+    w.handle = handle;
+    w.slot_edge = slot_edge;
+    w.slot_of_edge = slot_of_edge;
+}
 
 void run_tail(const TailInput& in, TailOutput& out, TailScratch& scratch) {
     const u32 n = (u32)in.n_nodes;
@@ -195,9 +267,9 @@ void run_tail(const TailInput& in, TailOutput& out, TailScratch& scratch) {
     out_deg.bind(scratch.out_deg, n, n, true);
     in_deg.bind(scratch.in_deg, n, n, true);
     diff.bind(scratch.diff, n, n, true);
-    // Counting and the adjacency fill below are order-independent, so they run on all host cores
-    // (relaxed atomic increments); only the pairing loop and the walk are inherently sequential.
-    // Small graphs stay on one thread, where a plain increment is ~10x cheaper than a locked one.
+    // Counting is order-independent, so it runs on all host cores for big inputs (relaxed atomic increments); only the
+    // pairing loop and the walk are inherently sequential.  Small graphs stay on one thread, where a plain increment
+    // is ~10x cheaper than a locked one.
     const bool par = E0 > (1u << 18);
     auto bump = [par](u32& x) {
         if (par) return __atomic_fetch_add(&x, 1u, __ATOMIC_RELAXED);
@@ -236,108 +308,90 @@ void run_tail(const TailInput& in, TailOutput& out, TailScratch& scratch) {
         MTG_REQUIRE(ok, MTG_ERR_INTERNAL, "Failed to make the graph Eulerian.");
     }
     double t2 = now_ms();
-    // ---- CSR, rows newest edge first.  Dummy pair j = edges E0+2j (out->in) and E0+2j+1 (mirror(in)->mirror(out)) ----
+    // ---- walk records.  Dummy pair j = edges E0+2j (out->in) and E0+2j+1 (mirror(in)->mirror(out)) ----
     const u64 E = E0 + 2 * pairs.size();
-    MTG_REQUIRE(E < 0xFFFFFFF0ull, MTG_ERR_UNSUPPORTED, "more than 2^32 edges");
+    MTG_REQUIRE(E < SLOT_MASK, MTG_ERR_UNSUPPORTED, "more than 2^30 edges");
     out.dummy_w.resize(2 * pairs.size());
-    HVec<NodeRow> rows;
-    rows.bind(scratch.rows, n, n, false);
-    u64 n_ext = 0;
-    for (u32 v = 0; v < n; v++) {
-        if (out_deg[v] <= ROW_INLINE) {
-            rows[v].cur = 0;  // used as fill cursor first
-            rows[v].end = out_deg[v];
-        } else {
-            rows[v].cur = (u32)n_ext;
-            n_ext += out_deg[v];
-            rows[v].end = (u32)n_ext | ROW_EXT;
-        }
-    }
-    MTG_REQUIRE(n_ext < ROW_EXT, MTG_ERR_UNSUPPORTED, "too many edges at high-degree nodes");
-    HVec<AdjEntry> ext;
-    ext.bind(scratch.ext, n_ext, n_ext, false);
-    NodeRow* rowp = rows.data();
-    AdjEntry* extp = ext.data();
-    auto place = [&](u32 v, AdjEntry a) {
-        NodeRow& r = rowp[v];
-        const u32 pos = par ? __atomic_fetch_add(&r.cur, 1u, __ATOMIC_RELAXED) : r.cur++;
-        if (r.end & ROW_EXT) extp[pos] = a;
-        else r.inl[pos] = a;
-    };
     u32 max_matching_w = 0;
     for (size_t j = 0; j < pairs.size(); j++) {
         out.dummy_w[2 * j] = out.dummy_w[2 * j + 1] = pairs[j].w;
         if (j < in.n_triples) max_matching_w = std::max(max_matching_w, pairs[j].w);
     }
-    if (!par) {
-        // one thread: placing the edges in descending id order leaves every row sorted (newest edge first)
-        for (size_t j = pairs.size(); j-- > 0;) {
-            const Pair& p = pairs[j];
-            const u32 e = (u32)(E0 + 2 * j);
-            place(in.mirror[p.in_node], {e + 1, in.mirror[p.out_node]});
-            place(p.out_node, {e, p.in_node});
-        }
-        for (u64 e = E0; e-- > 0;) place(in.from[e], {(u32)e, in.to[e]});
-        for (u32 v = 0; v < n; v++) {
-            NodeRow& r = rowp[v];
-            r.cur = (r.end & ROW_EXT) ? (r.end & ~ROW_EXT) - od[v] : 0u;
-        }
-    } else {
-#pragma omp parallel for schedule(static)
-        for (i64 j = 0; j < (i64)pairs.size(); j++) {
-            const Pair& p = pairs[j];
-            const u32 e = (u32)(E0 + 2 * j);
-            place(in.mirror[p.in_node], {e + 1, in.mirror[p.out_node]});
-            place(p.out_node, {e, p.in_node});
-        }
-#pragma omp parallel for schedule(static)
-        for (i64 e = 0; e < (i64)E0; e++) place(in.from[e], {(u32)e, in.to[e]});
-        // newest edge first inside every row (descending edge id), and reset the cursors
-        const auto newer = [](const AdjEntry& a, const AdjEntry& b) { return a.edge > b.edge; };
-#pragma omp parallel for schedule(dynamic, 4096)
-        for (i64 v = 0; v < (i64)n; v++) {
-            NodeRow& r = rowp[v];
-            if (r.end & ROW_EXT) {
-                const u32 end = r.end & ~ROW_EXT, begin = end - od[v];
-                std::sort(extp + begin, extp + end, newer);
-                r.cur = begin;
-            } else {
-                if (r.end > 1) std::sort(r.inl, r.inl + r.end, newer);
-                r.cur = 0;
-            }
-        }
-    }
-    const bool hints = n >= TAIL_HOST_PREP_MAX_NODES;
-    if (hints) {
-#pragma omp parallel for schedule(static) if (par)
-        for (i64 v = 0; v < (i64)n; v++) fill_row_hints(rowp, extp, (u32)v);
-    }
+    WalkInput w{in.k, in.n_nodes, E0, E, 0, nullptr, nullptr, nullptr, nullptr, nullptr, in.from, nullptr, out.dummy_w.data(), max_matching_w < in.k};
+    build_walk_records(n, E0, E, in.k, od, out.dummy_w.data(),
+                       [&](u32 e, u32* f, u32* t) {
+                           if (e < E0) {
+                               *f = in.from[e], *t = in.to[e];
+                           } else {
+                               const Pair& p = pairs[(e - E0) >> 1];
+                               if ((e - E0) & 1) *f = in.mirror[p.in_node], *t = in.mirror[p.out_node];
+                               else *f = p.out_node, *t = p.in_node;
+                           }
+                       },
+                       scratch, w);
     double t3 = now_ms();
     out.ms_degrees = t1 - t0;
     out.ms_eulerise = t2 - t1;
     out.ms_csr = t3 - t2;
-    WalkInput w{in.k, in.n_nodes, E0, E, in.from, in.to, rows.data(), ext.data(), out.dummy_w.data(), hints, in.n_triples, max_matching_w < in.k};
     walk_and_break(w, out, scratch);
 }
 
 // ---- F + G ----
 void walk_and_break(const WalkInput& in, TailOutput& out, TailScratch& scratch) {
     const u64 E0 = in.E0, E = in.E;
-    NodeRow* rows = in.rows;
-    const AdjEntry* ext = in.ext;
+    const WalkRec* const recs = in.recs;
+    u64* const used = in.used;
     double t3 = now_ms();
-    HVec<u64> used;
-    used.bind(scratch.used, (E + 63) / 64 + 1, (E + 63) / 64 + 1, true);
-    auto is_used = [&](u32 e) { return (used[e >> 6] >> (e & 63)) & 1ull; };
-    auto mark_pair = [&](u32 e) { used[e >> 6] |= 3ull << (e & 62); };  // e and e^1 share a word
-    // The cycle under construction: element i = (q_edge[i], q_from[i]).  Every extension appends a contiguous run
-    // (creation order == the order in which positions are scanned for leftover out-edges).  A run created while
-    // position i was the head sits, in cycle order, immediately before element i ("push_back on the rotated
-    // vector"); all runs created at i are consecutive, so i owns one block [begin, end) of later elements.  Heads are
-    // visited in ascending position, so `children` stays sorted.  Cycle order == in-order expansion of this tree --
-    // a short list of slices of q_edge, because re-roots are rare (about 100 per million steps).
-    HVec<u32> q_edge, q_from;
-    q_edge.bind(scratch.queue, E / 2 + 16, 0, false);
+    // bits of the (up to 4) slots of a small node.  Loads and marks use the same aligned 64-bit words, so a load right
+    // behind a mark of the same word is served by store forwarding (a byte store under a wider load is not).
+    auto slot_bits = [&](u32 base) -> u32 {
+        const u32 sh = base & 63;
+        u64 x = used[base >> 6] >> sh;
+        if (sh > 60) x |= used[(base >> 6) + 1] << (64 - sh);  // four slots starting at bit 62
+        return (u32)x;
+    };
+    auto mark = [&](u32 s) { used[s >> 6] |= 1ull << (s & 63); };
+    auto is_used = [&](u32 s) { return (u32)(used[s >> 6] >> (s & 63)) & 1u; };
+    bool more = false;  // set by first_unused: does the node own further unused slots behind the returned one?
+    // first unused slot of the node with handle h (NONE32: exhausted)
+    auto first_unused = [&](u32 h) -> u32 {
+        const u32 base = h & H_BASE;
+        if (!(h & H_BIG)) {
+            const u32 mask = (h & H_FOUR) ? 15u : 3u;
+            const u32 free_bits = ~slot_bits(base) & mask;
+            more = (free_bits & (free_bits - 1)) != 0;
+            return free_bits ? base + (u32)__builtin_ctz(free_bits) : NONE32;
+        }
+        const u32 d = recs[base].to;
+        u32 first = NONE32;
+        more = false;
+        for (u32 s = base + 2; s < base + 2 + d; s++)
+            if (!is_used(s)) {
+                if (first == NONE32) first = s;
+                else {
+                    more = true;
+                    break;
+                }
+            }
+        return first;
+    };
+    // the slot the node with handle h would hand out next, if the walk can tell without its records (small nodes)
+    auto peek = [&](u32 h, u32* j) -> u32 {
+        if (h & H_BIG) return NONE32;
+        const u32 base = h & H_BASE, mask = (h & H_FOUR) ? 15u : 3u;
+        const u32 free_bits = ~slot_bits(base) & mask;
+        if (!free_bits) return NONE32;
+        *j = (u32)__builtin_ctz(free_bits);
+        return base + *j;
+    };
+    // The cycle under construction: element i = (q_slot[i] = slot | flags, q_from[i] = handle of the node it leaves).
+    // Every extension appends a contiguous run (creation order == the order in which positions are scanned for leftover
+    // out-edges).  A run created while position i was the head sits, in cycle order, immediately before element i
+    // ("push_back on the rotated vector"); all runs created at i are consecutive, so i owns one block [begin, end) of later
+    // elements.  Heads are visited in ascending position, so `children` stays sorted.  Cycle order == in-order expansion
+    // of this tree -- a short list of slices of q_slot, because re-roots are rare (about 100 per million steps).
+    HVec<u32> q_slot, q_from;
+    q_slot.bind(scratch.queue, E / 2 + 16, 0, false);
     q_from.bind(scratch.cyc, E / 2 + 16, 0, false);
     struct Child {
         u32 pos, begin, end;
@@ -352,87 +406,97 @@ void walk_and_break(const WalkInput& in, TailOutput& out, TailScratch& scratch) 
         size_t ci, ce;   // children of this block: children[ci, ce)
     };
     std::vector<Frame> stack;
-    bool more = false;          // set by first_unused: does the row hold further entries behind the returned one?
-    const u32* hint = nullptr;  // set by first_unused: prefetch hints of the returned entry (inline rows only)
-    auto first_unused = [&](u32 v) -> const AdjEntry* {
-        NodeRow& r = rows[v];
-        if (!(r.end & ROW_EXT)) {
-            while (r.cur < r.end && is_used(r.inl[r.cur].edge)) r.cur++;
-            more = r.cur + 1 < r.end;
-            hint = r.hint[r.cur < r.end ? r.cur : 0];
-            return r.cur < r.end ? &r.inl[r.cur] : nullptr;
-        }
-        const u32 end = r.end & ~ROW_EXT;
-        while (r.cur < end && is_used(ext[r.cur].edge)) r.cur++;
-        more = r.cur + 1 < end;
-        hint = nullptr;
-        return r.cur < end ? &ext[r.cur] : nullptr;
-    };
-    const bool use_hints = in.hints && !getenv("MTG_TAIL_NOHINT");
+    const bool use_hints = !getenv("MTG_TAIL_NOHINT");
     // Positions whose from-node may still own an unused out-edge, in cycle order from the head.  A position is only
-    // recorded if its row had entries left when the walk passed (exhaustion is permanent), which skips about half of
-    // the re-root probes -- each one a cache miss.
+    // recorded if its node had slots left when the walk passed (exhaustion is permanent), which skips about half of
+    // the re-root probes.
     HVec<u32> cand;
-    cand.bind(scratch.cand, E / 2 + 16, 0, false);
-    out.walk_edges.clear();
+    cand.bind(scratch.cand, E + 16, 0, false);  // one per step at most, plus one per run
+    std::vector<u32> walk_slots;  // output pieces as slots; translated to edge ids at the end (independent gathers)
+    walk_slots.reserve(E / 2);
     out.walk_limits.clear();
-    out.walk_edges.reserve(E / 2);
     double ms_break = 0;
-    // Dummy weights without a lookup: breaking dummies (pairs >= n_matching) weigh exactly k; matching dummies weigh
-    // their distance, which is below k unless a caller of the host-only entry supplied something else (`light`).
-    const u32 brk_lo = (u32)(E0 + 2 * in.n_matching);
     const bool light = in.matching_light;
-    auto is_dummy = [&](u32 e) { return e >= E0; };
-    auto weight_of = [&](u32 e) { return e >= brk_lo ? in.k : in.dummy_w[e - E0]; };
-    auto breaks = [&](u32 e) { return e >= brk_lo || (!light && in.dummy_w[e - E0] >= in.k); };  // e is a dummy
-    for (u64 e0 = 0; e0 < E; e0++) {
-        if (is_used((u32)e0)) continue;
-        // one closed walk per component, started at the lowest unused edge id
+    auto is_dummy = [&](u32 q) { return (q & SLOT_DUMMY) != 0; };
+    auto weight_of = [&](u32 q) { return (q & SLOT_BREAK) ? in.k : in.dummy_w[in.slot_edge[q & SLOT_MASK] - E0]; };  // q is a dummy
+    auto breaks = [&](u32 q) { return (q & SLOT_BREAK) != 0; };
+    u64 steps_total = 0;
+    for (u64 e0 = 0; e0 < E0 && steps_total < E / 2; e0++) {
+        if (is_used(in.slot_of_edge[e0])) continue;
+        // one closed walk per component, started at the lowest unused edge id (every node owns an original edge, so the
+        // lowest unused edge of a component is never a dummy)
         size_t cf = 0;
-        q_edge.clear();
+        q_slot.clear();
         q_from.clear();
         cand.clear();
         children.clear();
-        // every node owns an original edge, so the lowest unused edge of a component is never a dummy
-        MTG_REQUIRE(e0 < E0, MTG_ERR_INTERNAL, "closed walk would start at a dummy edge");
-        u32 start_edge = (u32)e0, start_from = in.from[e0], start_to = in.to[e0];
+        u32 start_slot = in.slot_of_edge[e0], start_from = in.start_handle ? in.start_handle[e0] : in.handle[in.from[e0]];
         u32 head_idx = 0;  // position of the element the (rotated) cycle vector currently starts with
         u32 n0 = 0;        // length of the initial closed walk == the root block [0, n0)
         bool rooted = false;
         for (;;) {
-            mark_pair(start_edge);
-            cand.push_back((u32)q_edge.size());  // a walk start is always probed again
-            q_edge.push_back(start_edge);
-            q_from.push_back(start_from);
-            u32 cur_node = start_to;
-            for (const AdjEntry* a; (a = first_unused(cur_node)) != nullptr;) {
-                __builtin_prefetch(&rows[a->to]);
-                if (hint && use_hints) {  // two steps ahead: the likely successors of a->to
-                    __builtin_prefetch(&rows[hint[0]]);
-                    __builtin_prefetch(&rows[hint[1]]);
+            cand.push_back((u32)q_slot.size());  // a walk start is always probed again
+            u32 s = start_slot, from_h = start_from;
+            // What the walk expects two, three and four steps from now (slot, and its index inside its node), carried
+            // from step to step: as long as the next slot is the one expected, only the deepest level has to be worked out.
+            u32 S2 = NONE32, S3 = NONE32, S4 = NONE32, J3 = 0, J4 = 0;
+            while (s != NONE32) {
+                const WalkRec& r = recs[s];
+                const u32 ms = r.mslot;
+                mark(s);
+                mark(ms & SLOT_MASK);
+                q_slot.push_back(s | (ms & ~SLOT_MASK));
+                q_from.push_back(from_h);
+                const u32 c = r.to;
+                const u32 nxt = first_unused(c);  // the next step is certain
+                cand.p[cand.n] = (u32)q_slot.size();
+                cand.n += more;
+                // The steps after it are worked out from the used bits of the nodes ahead, whose handles this record
+                // carries: one prefetch per level instead of a fan-out over all candidates.
+                const u32 j1 = nxt - (c & H_BASE);  // garbage for NONE32: >= 2
+                if (use_hints && j1 < 2 && !(c & H_BIG)) {
+                    u32 s2, s3 = NONE32, s4 = NONE32, j2 = 2, j3 = 2, j4 = 2;
+                    if (nxt == S2 && S3 != NONE32 && S4 != NONE32 && (J3 | J4) < 2) {
+                        s2 = S3, j2 = J3, s3 = S4, j3 = J4;
+                    } else {
+                        __builtin_prefetch(&recs[nxt]);
+                        s2 = peek(r.h2[j1], &j2);
+                        if (s2 != NONE32) {
+                            __builtin_prefetch(&recs[s2]);
+                            if (j2 < 2) {
+                                s3 = peek(r.h3[2 * j1 + j2], &j3);
+                                if (s3 != NONE32) __builtin_prefetch(&recs[s3]);
+                            }
+                        }
+                    }
+#if MTG_WALK_DEPTH >= 4
+                    if (s3 != NONE32 && j3 < 2 && j2 < 2) {
+                        s4 = peek(r.h4[4 * j1 + 2 * j2 + j3], &j4);
+                        if (s4 != NONE32) __builtin_prefetch(&recs[s4]);
+                    }
+#endif
+                    S2 = s2, S3 = s3, S4 = s4, J3 = j3, J4 = j4;
+                } else {
+                    if (nxt != NONE32) __builtin_prefetch(&recs[nxt]);
+                    S2 = S3 = S4 = NONE32;
                 }
-                mark_pair(a->edge);
-                if (more) cand.push_back((u32)q_edge.size());
-                q_edge.push_back(a->edge);
-                q_from.push_back(cur_node);
-                cur_node = a->to;
+                from_h = c;
+                s = nxt;
             }
-            if (rooted) children.back().end = (u32)q_edge.size();  // the run just appended belongs to the head's block
-            else n0 = (u32)q_edge.size();
+            if (rooted) children.back().end = (u32)q_slot.size();  // the run just appended belongs to the head's block
+            else n0 = (u32)q_slot.size();
             // re-root at the first cycle position (from the head) whose from-node still has an unused out-edge
             bool found = false;
             while (cf < cand.size()) {
-                if (cf + 12 < cand.size()) __builtin_prefetch(&rows[q_from[cand[cf + 12]]]);  // independent misses: overlap them
                 const u32 qf = cand[cf];
-                const AdjEntry* a = first_unused(q_from[qf]);
-                if (a) {
+                const u32 a = first_unused(q_from[qf]);
+                if (a != NONE32) {
                     head_idx = qf;  // rotate_left(position)
                     rooted = true;
                     if (children.empty() || children.back().pos != qf)  // first run spliced before qf
-                        children.push_back({qf, (u32)q_edge.size(), (u32)q_edge.size()});
-                    start_edge = a->edge;
+                        children.push_back({qf, (u32)q_slot.size(), (u32)q_slot.size()});
+                    start_slot = a;
                     start_from = q_from[qf];
-                    start_to = a->to;
                     found = true;
                     break;
                 }
@@ -441,8 +505,9 @@ void walk_and_break(const WalkInput& in, TailOutput& out, TailScratch& scratch) 
             if (!found) break;
         }
         double tb = now_ms();
-        const size_t len = q_edge.size();
-        // in-order expansion of the block tree into slices of q_edge; the root block is the initial closed walk [0, n0)
+        const size_t len = q_slot.size();
+        steps_total += len;
+        // in-order expansion of the block tree into slices of q_slot; the root block is the initial closed walk [0, n0)
         const auto child_range = [&](u32 b, u32 e, size_t* ci, size_t* ce) {
             const auto lt = [](const Child& c, u32 v) { return c.pos < v; };
             *ci = std::lower_bound(children.begin(), children.end(), b, lt) - children.begin();
@@ -480,7 +545,7 @@ void walk_and_break(const WalkInput& in, TailOutput& out, TailScratch& scratch) 
         // G. greedytigs/mod.rs:736-788: start at the heaviest dummy (the first one on ties, strict `>`), cut at every dummy
         // of weight >= k and at a dummy in position 0.  Nothing is rotated or copied: pieces go straight from the slices
         // to the output.
-        const u32* qe = q_edge.data();
+        const u32* qe = q_slot.data();
         size_t rot_s = 0;
         u32 rot_o = 0, best_w = 0;
         for (size_t si = 0; si < order.size(); si++) {
@@ -489,6 +554,7 @@ void walk_and_break(const WalkInput& in, TailOutput& out, TailScratch& scratch) 
             for (u32 j = sl.b; j < sl.e; j++) {
                 const u32 x = qe[j];
                 if (!is_dummy(x)) continue;
+                if (light && !breaks(x) && best_w >= in.k) continue;
                 const u32 w = weight_of(x);
                 if (w > best_w) {
                     best_w = w;
@@ -503,15 +569,14 @@ void walk_and_break(const WalkInput& in, TailOutput& out, TailScratch& scratch) 
             if (done) break;
         }
         // one streaming copy: every element except the cutting dummies goes to the output, in order
-        std::vector<u32>& we = out.walk_edges;
-        const size_t base = we.size();
-        we.resize(base + len);
-        u32* wp = we.data() + base;
+        const size_t base = walk_slots.size();
+        walk_slots.resize(base + len);
+        u32* wp = walk_slots.data() + base;
         u32* piece = wp;  // start of the piece being collected
         auto close = [&] {
             if (wp == piece) return;
-            MTG_REQUIRE(*piece < E0, MTG_ERR_INTERNAL, "walk starts with a dummy edge");
-            out.walk_limits.push_back((u64)(wp - we.data()));
+            MTG_REQUIRE(!is_dummy(*piece), MTG_ERR_INTERNAL, "walk starts with a dummy edge");
+            out.walk_limits.push_back((u64)(wp - walk_slots.data()));
             piece = wp;
         };
         bool first = true;
@@ -533,13 +598,26 @@ void walk_and_break(const WalkInput& in, TailOutput& out, TailScratch& scratch) 
         emit_range(order[rot_s].b, order[rot_s].b + rot_o);
         if (wp != piece && is_dummy(wp[-1])) wp--;  // a trailing (light) dummy is dropped
         close();
-        we.resize((size_t)(wp - we.data()));
+        walk_slots.resize((size_t)(wp - walk_slots.data()));
         out.cycles++;
         ms_break += now_ms() - tb;
     }
+    // E. (greedytigs/mod.rs:708-715) every edge pair was walked exactly once, or the graph was not Eulerian after all
+    MTG_REQUIRE(steps_total == E / 2, MTG_ERR_INTERNAL, "Failed to make the graph Eulerian (the closed walks do not cover every edge).");
+    double tt = now_ms();
+    // slots -> edge ids: independent gathers, spread over the host cores
+    out.walk_edges.resize(walk_slots.size());
+    {
+        const u32* ws = walk_slots.data();
+        u32* we = out.walk_edges.data();
+        const u32* se = in.slot_edge;
+        const i64 n = (i64)walk_slots.size();
+#pragma omp parallel for schedule(static) if (n > (1 << 16))
+        for (i64 i = 0; i < n; i++) we[i] = se[ws[i] & SLOT_MASK];
+    }
     double t4 = now_ms();
-    out.ms_break = ms_break;
-    out.ms_walk = t4 - t3 - ms_break;
+    out.ms_break = ms_break + (t4 - tt);
+    out.ms_walk = t4 - t3 - out.ms_break;
 }
 
 }  // namespace
@@ -668,24 +746,13 @@ void finish_walks(mtg_ctx* ctx) {
     eulerise_sparse(ctx->k, lo, breaking);
     const u64 n_break = breaking.size() / 2;
     double t1 = now_ms();
-    // adjacency rows on the device, DMA into the walk's arenas; endpoints of the original edges for the walk starts
-    // DMA lands in page-locked staging memory; the walk then works on a copy inside its huge-page arena
-    // (page-locking the arena itself made the walk ~40 % slower: the pinned mapping loses the huge pages)
-    NodeRow* rows_stage = ctx->tail_stage[2].as<NodeRow>(N + 1);
-    u32* from = ctx->tail_stage[0].as<u32>(E0 + 1);
-    u32* to = ctx->tail_stage[1].as<u32>(E0 + 1);
-    if (E0) {
-        MTG_CUDA(cudaMemcpyAsync(from, ctx->edge_from.p, E0 * sizeof(u32), cudaMemcpyDeviceToHost, s));
-        MTG_CUDA(cudaMemcpyAsync(to, ctx->edge_to.p, E0 * sizeof(u32), cudaMemcpyDeviceToHost, s));
-    }
-    u64 n_ext = 0, P = 0;
-    tail_build_rows(ctx, breaking.data(), n_break, rows_stage, ctx->tail_stage[3], &n_ext, &P);
-    MTG_CUDA(cudaStreamSynchronize(s));
-    NodeRow* rows = static_cast<NodeRow*>(scratch.rows.ensure(std::max<u64>(N, 1) * sizeof(NodeRow)));
-    AdjEntry* ext = static_cast<AdjEntry*>(scratch.ext.ensure(std::max<u64>(n_ext, 1) * sizeof(AdjEntry)));
-    // copied in cache-sized chunks: one big memcpy would use non-temporal stores and leave the rows cold in
-    // DRAM, while the walk is a latency chain that runs ~1.5x faster when the last-level cache holds them.
-    // Rows that exceed any last-level cache anyway are copied by a few threads instead.
+    // walk records on the device (includes the Eulerian check), DMA into page-locked staging
+    TailRecords tr;
+    tail_build_records(ctx, breaking.data(), n_break, &tr);
+    const u64 P = tr.n_pairs;
+    (void)N;
+    // The walk works on a copy inside its huge-page arena (page-locking the arena itself loses the huge pages); copied in
+    // cache-sized chunks by a few threads: one big memcpy would use non-temporal stores and leave everything cold.
     auto warm_copy = [](void* dst, const void* src, size_t bytes) {
         const size_t chunk = 256 << 10;
         const i64 n_chunks = (i64)((bytes + chunk - 1) / chunk);
@@ -695,20 +762,28 @@ void finish_walks(mtg_ctx* ctx) {
             memcpy((char*)dst + o, (const char*)src + o, std::min(chunk, bytes - o));
         }
     };
-    warm_copy(rows, rows_stage, N * sizeof(NodeRow));
-    warm_copy(ext, ctx->tail_stage[3].p, n_ext * sizeof(AdjEntry));
+    const WalkRec* recs = tr.recs;
+    if (!getenv("MTG_TAIL_NOCOPY")) {
+        WalkRec* arena = static_cast<WalkRec*>(scratch.recs.ensure(std::max<u64>(tr.n_slots, 1) * sizeof(WalkRec)));
+        warm_copy(arena, tr.recs, tr.n_slots * sizeof(WalkRec));
+        recs = arena;
+    }
+    const size_t used_bytes = (tr.n_slots / 64 + 2) * sizeof(u64);
+    u64* used = static_cast<u64*>(scratch.used.ensure(used_bytes));
+    memcpy(used, tr.used0, used_bytes);
     // dummy weights: matching dummies carry their distance, breaking dummies weigh k
     TailOutput out;
     out.dummy_w.resize(2 * P);
-    const u32* tr = ctx->h_triples.data();
+    const u32* trp = ctx->h_triples.data();
     u32 max_matching_w = 0;
     for (u64 j = 0; j < ctx->n_triples; j++) {
-        out.dummy_w[2 * j] = out.dummy_w[2 * j + 1] = tr[3 * j + 2];
-        max_matching_w = std::max(max_matching_w, tr[3 * j + 2]);
+        out.dummy_w[2 * j] = out.dummy_w[2 * j + 1] = trp[3 * j + 2];
+        max_matching_w = std::max(max_matching_w, trp[3 * j + 2]);
     }
     for (u64 j = ctx->n_triples; j < P; j++) out.dummy_w[2 * j] = out.dummy_w[2 * j + 1] = ctx->k;
     double t2 = now_ms();
-    WalkInput w{ctx->k, N, E0, E0 + 2 * P, from, to, rows, ext, out.dummy_w.data(), true, ctx->n_triples, max_matching_w < ctx->k};
+    WalkInput w{ctx->k, N, E0, E0 + 2 * P, tr.n_slots, recs, used, nullptr, tr.slot_edge, tr.slot_of_edge, nullptr, tr.handle,
+                out.dummy_w.data(), max_matching_w < ctx->k};
     walk_and_break(w, out, scratch);
     ctx->walk_edges.swap(out.walk_edges);
     ctx->walk_limits.swap(out.walk_limits);

@@ -122,44 +122,50 @@ struct PinnedBuf {
     }
 };
 
-// Adjacency record of the host Euler walk, built either on the host or on the device (tail_prep.cu).
-struct AdjEntry {
-    u32 edge, to;
+// ---- records of the host Euler walk (built on the device by tail_prep.cu, or on the host for small graphs) ----
+// Every out-edge of every node owns one slot; the slots of a node are consecutive, in petgraph's iteration order
+// (newest edge first).  A node is addressed by its HANDLE: first slot (even) | H_FOUR (four slots instead
+// of two) | H_BIG (more than four out-edges: slot `base` is a header whose `to` holds the degree, entries start at
+// base + 2).  Which slots are used up lives in a bitset over slots (padding slots are marked from the start), so "first
+// unused out-edge of node h" is one unaligned 64-bit load and a count-trailing-zeros -- for ANY node whose handle is
+// known, without touching its records.  That is what the records exploit: the walk is one dependent cache miss per
+// step, and a record carries the handles of the nodes 2 .. WALK_DEPTH steps ahead along the first two slots of every
+// node on the way, so the walk can work out exactly which record it will need WALK_DEPTH steps from now and prefetch
+// that one line (instead of fanning out over 2^depth candidates).
+#ifndef MTG_WALK_DEPTH
+#define MTG_WALK_DEPTH 4
+#endif
+constexpr u32 WALK_DEPTH = MTG_WALK_DEPTH;
+constexpr u32 H_BIG = 0x80000000u, H_FOUR = 1u, H_BASE = 0x7FFFFFFEu;
+constexpr u32 SLOT_MASK = 0x3FFFFFFFu, SLOT_DUMMY = 0x40000000u, SLOT_BREAK = 0x80000000u;
+struct alignas(MTG_WALK_DEPTH >= 4 ? 64 : 32) WalkRec {
+    u32 to;     // handle of the node this edge leads to
+    u32 mslot;  // slot of the mirror edge | SLOT_DUMMY | SLOT_BREAK (dummy of weight >= k)
+    u32 h2[2];  // handles two steps ahead: `to`'s slots 0 and 1
+    u32 h3[4];  // three steps ahead: [2 * j1 + j2]
+#if MTG_WALK_DEPTH >= 4
+    u32 h4[8];  // four steps ahead: [4 * j1 + 2 * j2 + j3]
+#endif
 };
-// One cache line per node: row cursor + up to three out-edges inline (newest edge first), so that stepping
-// through a node touches a single line.  Rows with more than three edges live in `ext`.
-// hint[i] = targets of the first two out-edges of node inl[i].to: the walk is one dependent cache miss per step, and
-// the hints let it prefetch the line it will most likely need two steps ahead while the next one is still in flight.
-constexpr u32 ROW_INLINE = 3;
-constexpr u32 ROW_EXT = 0x80000000u;
-struct alignas(64) NodeRow {
-    u32 cur, end;  // next position to inspect / end of the row (ROW_EXT flag: positions refer to `ext`)
-    AdjEntry inl[ROW_INLINE];
-    u32 hint[ROW_INLINE][2];
-    u32 pad[2];
-};
-static_assert(sizeof(NodeRow) == 64, "one cache line per node");
-
-// Fills the prefetch hints of row v (rows and cursors must be final).  Shared by the device and the host row builders.
-__host__ __device__ inline void fill_row_hints(NodeRow* rows, const AdjEntry* ext, u32 v) {
-    NodeRow& r = rows[v];
-    const u32 n = (r.end & ROW_EXT) ? 0u : r.end;
-    for (u32 i = 0; i < ROW_INLINE; i++) {
-        u32 h0 = v, h1 = v;
-        if (i < n) {
-            const u32 w = r.inl[i].to;
-            const NodeRow& t = rows[w];
-            h0 = h1 = w;
-            if (t.end & ROW_EXT) {  // more than ROW_INLINE entries
-                h0 = ext[t.cur].to;
-                h1 = ext[t.cur + 1].to;
-            } else if (t.end) {
-                h0 = t.inl[0].to;
-                h1 = t.end > 1 ? t.inl[1].to : h0;
-            }
-        }
-        r.hint[i][0] = h0;
-        r.hint[i][1] = h1;
+static_assert(sizeof(WalkRec) == (MTG_WALK_DEPTH >= 4 ? 64 : 32), "record size");
+__host__ __device__ inline u32 walk_cap(u32 d) { return d <= 2 ? 2u : d <= 4 ? 4u : 2u + ((d + 1) & ~1u); }
+__host__ __device__ inline u32 walk_handle(u32 base, u32 d) { return base | ((d > 2 && d <= 4) ? H_FOUR : 0u) | (d > 4 ? H_BIG : 0u); }
+// first entry slot and entry count of node h given its degree (entries of a big node sit behind its header pair)
+__host__ __device__ inline u32 walk_first_slot(u32 h) { return (h & H_BASE) + ((h & H_BIG) ? 2u : 0u); }
+// Level t+1 of the hints of record r from level t of the records of `to`'s first two slots (levels are built one
+// after the other over all records).  `to_deg` = out-degree of the node r leads to.
+__host__ __device__ inline void walk_fill_hints(WalkRec* recs, u32 s, u32 to_deg, u32 level) {
+    WalkRec& r = recs[s];
+    const u32 c0 = walk_first_slot(r.to);
+    for (u32 j = 0; j < 2; j++) {
+        const bool have = j < to_deg;
+        const WalkRec& c = recs[c0 + (have ? j : 0u)];
+        if (level == 2) r.h2[j] = have ? c.to : r.to;
+        if (level == 3) r.h3[2 * j] = c.h2[0], r.h3[2 * j + 1] = c.h2[1];
+#if MTG_WALK_DEPTH >= 4
+        if (level == 4)
+            for (u32 x = 0; x < 4; x++) r.h4[4 * j + x] = c.h3[x];
+#endif
     }
 }
 
@@ -177,7 +183,7 @@ struct HugeBuf {
     ~HugeBuf() { release(); }
 };
 struct TailScratch {
-    HugeBuf out_deg, in_deg, diff, rows, ext, used, queue, cand, cyc;
+    HugeBuf out_deg, in_deg, diff, recs, used, queue, cand, cyc, slot_edge, slot_of_edge, handle;
 };
 // Nodes still unbalanced after the matching, ascending node id (device compaction, tail_prep.cu).
 // partner = position of the node's mirror in the opposite list.
@@ -263,7 +269,8 @@ struct mtg_ctx {
     mtg::DBuf<mtg::u32> d_dummy_w;    // weights of dummy edges, index = edge id - 2U
 
     mtg::PinnedBuf text_stage[3];     // bitvector / GFA / FASTA bytes, valid until the next call of the same kind
-    mtg::PinnedBuf tail_stage[4];     // edge_from, edge_to, node rows, overflow rows: DMA targets of the host tail
+    mtg::PinnedBuf tail_stage[6];     // DMA targets of the host tail (graph arrays for the host-prepared path; walk records,
+                                      // slot tables and the initial bitset for the device-prepared path)
     mtg::TailScratch tail_scratch;    // cached working arrays of the host tail
 
     mtg_search_stats stats{};
@@ -321,7 +328,14 @@ u64 assemble_tigs(mtg_ctx* ctx, int format, char* out, u64 cap, bool size_only, 
 // ---- host tail (host_tail.cpp) and its device-side preparation (tail_prep.cu) ----
 void finish_walks(mtg_ctx* ctx);
 void tail_leftover(mtg_ctx* ctx, TailLeftover& lo);
-void tail_build_rows(mtg_ctx* ctx, const u32* breaking_pairs, u64 n_break, NodeRow* h_rows, PinnedBuf& ext_stage, u64* n_ext_out,
-                     u64* n_pairs_out);
+// Builds the walk records on the device and copies them (plus slot -> edge id, original edge -> slot, node -> handle and the
+// initial used-slot bitset) into the page-locked staging buffers of the context.
+struct TailRecords {
+    u64 n_slots = 0, n_pairs = 0;
+    WalkRec* recs = nullptr;
+    u32 *slot_edge = nullptr, *slot_of_edge = nullptr, *handle = nullptr;
+    u64* used0 = nullptr;
+};
+void tail_build_records(mtg_ctx* ctx, const u32* breaking_pairs, u64 n_break, TailRecords* out);
 
 }  // namespace mtg

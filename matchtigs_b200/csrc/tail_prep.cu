@@ -5,8 +5,10 @@
 //     make_graph_eulerian_with_breaking_edges, src/implementation/mod.rs:408-427) are a compaction of the
 //     final multiplicity array -- three flag scans;
 //   * the adjacency the walk iterates (petgraph order: newest edge first) is a stable radix sort of
-//     (from-node, edge id) over all original and dummy edges, written straight into the one-line node records
-//     (with their prefetch hints) the walk uses, DMA'd to the host.
+//     (from-node, edge id) over all original and dummy edges, written straight into the per-edge walk records
+//     (WalkRec, mtg_internal.cuh: where the edge leads, its mirror's slot, and the handles of the nodes up to
+//     WALK_DEPTH steps ahead) the host walk uses, DMA'd to the host;
+//   * the Eulerian check (greedytigs/mod.rs:708-715) is a reduction over the final degrees.
 // Only the pairing loop of eulerise (sequential by definition) runs on the host in between.
 #include <algorithm>
 
@@ -96,43 +98,82 @@ __global__ void __launch_bounds__(TB)
     val[q] = e;
 }
 
-__global__ void __launch_bounds__(TB) ext_counts(const u32* __restrict__ deg, u64 N, u32* __restrict__ cnt) {
+__global__ void __launch_bounds__(TB) slot_caps(const u32* __restrict__ deg, u64 N, u32* __restrict__ cap) {
     u64 v = (u64)blockIdx.x * TB + threadIdx.x;
-    if (v < N) cnt[v] = deg[v] > ROW_INLINE ? deg[v] : 0u;
+    if (v < N) cap[v] = walk_cap(deg[v]);
 }
 
+// handles, headers of big nodes and the initial used-slot bitset (padding slots and header pairs are never handed out)
 __global__ void __launch_bounds__(TB)
-    fill_rows(const u32* __restrict__ key, const u32* __restrict__ val, u64 E, u64 E0, const u32* __restrict__ edge_to,
-              const u32* __restrict__ pair_out, const u32* __restrict__ pair_in, const u32* __restrict__ mirror,
-              const u32* __restrict__ deg, const u32* __restrict__ row_ptr, const u32* __restrict__ ext_off, NodeRow* __restrict__ rows,
-              AdjEntry* __restrict__ ext) {
+    node_handles(const u32* __restrict__ deg, const u32* __restrict__ base, u64 N, u32* __restrict__ handle, WalkRec* __restrict__ recs,
+                 u32* __restrict__ used0) {
+    u64 v = (u64)blockIdx.x * TB + threadIdx.x;
+    if (v >= N) return;
+    const u32 d = deg[v], b = base[v], h = walk_handle(b, d), cap = walk_cap(d);
+    handle[v] = h;
+    const u32 first = walk_first_slot(h);
+    if (d > 4) {
+        recs[b].to = d;
+        atomicOr(&used0[b >> 5], 3u << (b & 31));  // b is even: both header slots share a word
+    }
+    for (u32 sl = first + d; sl < b + cap; sl++) atomicOr(&used0[sl >> 5], 1u << (sl & 31));
+}
+
+// sorted position i holds edge val[i] of node key[i]; its rank inside the node is its iteration position
+__global__ void __launch_bounds__(TB)
+    place_slots(const u32* __restrict__ key, const u32* __restrict__ val, u64 E, u64 E0, const u32* __restrict__ edge_to,
+                const u32* __restrict__ pair_out, const u32* __restrict__ pair_in, const u32* __restrict__ mirror,
+                const u32* __restrict__ row_ptr, const u32* __restrict__ handle, WalkRec* __restrict__ recs, u32* __restrict__ slot_edge,
+                u32* __restrict__ slot_of_edge, u32* __restrict__ slot_to) {
     u64 i = (u64)blockIdx.x * TB + threadIdx.x;
     if (i >= E) return;
     const u32 v = key[i], e = val[i];
-    const u32 rank = (u32)i - row_ptr[v];
-    const AdjEntry a{e, edge_to_of(e, E0, edge_to, pair_out, pair_in, mirror)};
-    if (deg[v] <= ROW_INLINE) rows[v].inl[rank] = a;
-    else ext[ext_off[v] + rank] = a;
+    const u32 sl = walk_first_slot(handle[v]) + ((u32)i - row_ptr[v]);
+    const u32 t = edge_to_of(e, E0, edge_to, pair_out, pair_in, mirror);
+    slot_edge[sl] = e;
+    slot_of_edge[e] = sl;
+    slot_to[sl] = t;
+    recs[sl].to = handle[t];
 }
 
-__global__ void __launch_bounds__(TB) row_headers(const u32* __restrict__ deg, const u32* __restrict__ ext_off, u64 N, NodeRow* __restrict__ rows) {
+__global__ void __launch_bounds__(TB)
+    slot_mirrors(const u32* __restrict__ slot_edge, const u32* __restrict__ slot_of_edge, u64 n_slots, u64 E0, u64 n_matching,
+                 const u32* __restrict__ triples, u32 k, WalkRec* __restrict__ recs) {
+    u64 sl = (u64)blockIdx.x * TB + threadIdx.x;
+    if (sl >= n_slots) return;
+    const u32 e = slot_edge[sl];
+    if (e == NONE32) return;
+    u32 m = slot_of_edge[e ^ 1u];
+    if (e >= E0) {
+        const u64 j = (e - E0) >> 1;  // matching dummies weigh their distance, breaking dummies k
+        const u32 w = j < n_matching ? triples[3 * j + 2] : k;
+        m |= SLOT_DUMMY | (w >= k ? SLOT_BREAK : 0u);
+    }
+    recs[sl].mslot = m;
+}
+
+__global__ void __launch_bounds__(TB)
+    slot_hints(const u32* __restrict__ slot_edge, const u32* __restrict__ slot_to, const u32* __restrict__ deg, u64 n_slots, u32 level,
+               WalkRec* recs) {
+    u64 sl = (u64)blockIdx.x * TB + threadIdx.x;
+    if (sl >= n_slots || slot_edge[sl] == NONE32) return;
+    walk_fill_hints(recs, (u32)sl, deg[slot_to[sl]], level);
+}
+
+__global__ void __launch_bounds__(TB)
+    start_handles(const u32* __restrict__ edge_from, const u32* __restrict__ handle, u64 E0, u32* __restrict__ out) {
+    u64 e = (u64)blockIdx.x * TB + threadIdx.x;
+    if (e < E0) out[e] = handle[edge_from[e]];
+}
+
+// E. (greedytigs/mod.rs:708-715, bigraph decomposes_into_eulerian_bicycles): out-degree == in-degree for every node
+// (in-degree(v) == out-degree(mirror(v)) by the mirror property), even out-degree at self-mirrors.
+__global__ void __launch_bounds__(TB) eulerian_check(const u32* __restrict__ deg, const u32* __restrict__ mirror, u64 N, u32* __restrict__ bad) {
     u64 v = (u64)blockIdx.x * TB + threadIdx.x;
     if (v >= N) return;
-    const u32 d = deg[v];
-    if (d <= ROW_INLINE) {
-        rows[v].cur = 0;
-        rows[v].end = d;
-    } else {
-        rows[v].cur = ext_off[v];
-        rows[v].end = (ext_off[v] + d) | ROW_EXT;
-    }
-}
-
-// rows and cursors are final: prefetch hints for the host walk (two random gathers per entry, cheap here, a cache miss
-// each on the host)
-__global__ void __launch_bounds__(TB) row_hints(NodeRow* rows, const AdjEntry* __restrict__ ext, u64 N) {
-    u64 v = (u64)blockIdx.x * TB + threadIdx.x;
-    if (v < N) fill_row_hints(rows, ext, (u32)v);
+    const u32 m = mirror[v];
+    const bool ok = m == (u32)v ? !(deg[v] & 1u) : deg[v] == deg[m];
+    if (!ok) atomicAdd(bad, 1u);
 }
 
 int bits_for(u64 n) {
@@ -191,17 +232,16 @@ void tail_leftover(mtg_ctx* ctx, TailLeftover& lo) {
     d_id.release(s);
 }
 
-void tail_build_rows(mtg_ctx* ctx, const u32* breaking_pairs, u64 n_break, NodeRow* h_rows, PinnedBuf& ext_stage, u64* n_ext_out,
-                     u64* n_pairs_out) {
+void tail_build_records(mtg_ctx* ctx, const u32* breaking_pairs, u64 n_break, TailRecords* out) {
     cudaStream_t s = ctx->stream;
     const u64 N = ctx->N, E0 = ctx->E, P = ctx->n_triples + n_break, E = E0 + 2 * P;
-    MTG_REQUIRE(E < 0xFFFFFFF0ull, MTG_ERR_UNSUPPORTED, "more than 2^32 edges");
-    *n_pairs_out = P;
-    *n_ext_out = 0;
+    MTG_REQUIRE(E < SLOT_MASK, MTG_ERR_UNSUPPORTED, "more than 2^30 edges");
+    *out = TailRecords();
+    out->n_pairs = P;
     if (N == 0) return;
-    DBuf<u32> d_break, pair_out, pair_in, deg, key_a, key_b, val_a, val_b, row_ptr, ext_cnt, ext_off, total;
-    DBuf<NodeRow> rows;
-    DBuf<AdjEntry> ext;
+    DBuf<u32> d_break, pair_out, pair_in, deg, key_a, key_b, val_a, val_b, row_ptr, cap, base, total, handle, slot_edge, slot_of_edge, slot_to,
+        used0, from_handle;
+    DBuf<WalkRec> recs;
     d_break.upload(breaking_pairs, 2 * n_break, s);
     pair_out.resize(P, s);
     pair_in.resize(P, s);
@@ -216,32 +256,56 @@ void tail_build_rows(mtg_ctx* ctx, const u32* breaking_pairs, u64 n_break, NodeR
     if (E) MTG_LAUNCH(ctx, edge_sort_keys, grid_for(E, TB), TB, 0, E, E0, ctx->edge_from.p, pair_out.p, pair_in.p, ctx->mirror.p, key_a.p, val_a.p);
     const int which = radix_sort_pairs_u32(ctx, key_a.p, key_b.p, val_a.p, val_b.p, E, bits_for(N));
     row_ptr.resize(N + 1, s);
-    ext_cnt.resize(N, s);
-    ext_off.resize(N, s);
-    total.resize(2, s);
+    cap.resize(N, s);
+    base.resize(N, s);
+    total.resize(3, s);
+    total.zero(s);
     exclusive_sum_u32(ctx, deg.p, row_ptr.p, N, total.p + 0);
-    MTG_LAUNCH(ctx, ext_counts, grid_for(N, TB), TB, 0, deg.p, N, ext_cnt.p);
-    exclusive_sum_u32(ctx, ext_cnt.p, ext_off.p, N, total.p + 1);
-    u32 h_total[2];
+    MTG_LAUNCH(ctx, slot_caps, grid_for(N, TB), TB, 0, deg.p, N, cap.p);
+    exclusive_sum_u32(ctx, cap.p, base.p, N, total.p + 1);
+    MTG_LAUNCH(ctx, eulerian_check, grid_for(N, TB), TB, 0, deg.p, ctx->mirror.p, N, total.p + 2);
+    u32 h_total[3];
     MTG_CUDA(cudaMemcpyAsync(h_total, total.p, sizeof(h_total), cudaMemcpyDeviceToHost, s));
     MTG_CUDA(cudaStreamSynchronize(s));
     MTG_REQUIRE(h_total[0] == E, MTG_ERR_INTERNAL, "degree sum does not match the edge count");
-    const u64 n_ext = h_total[1];
-    MTG_REQUIRE(n_ext < ROW_EXT, MTG_ERR_UNSUPPORTED, "too many edges at high-degree nodes");
-    rows.resize(N, s);
-    ext.resize(std::max<u64>(n_ext, 1), s);
-    if (E) MTG_LAUNCH(ctx, fill_rows, grid_for(E, TB), TB, 0, which ? key_b.p : key_a.p, which ? val_b.p : val_a.p, E, E0, ctx->edge_to.p,
-                      pair_out.p, pair_in.p, ctx->mirror.p, deg.p, row_ptr.p, ext_off.p, rows.p, ext.p);
-    MTG_LAUNCH(ctx, row_headers, grid_for(N, TB), TB, 0, deg.p, ext_off.p, N, rows.p);
-    MTG_LAUNCH(ctx, row_hints, grid_for(N, TB), TB, 0, rows.p, ext.p, N);
-    MTG_CUDA(cudaMemcpyAsync(h_rows, rows.p, N * sizeof(NodeRow), cudaMemcpyDeviceToHost, s));
-    AdjEntry* h_ext = ext_stage.as<AdjEntry>(std::max<u64>(n_ext, 1));
-    if (n_ext) MTG_CUDA(cudaMemcpyAsync(h_ext, ext.p, n_ext * sizeof(AdjEntry), cudaMemcpyDeviceToHost, s));
+    MTG_REQUIRE(h_total[2] == 0, MTG_ERR_INTERNAL, "Failed to make the graph Eulerian.");  // greedytigs/mod.rs:708-715
+    const u64 n_slots = h_total[1];
+    MTG_REQUIRE(n_slots < SLOT_MASK, MTG_ERR_UNSUPPORTED, "more than 2^30 edge slots");
+    const u64 used_words32 = 2 * (n_slots / 64 + 2);
+    recs.resize(n_slots, s);
+    handle.resize(N, s);
+    slot_edge.resize(n_slots, s);
+    slot_edge.fill_ff(s);
+    slot_of_edge.resize(E, s);
+    slot_to.resize(n_slots, s);
+    used0.resize(used_words32, s);
+    used0.zero(s);
+    from_handle.resize(E0, s);
+    MTG_LAUNCH(ctx, node_handles, grid_for(N, TB), TB, 0, deg.p, base.p, N, handle.p, recs.p, used0.p);
+    if (E) {
+        MTG_LAUNCH(ctx, place_slots, grid_for(E, TB), TB, 0, which ? key_b.p : key_a.p, which ? val_b.p : val_a.p, E, E0, ctx->edge_to.p, pair_out.p,
+                   pair_in.p, ctx->mirror.p, row_ptr.p, handle.p, recs.p, slot_edge.p, slot_of_edge.p, slot_to.p);
+        MTG_LAUNCH(ctx, slot_mirrors, grid_for(n_slots, TB), TB, 0, slot_edge.p, slot_of_edge.p, n_slots, E0, ctx->n_triples, ctx->triples.p, ctx->k,
+                   recs.p);
+        for (u32 level = 2; level <= WALK_DEPTH; level++)
+            MTG_LAUNCH(ctx, slot_hints, grid_for(n_slots, TB), TB, 0, slot_edge.p, slot_to.p, deg.p, n_slots, level, recs.p);
+        if (E0) MTG_LAUNCH(ctx, start_handles, grid_for(E0, TB), TB, 0, ctx->edge_from.p, handle.p, E0, from_handle.p);
+    }
+    // DMA into page-locked staging (full link speed); the records first, they are what the walk waits for
+    out->n_slots = n_slots;
+    out->recs = ctx->tail_stage[0].as<WalkRec>(n_slots + 1);
+    out->used0 = ctx->tail_stage[1].as<u64>(used_words32 / 2 + 1);
+    out->slot_of_edge = ctx->tail_stage[2].as<u32>(E0 + 1);
+    out->handle = ctx->tail_stage[3].as<u32>(E0 + 1);  // handle of the from-node of every original edge
+    out->slot_edge = ctx->tail_stage[4].as<u32>(n_slots + 1);
+    MTG_CUDA(cudaMemcpyAsync(out->recs, recs.p, n_slots * sizeof(WalkRec), cudaMemcpyDeviceToHost, s));
+    MTG_CUDA(cudaMemcpyAsync(out->used0, used0.p, used_words32 * sizeof(u32), cudaMemcpyDeviceToHost, s));
+    if (E0) {
+        MTG_CUDA(cudaMemcpyAsync(out->slot_of_edge, slot_of_edge.p, E0 * sizeof(u32), cudaMemcpyDeviceToHost, s));
+        MTG_CUDA(cudaMemcpyAsync(out->handle, from_handle.p, E0 * sizeof(u32), cudaMemcpyDeviceToHost, s));
+    }
+    MTG_CUDA(cudaMemcpyAsync(out->slot_edge, slot_edge.p, n_slots * sizeof(u32), cudaMemcpyDeviceToHost, s));
     MTG_CUDA(cudaStreamSynchronize(s));
-    *n_ext_out = n_ext;
-    for (DBuf<u32>* b : {&d_break, &pair_out, &pair_in, &deg, &key_a, &key_b, &val_a, &val_b, &row_ptr, &ext_cnt, &ext_off, &total}) b->release(s);
-    rows.release(s);
-    ext.release(s);
 }
 
 }  // namespace mtg

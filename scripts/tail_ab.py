@@ -1,0 +1,35 @@
+"""A/B timings of the host tail on one workload: the graph, the searches and the matching run once, mtg_finish_walks is
+repeated under different environment switches.  usage: tail_ab.py <workload> <scale> [reps]"""
+import os
+import sys
+import time
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+import bench  # noqa: E402
+import matchtigs_b200 as mt  # noqa: E402
+
+name, scale = sys.argv[1], float(sys.argv[2])
+reps = int(sys.argv[3]) if len(sys.argv) > 3 else 5
+text, k, info = bench.make_workload(name, scale)
+ctx = mt.Context(0)
+ctx.build_graph_from_text(text, k, bcalm=bench.WORKLOADS[name]["bcalm"])
+ctx.dijkstra_candidates(bench.CAP, 0, 1)
+ctx.greedy_match()
+print(ctx.graph_info())
+for label, env in (("default", {}), ("nocopy", {"MTG_TAIL_NOCOPY": "1"}), ("nohint", {"MTG_TAIL_NOHINT": "1"}),
+                   ("nocopy+nohint", {"MTG_TAIL_NOCOPY": "1", "MTG_TAIL_NOHINT": "1"}), ("default", {})):
+    for k_, v in env.items():
+        os.environ[k_] = v
+    rows = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        nw, ne = ctx.finish_walks()
+        dt = 1e3 * (time.perf_counter() - t0)
+        rows.append((dt, ctx.diagnostics()["tail_ms"]))
+    rows.sort(key=lambda r: r[0])
+    dt, ms = rows[len(rows) // 2]
+    steps = ne + nw
+    print(f"{label:14s} tail {dt:7.1f} ms  {ms}  walks {nw}  ~{1e6 * ms['euler_walk'] / max(steps, 1):.1f} ns/step", flush=True)
+    for k_ in env:
+        del os.environ[k_]
