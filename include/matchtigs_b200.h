@@ -68,12 +68,25 @@ typedef struct mtg_search_stats {
     float match_ms;             /* device time of the matching step (set-up kernels, sort, dataflow kernel, copies) */
     float dijkstra_kernel_ms;   /* device time of the tier-0 (thread-per-source) search kernel of the last main search */
     float match_kernel_ms;      /* device time of the dataflow matching kernel (first phase) */
+    /* What the reference's DijkstraPerformanceCounter reports (--dijkstra-performance-data-type Complete,
+     * greedytigs/mod.rs:647-673), as far as it has a meaning here: a search labels nodes in a table ("distance array"); its
+     * open labels are what a heap would hold.  There is no lazy deletion (decrease-key happens in place), so no label is ever
+     * extracted twice: iterations == settled_nodes, unnecessary heap elements == 0. */
+    uint64_t labelled_nodes;      /* labelled nodes summed over the searches */
+    uint64_t max_labelled_nodes;  /* most labelled nodes in one search ("maximum maximum distance array size") */
+    uint64_t max_open_nodes;      /* most open labels at once in one thread-tier search ("maximum maximum heap size") */
 } mtg_search_stats;
 
 /* ---- lifecycle ---- */
 int mtg_ctx_create(mtg_ctx** out, int device);
 void mtg_ctx_destroy(mtg_ctx* ctx);
 const char* mtg_last_error(const mtg_ctx* ctx);
+/* Parity assumptions about the reference's un-vendored dependencies as switches; 0 = as assumed.
+ * Names: p1_tie_desc, p1_exclusive_bound (Dijkstra settle order / bound, traitgraph-algo), p2_self_mirror_zero (imbalance
+ * of self-mirror nodes, bigraph), p3_oldest_first (adjacency iteration order, petgraph), p6_bcalm_kmer_numbering (bcalm2
+ * reader numbering, genome-graph), p7_first_root_wins (union-find tie rule, disjoint-sets).  Same names as the oracle's
+ * mto_set_option; MTG_ASSUME_<NAME>=1 in the environment sets the default.  Invalidates the resident graph. */
+int mtg_ctx_set_option(mtg_ctx* ctx, const char* name, int value);
 /* The CUDA stream (cudaStream_t) every kernel of this context is launched on; for event timing by the caller. */
 void* mtg_ctx_stream(mtg_ctx* ctx);
 /* Number of kernels this context has launched since creation (the caller's gpu_launches claim). */

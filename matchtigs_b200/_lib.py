@@ -18,7 +18,7 @@ STATUS_NAMES = {0: "MTG_OK", -1: "MTG_ERR_INVALID", -2: "MTG_ERR_CUDA", -3: "MTG
 
 # every symbol include/matchtigs_b200.h declares (tests check that the library exports all of them)
 EXPORTED_SYMBOLS = [
-    "mtg_ctx_create", "mtg_ctx_destroy", "mtg_last_error", "mtg_ctx_stream", "mtg_ctx_kernel_launches",
+    "mtg_ctx_create", "mtg_ctx_destroy", "mtg_last_error", "mtg_ctx_set_option", "mtg_ctx_stream", "mtg_ctx_kernel_launches",
     "mtg_build_graph_from_sequences", "mtg_build_graph_from_links", "mtg_build_graph_from_text", "mtg_graph_get_info", "mtg_graph_export",
     "mtg_dijkstra_candidates", "mtg_candidates_local", "mtg_candidates_export",
     "mtg_greedy_match", "mtg_triples_export",
@@ -45,7 +45,8 @@ class SearchStats(C.Structure):
                 ("candidates", C.c_uint64), ("truncated_sources", C.c_uint64), ("overflow_sources", C.c_uint64),
                 ("match_rounds", C.c_uint64), ("requery_phases", C.c_uint64), ("matched", C.c_uint64),
                 ("dijkstra_ms", C.c_float), ("match_ms", C.c_float), ("dijkstra_kernel_ms", C.c_float),
-                ("match_kernel_ms", C.c_float)]
+                ("match_kernel_ms", C.c_float), ("labelled_nodes", C.c_uint64), ("max_labelled_nodes", C.c_uint64),
+                ("max_open_nodes", C.c_uint64)]
 
     def as_dict(self) -> dict:
         return {n: (float(getattr(self, n)) if t is C.c_float else int(getattr(self, n))) for n, t in self._fields_}
@@ -67,6 +68,7 @@ def load() -> C.CDLL:
     l.mtg_ctx_create.argtypes = [C.POINTER(vp), i32]
     l.mtg_ctx_destroy.argtypes = [vp]
     l.mtg_ctx_destroy.restype = None
+    l.mtg_ctx_set_option.argtypes = [vp, C.c_char_p, i32]
     l.mtg_last_error.argtypes = [vp]
     l.mtg_last_error.restype = C.c_char_p
     l.mtg_ctx_stream.argtypes = [vp]

@@ -101,6 +101,13 @@ class Context:
         if rc != 0:
             raise MatchtigsError(rc, self._l.mtg_last_error(self._h).decode())
 
+    ASSUMPTIONS = ("p1_tie_desc", "p1_exclusive_bound", "p2_self_mirror_zero", "p3_oldest_first", "p6_bcalm_kmer_numbering",
+                   "p7_first_root_wins")
+
+    def set_option(self, name: str, value: int):
+        """Parity-assumption switches (same names as the oracle's ``set_option``)."""
+        self._check(self._l.mtg_ctx_set_option(self._h, name.encode(), int(value)))
+
     # ---- step 1 ----
     def build_graph_from_sequences(self, seq: np.ndarray, offsets: np.ndarray, k: int):
         seq = np.ascontiguousarray(seq, dtype=np.uint8)

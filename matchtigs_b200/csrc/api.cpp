@@ -1,5 +1,6 @@
 // api.cpp -- the C ABI declared in include/matchtigs_b200.h: exception firewall around the
 // step functions plus the reference's own C API (src/clib.rs) on top of them.
+#include <cctype>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -43,6 +44,21 @@ int guarded(mtg_ctx* ctx, F&& f) {
 
 }  // namespace
 
+static int* option_slot(mtg_ctx* ctx, const char* name) {
+    static const struct {
+        const char* name;
+        int mtg_options::*field;
+    } table[] = {{"p1_tie_desc", &mtg_options::p1_tie_desc},
+                 {"p1_exclusive_bound", &mtg_options::p1_exclusive_bound},
+                 {"p2_self_mirror_zero", &mtg_options::p2_self_mirror_zero},
+                 {"p3_oldest_first", &mtg_options::p3_oldest_first},
+                 {"p6_bcalm_kmer_numbering", &mtg_options::p6_bcalm_kmer_numbering},
+                 {"p7_first_root_wins", &mtg_options::p7_first_root_wins}};
+    for (const auto& t : table)
+        if (!strcmp(name, t.name)) return &(ctx->opt.*(t.field));
+    return nullptr;
+}
+
 extern "C" {
 
 int mtg_ctx_create(mtg_ctx** out, int device) {
@@ -56,6 +72,12 @@ int mtg_ctx_create(mtg_ctx** out, int device) {
     mtg_ctx* ctx = new (std::nothrow) mtg_ctx();
     if (!ctx) return MTG_ERR_INTERNAL;
     ctx->device = device;
+    for (const char* name : {"p1_tie_desc", "p1_exclusive_bound", "p2_self_mirror_zero", "p3_oldest_first", "p6_bcalm_kmer_numbering",
+                             "p7_first_root_wins"}) {  // MTG_ASSUME_P1_TIE_DESC=1 ... in the environment
+        std::string env = std::string("MTG_ASSUME_") + name;
+        for (auto& c : env) c = (char)toupper((unsigned char)c);
+        if (const char* v = getenv(env.c_str())) *option_slot(ctx, name) = atoi(v);
+    }
     int rc = guarded(ctx, [&] {
         MTG_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
         MTG_CUDA(cudaEventCreate(&ctx->ev0));
@@ -125,6 +147,16 @@ void mtg_ctx_destroy(mtg_ctx* ctx) {
     for (auto& e : ctx->ev_build)
         if (e) cudaEventDestroy(e);
     delete ctx;
+}
+
+int mtg_ctx_set_option(mtg_ctx* ctx, const char* name, int value) {
+    return guarded(ctx, [&] {
+        MTG_REQUIRE(name, MTG_ERR_INVALID, "null option name");
+        int* slot = option_slot(ctx, name);
+        MTG_REQUIRE(slot, MTG_ERR_INVALID, std::string("unknown option ") + name);
+        *slot = value;
+        ctx->have_graph = ctx->have_cand = ctx->have_triples = ctx->have_walks = false;  // results of other assumptions are void
+    });
 }
 
 const char* mtg_last_error(const mtg_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }

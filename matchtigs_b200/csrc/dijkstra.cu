@@ -64,6 +64,7 @@ struct SearchArgs {
     u64 n_items;           // number of work items of this launch
     u32 shard_rank, shard_count;
     u32 cap, max_weight;
+    u32 tie_flip;          // 0: ties inside a distance level go to the smaller node id (P1); 0xFFFFFFFF: to the larger
     u64* records;          // [n_work * cap]
     u32* meta;             // [n_work]
     u32* overflow_list;    // work items for tier 2
@@ -106,28 +107,34 @@ __device__ __forceinline__ u64 warp_or64(u64 v) {
 // ---------------- tier 0: one THREAD per source ----------------
 // Most searches label a few dozen nodes and settle one node per distance level, so a whole warp per
 // source idles 31 lanes and pays every per-level warp operation for nothing.  Here every lane runs its own
-// search: labels live in a per-thread slice of shared memory (lane-interleaved, so equal indices never
-// conflict), extraction is a scan for the smallest unsettled (dist, node) -- exactly the heap's pop order --
-// and relaxation is a linear search of the few labelled nodes.  32 independent load chains per warp hide the
-// L2 latency that a single chain cannot.  Searches that outgrow T0_ENTRIES labels go to the warp tier.
+// search; 32 independent load chains per warp hide the L2 latency that a single chain cannot.  Labels live in a
+// per-thread slice of shared memory (lane-interleaved, so equal indices never conflict):
+//   [0, ns)  settled labels, [ns, n)  open labels -- extract-min scans the open ones only (the frontier of these
+//   searches is a handful of nodes) for the smallest (dist, node id), exactly the heap's pop order, and swaps the
+//   winner to position ns;
+//   a relaxed edge first asks a 64-bit signature of the labelled node ids (one bit per hash class): most relaxed
+//   edges lead to a node not seen before and skip the linear search of the labels altogether.
+// Searches that outgrow T0_ENTRIES labels go to the warp tier.
 constexpr int T0_THREADS = 128;
 #ifndef MTG_T0_ENTRIES
 #define MTG_T0_ENTRIES 48
 #endif
 constexpr int T0_ENTRIES = MTG_T0_ENTRIES;
-constexpr u32 T0_SETTLED = 0x80u;
 
 __global__ void __launch_bounds__(T0_THREADS) dijkstra_thread_kernel(SearchArgs a) {
     __shared__ u32 s_key[T0_ENTRIES][T0_THREADS];
     __shared__ u8 s_dist[T0_ENTRIES][T0_THREADS];
     const unsigned tid = threadIdx.x, lane = tid & 31;
-    unsigned long long st_settled = 0, st_relaxed = 0, st_cand = 0, st_searched = 0, st_trunc = 0, st_ovf = 0;
+    const u32 flip = a.tie_flip;
+    unsigned long long st_settled = 0, st_relaxed = 0, st_cand = 0, st_searched = 0, st_trunc = 0, st_ovf = 0, st_labels = 0;
+    u32 st_max_labels = 0, st_max_open = 0;
     // One flat loop: every iteration a lane either fetches its next source or settles ONE node of its current search.
     // Lanes whose search ends refill on the next iteration instead of idling until the largest search of the warp
     // is done (a nested search loop would reconverge only after all 32 searches).
     bool active = false;
     u64 t = 0;
-    u32 src = 0, n = 0, open = 0, emitted = 0, settled = 0, relaxed = 0;
+    u64 sig = 0;  // signature of the labelled node ids
+    u32 src = 0, n = 0, ns = 0, emitted = 0, relaxed = 0, max_open = 0;
     for (;;) {
         if (!active) {
             u64 q;
@@ -147,30 +154,34 @@ __global__ void __launch_bounds__(T0_THREADS) dijkstra_thread_kernel(SearchArgs 
             } else {
                 st_searched++;
                 n = 1;
-                open = 1;  // labelled, not yet settled
-                emitted = settled = relaxed = 0;
+                ns = 0;
+                emitted = relaxed = 0;
+                max_open = 1;
                 s_key[0][tid] = src;
                 s_dist[0][tid] = 0;
+                sig = 1ull << ((src * 0x9E3779B1u) >> 26);
                 active = true;
             }
         }
         if (active) {
-            // extract-min over the unsettled labels: total order (dist, node id)
+            // extract-min over the open labels: total order (dist, node id)
             unsigned long long best = ~0ull;
-            u32 bi = 0;
-            for (u32 i = 0; i < n; i++) {
-                const u32 dd = s_dist[i][tid];
-                if (dd & T0_SETTLED) continue;
-                const unsigned long long val = ((unsigned long long)dd << 32) | s_key[i][tid];
+            u32 bi = ns;
+            for (u32 i = ns; i < n; i++) {
+                const unsigned long long val = ((unsigned long long)s_dist[i][tid] << 32) | (s_key[i][tid] ^ flip);
                 if (val < best) {
                     best = val;
                     bi = i;
                 }
             }
-            const u32 d = (u32)(best >> 32), v = (u32)best;
-            s_dist[bi][tid] = (u8)(d | T0_SETTLED);
-            settled++;
-            open--;
+            const u32 d = (u32)(best >> 32), v = (u32)best ^ flip;
+            if (bi != ns) {  // the winner joins the settled prefix
+                s_key[bi][tid] = s_key[ns][tid];
+                s_dist[bi][tid] = s_dist[ns][tid];
+                s_key[ns][tid] = v;
+                s_dist[ns][tid] = (u8)d;
+            }
+            ns++;
             if (v != src && ((a.bitmap[v >> 5] >> (v & 31)) & 1u)) a.records[t * a.cap + emitted++] = (u64)v | ((u64)d << 32);
             bool overflow = false;
             const u32 e0 = a.row_s[v], e1 = a.row_s[v + 1];
@@ -179,35 +190,42 @@ __global__ void __launch_bounds__(T0_THREADS) dijkstra_thread_kernel(SearchArgs 
                 relaxed++;
                 if (nw > a.max_weight) continue;
                 const u32 u = a.col_s[e];
-                u32 j = 0;
-                while (j < n && s_key[j][tid] != u) j++;
+                const u64 bit = 1ull << ((u * 0x9E3779B1u) >> 26);
+                u32 j = n;
+                if (sig & bit) {
+                    j = 0;
+                    while (j < n && s_key[j][tid] != u) j++;
+                }
                 if (j < n) {
-                    const u32 dd = s_dist[j][tid];
-                    if (!(dd & T0_SETTLED) && nw < dd) s_dist[j][tid] = (u8)nw;
+                    if (j >= ns && nw < s_dist[j][tid]) s_dist[j][tid] = (u8)nw;  // open label: decrease-key in place
                 } else if (n < T0_ENTRIES) {
                     s_key[n][tid] = u;
                     s_dist[n][tid] = (u8)nw;
                     n++;
-                    open++;
+                    sig |= bit;
                 } else {
                     overflow = true;
                     break;
                 }
             }
+            max_open = max(max_open, n - ns);
             if (overflow) {
                 a.meta[t] = META_OVERFLOW;
                 a.overflow_list[atomicAdd(a.overflow_count, 1u)] = (u32)t;
                 st_ovf++;
                 active = false;
-            } else if (open == 0 || emitted == a.cap) {
+            } else if (ns == n || emitted == a.cap) {
                 // a full list is complete only if nothing is left to settle (checked after v's own relaxation, because
                 // the last target may be the only way to further ones)
-                const bool truncated = open != 0;
+                const bool truncated = ns != n;
                 a.meta[t] = emitted | (truncated ? META_TRUNC : 0u);
-                st_settled += settled;
+                st_settled += ns;
                 st_relaxed += relaxed;
                 st_cand += emitted;
                 st_trunc += truncated;
+                st_labels += n;
+                st_max_labels = max(st_max_labels, n);
+                st_max_open = max(st_max_open, max_open);
                 active = false;
             }
         }
@@ -219,6 +237,9 @@ __global__ void __launch_bounds__(T0_THREADS) dijkstra_thread_kernel(SearchArgs 
         st_searched += __shfl_down_sync(0xffffffffu, st_searched, o);
         st_trunc += __shfl_down_sync(0xffffffffu, st_trunc, o);
         st_ovf += __shfl_down_sync(0xffffffffu, st_ovf, o);
+        st_labels += __shfl_down_sync(0xffffffffu, st_labels, o);
+        st_max_labels = max(st_max_labels, __shfl_down_sync(0xffffffffu, st_max_labels, o));
+        st_max_open = max(st_max_open, __shfl_down_sync(0xffffffffu, st_max_open, o));
     }
     if (lane == 0) {
         if (st_searched) atomicAdd(&a.stats->sources_searched, st_searched);
@@ -227,6 +248,9 @@ __global__ void __launch_bounds__(T0_THREADS) dijkstra_thread_kernel(SearchArgs 
         if (st_cand) atomicAdd(&a.stats->candidates, st_cand);
         if (st_trunc) atomicAdd(&a.stats->truncated, st_trunc);
         if (st_ovf) atomicAdd(&a.stats->overflow, st_ovf);
+        if (st_labels) atomicAdd(&a.stats->labels, st_labels);
+        if (st_max_labels) atomicMax(&a.stats->max_labels, (unsigned long long)st_max_labels);
+        if (st_max_open) atomicMax(&a.stats->max_open, (unsigned long long)st_max_open);
     }
 }
 
@@ -327,7 +351,7 @@ __global__ void __launch_bounds__(DJ_THREADS) dijkstra_warp_kernel(SearchArgs a)
                     // settle order inside a level is ascending node id: rank by counting (ids are distinct)
                     for (u32 e = lane; e < lvl_cnt; e += 32) {
                         u32 x = ws->lvl[e], rank = 0;
-                        for (u32 j = 0; j < lvl_cnt; j++) rank += ws->lvl[j] < x;
+                        for (u32 j = 0; j < lvl_cnt; j++) rank += (ws->lvl[j] ^ a.tie_flip) < (x ^ a.tie_flip);
                         if (emitted + rank < a.cap) out[emitted + rank] = (u64)x | ((u64)d << 32);
                     }
                     emitted += lvl_cnt;
@@ -358,6 +382,10 @@ __global__ void __launch_bounds__(DJ_THREADS) dijkstra_warp_kernel(SearchArgs a)
                 st_cand += (lane == 0) ? emitted : 0;
                 st_trunc += (lane == 0 && truncated);
                 const u32 n_end = ((volatile u32*)&ws->n)[0];
+                if (lane == 0) {
+                    atomicAdd(&a.stats->labels, (unsigned long long)n_end);
+                    atomicMax(&a.stats->max_labels, (unsigned long long)n_end);
+                }
                 for (u32 i = lane; i < n_end; i += 32) {
                     u32 slot = ws->slots[i];
                     ws->key[slot] = EMPTY;
@@ -465,7 +493,7 @@ __global__ void __launch_bounds__(BIG_THREADS) dijkstra_cta_kernel(BigArgs b) {
             if (lvl_cnt) {
                 for (u32 e = threadIdx.x; e < lvl_cnt; e += BIG_THREADS) {
                     u32 x = lt[e], rank = 0;
-                    for (u32 j = 0; j < lvl_cnt && rank + emitted < a.cap; j++) rank += lt[j] < x;
+                    for (u32 j = 0; j < lvl_cnt && rank + emitted < a.cap; j++) rank += (lt[j] ^ a.tie_flip) < (x ^ a.tie_flip);
                     if (emitted + rank < a.cap) out[emitted + rank] = (u64)x | ((u64)d << 32);
                 }
                 emitted += lvl_cnt;
@@ -484,6 +512,8 @@ __global__ void __launch_bounds__(BIG_THREADS) dijkstra_cta_kernel(BigArgs b) {
             a.meta[t] = emitted | (truncated ? META_TRUNC : 0u);
             atomicAdd(&a.stats->candidates, (unsigned long long)emitted);
             if (truncated) atomicAdd(&a.stats->truncated, 1ull);
+            atomicAdd(&a.stats->labels, (unsigned long long)n_end);
+            atomicMax(&a.stats->max_labels, (unsigned long long)n_end);
         }
         __syncthreads();
     }
@@ -518,7 +548,8 @@ void run_searches(mtg_ctx* ctx, const u32* bitmap, const u32* work_list, u64 n_w
     a.shard_rank = shard_rank;
     a.shard_count = shard_count;
     a.cap = cap;
-    a.max_weight = ctx->k - 1;
+    a.max_weight = ctx->k - 1 - (ctx->opt.p1_exclusive_bound ? 1u : 0u);
+    a.tie_flip = ctx->opt.p1_tie_desc ? 0xFFFFFFFFu : 0u;
     a.records = records;
     a.meta = meta;
     a.stats = ctx->dstats.p;
@@ -639,6 +670,9 @@ void dijkstra_candidates(mtg_ctx* ctx, u32 cap, u32 shard_rank, u32 shard_count)
     ctx->stats.candidates = h.candidates;
     ctx->stats.truncated_sources = h.truncated;
     ctx->stats.overflow_sources = h.overflow;
+    ctx->stats.labelled_nodes = h.labels;
+    ctx->stats.max_labelled_nodes = h.max_labels;
+    ctx->stats.max_open_nodes = h.max_open;
     ctx->stats.dijkstra_ms = ms;
     ctx->stats.dijkstra_kernel_ms = ctx->last_kernel_ms;
     ctx->have_cand = true;

@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(TB) count_degrees(const u32* __restrict__ edge
 // compute_eulerian_superfluous_out_biedges + the scan of greedytigs/mod.rs:229-245.
 // in_degree(v) == out_degree(mirror(v)) by the mirror property of the bigraph.
 __global__ void __launch_bounds__(TB)
-    classify_nodes(const u32* __restrict__ out_deg, const u32* __restrict__ mirror, u64 N, i32* __restrict__ imbalance,
+    classify_nodes(const u32* __restrict__ out_deg, const u32* __restrict__ mirror, u64 N, bool self_mirror_zero, i32* __restrict__ imbalance,
                    u32* __restrict__ src_flag, u32* __restrict__ target_bits, unsigned long long* __restrict__ counters) {
     u64 v = (u64)blockIdx.x * TB + threadIdx.x;
     bool is_src = false, is_tgt = false, self_unb = false;
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(TB)
     if (v < N) {
         u32 m = mirror[v];
         if (m == (u32)v) {
-            diff = (i32)(out_deg[v] & 1u);
+            diff = self_mirror_zero ? 0 : (i32)(out_deg[v] & 1u);  // assumption P2
             is_src = is_tgt = self_unb = diff != 0;
         } else {
             diff = (i32)out_deg[v] - (i32)out_deg[m];
@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(TB)
 // union-by-rank rule (disjoint-sets 0.4.2, assumption P7): equal ranks attach the first root below the second.
 __global__ void __launch_bounds__(TB)
     replay_unions(const u32* __restrict__ key_sorted, const u32* __restrict__ op_sorted, u64 nops, const u64* __restrict__ a,
-                  const u8* __restrict__ sa, const u64* __restrict__ b, const u8* __restrict__ sb, u32* parent, u8* rank) {
+                  const u8* __restrict__ sa, const u64* __restrict__ b, const u8* __restrict__ sb, bool first_root_wins, u32* parent, u8* rank) {
     u64 i = (u64)blockIdx.x * TB + threadIdx.x;
     if (i >= nops) return;
     u32 comp = key_sorted[i];
@@ -344,7 +344,10 @@ __global__ void __launch_bounds__(TB)
         u8 rx = rank[x], ry = rank[y];
         if (rx > ry) parent[y] = x;
         else if (ry > rx) parent[x] = y;
-        else {
+        else if (first_root_wins) {  // assumption P7 flipped
+            parent[y] = x;
+            rank[x] = rx + 1;
+        } else {
             parent[x] = y;
             rank[y] = ry + 1;
         }
@@ -472,7 +475,7 @@ void finish_graph(mtg_ctx* ctx) {
     MTG_CUDA(cudaMemsetAsync(d_counters, 0, 4 * sizeof(unsigned long long), s));
     if (N) {
         u64 padded = (N + 31) / 32 * 32;
-        MTG_LAUNCH(ctx, classify_nodes, grid_for(padded, TB), TB, 0, ctx->out_deg.p, ctx->mirror.p, N, ctx->imbalance.p, src_flag.p,
+        MTG_LAUNCH(ctx, classify_nodes, grid_for(padded, TB), TB, 0, ctx->out_deg.p, ctx->mirror.p, N, ctx->opt.p2_self_mirror_zero != 0, ctx->imbalance.p, src_flag.p,
                    ctx->target_bits.p, d_counters);
     }
     // source positions, short-edge rows and short-edge positions: three scans, then ONE round trip for all totals
@@ -613,6 +616,8 @@ void build_graph_from_links(mtg_ctx* ctx, u64 U, const u64* weights, u64 n_links
     MTG_REQUIRE(U == 0 || weights, MTG_ERR_INVALID, "null weights");
     MTG_REQUIRE(n_links == 0 || (a && sa && b && sb), MTG_ERR_INVALID, "null links");
     MTG_REQUIRE(2 * n_links < 0xFFFFFFFFull, MTG_ERR_UNSUPPORTED, "too many links");
+    if (ctx->opt.p6_bcalm_kmer_numbering && seq && offsets)  // assumption P6 flipped: the links are ignored, nodes come from the k-mer join
+        return build_graph_from_sequences(ctx, seq, offsets, U, k, on_device, total_bases);
     cudaStream_t s = ctx->stream;
     ctx->have_graph = false;
     ctx->build_timed = false;
@@ -666,7 +671,7 @@ void build_graph_from_links(mtg_ctx* ctx, u64 U, const u64* weights, u64 n_links
         MTG_LAUNCH(ctx, op_component_keys, grid_for(nops, TB), TB, 0, d_a.p, d_sa.p, d_b.p, d_sb.p, nops, cc.p, key_a.p, op_a.p);
         int which = radix_sort_pairs_u32(ctx, key_a.p, key_b.p, op_a.p, op_b.p, nops, bits_for(nslots));
         MTG_LAUNCH(ctx, replay_unions, grid_for(nops, TB), TB, 0, which ? key_b.p : key_a.p, which ? op_b.p : op_a.p, nops, d_a.p,
-                   d_sa.p, d_b.p, d_sb.p, parent.p, rank.p);
+                   d_sa.p, d_b.p, d_sb.p, ctx->opt.p7_first_root_wins != 0, parent.p, rank.p);
     }
     rep.resize(nslots, s);
     is_rep.resize(nslots, s);

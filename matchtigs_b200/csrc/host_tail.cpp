@@ -72,6 +72,7 @@ struct TailInput {
     const u32 *from, *to, *unitig_w, *mirror;
     const u32* triples;
     u64 n_triples;
+    bool oldest_first;  // assumption P3 flipped: out-edges are iterated oldest first
 };
 
 struct TailOutput {
@@ -190,8 +191,8 @@ void walk_and_break(const WalkInput& w, TailOutput& out, TailScratch& scratch);
 // Host-side record builder (small graphs, the host-only entry, tests): same records as tail_prep.cu builds on the device.
 // `edge_end(e, &from, &to)` yields the end nodes of any original or dummy edge.
 template <class EdgeEnds>
-void build_walk_records(u32 n, u64 E0, u64 E, u32 k, const u32* out_deg, const u32* dummy_w, EdgeEnds&& edge_ends, TailScratch& scratch,
-                        WalkInput& w) {
+void build_walk_records(u32 n, u64 E0, u64 E, u32 k, const u32* out_deg, const u32* dummy_w, bool oldest_first, EdgeEnds&& edge_ends,
+                        TailScratch& scratch, WalkInput& w) {
     u32* handle = static_cast<u32*>(scratch.handle.ensure(std::max<size_t>(n, 1) * sizeof(u32)));
     u64 n_slots = 0;
     for (u32 v = 0; v < n; v++) {
@@ -219,7 +220,8 @@ void build_walk_records(u32 n, u64 E0, u64 E, u32 k, const u32* out_deg, const u
         }
         for (u32 j = fill[v] - base + d; j < cap; j++) mark(base + j);  // padding
     }
-    for (u64 e = E; e-- > 0;) {
+    for (u64 q = 0; q < E; q++) {
+        const u64 e = oldest_first ? q : E - 1 - q;
         u32 f, t;
         edge_ends((u32)e, &f, &t);
         const u32 sl = fill[f]++;
@@ -318,7 +320,7 @@ void run_tail(const TailInput& in, TailOutput& out, TailScratch& scratch) {
         if (j < in.n_triples) max_matching_w = std::max(max_matching_w, pairs[j].w);
     }
     WalkInput w{in.k, in.n_nodes, E0, E, 0, nullptr, nullptr, nullptr, nullptr, nullptr, in.from, nullptr, out.dummy_w.data(), max_matching_w < in.k};
-    build_walk_records(n, E0, E, in.k, od, out.dummy_w.data(),
+    build_walk_records(n, E0, E, in.k, od, out.dummy_w.data(), in.oldest_first,
                        [&](u32 e, u32* f, u32* t) {
                            if (e < E0) {
                                *f = in.from[e], *t = in.to[e];
@@ -710,7 +712,7 @@ static void finish_walks_host_prep(mtg_ctx* ctx) {
         stage_tail_inputs(ctx);
         MTG_CUDA(cudaStreamSynchronize(s));
     }
-    TailInput in{ctx->k, N, E, from, to, uw, mirror, ctx->h_triples.data(), ctx->n_triples};
+    TailInput in{ctx->k, N, E, from, to, uw, mirror, ctx->h_triples.data(), ctx->n_triples, ctx->opt.p3_oldest_first != 0};
     TailOutput out;
     run_tail(in, out, ctx->tail_scratch);
     ctx->walk_edges.swap(out.walk_edges);
@@ -821,7 +823,8 @@ extern "C" int mtg_host_tail(uint32_t k, uint64_t nodes, uint64_t unitigs, const
     };
     if (!walk_edges || !walk_limits || !dummy_w || !n_walks || !n_walk_edges || !n_dummy_edges) return fail(MTG_ERR_INVALID, "null output");
     try {
-        TailInput in{k, nodes, 2 * unitigs, edge_from, edge_to, unitig_w, mirror, triples, n_triples};
+        const char* p3 = getenv("MTG_ASSUME_P3_OLDEST_FIRST");
+        TailInput in{k, nodes, 2 * unitigs, edge_from, edge_to, unitig_w, mirror, triples, n_triples, p3 && *p3 == '1'};
         TailOutput out;
         static thread_local TailScratch scratch;  // arenas are reused across calls, like the context does
         run_tail(in, out, scratch);

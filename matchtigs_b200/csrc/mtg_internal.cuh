@@ -200,12 +200,28 @@ struct DevStats {
     unsigned long long candidates;
     unsigned long long truncated;
     unsigned long long overflow;
+    unsigned long long labels;      // labelled nodes summed over the searches (tier 0): the "distance array size" of a search
+    unsigned long long max_labels;  // largest number of labelled nodes of one search (tier 0)
+    unsigned long long max_open;    // largest number of open (labelled, unsettled) nodes of one search: the "heap size"
 };
 
 }  // namespace mtg
 
+// The parity assumptions of SURVEY.md Appendix C as switches (defaults = the assumptions as stated there).  A golden
+// output of the real reference that disagrees with an assumption is then a flag flip here and in the oracle
+// (mto_set_option, same names), not a rewrite.  Set with mtg_ctx_set_option or MTG_ASSUME_<NAME>=1 in the environment.
+struct mtg_options {
+    int p1_tie_desc = 0;          // P1: ties inside a distance level settle the LARGER node id first
+    int p1_exclusive_bound = 0;   // P1: the search bound k-1 is exclusive
+    int p2_self_mirror_zero = 0;  // P2: a self-mirror node never counts as unbalanced in the imbalance scan
+    int p3_oldest_first = 0;      // P3: out-edges are iterated oldest first
+    int p6_bcalm_kmer_numbering = 0;  // P6: --bcalm-in numbers nodes like --fa-in (k-mer join, links ignored)
+    int p7_first_root_wins = 0;   // P7: union of equal ranks attaches the second root below the first
+};
+
 struct mtg_ctx {
     int device = 0;
+    mtg_options opt;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     cudaEvent_t ev_build[3] = {nullptr, nullptr, nullptr};  // start of the last graph build, end of its parsing, end of the build

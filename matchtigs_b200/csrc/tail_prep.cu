@@ -20,13 +20,18 @@ namespace {
 
 constexpr int TB = 256;
 
-__global__ void __launch_bounds__(TB) leftover_flags(const i32* __restrict__ mult, const u32* __restrict__ mirror, u64 N,
-                                                     u32* __restrict__ f_self, u32* __restrict__ f_out, u32* __restrict__ f_in) {
+__global__ void __launch_bounds__(TB) leftover_flags(const i32* __restrict__ mult, const u32* __restrict__ mirror, const u32* __restrict__ out_deg,
+                                                     bool self_by_degree, u64 N, u32* __restrict__ f_self, u32* __restrict__ f_out,
+                                                     u32* __restrict__ f_in) {
     u64 v = (u64)blockIdx.x * TB + threadIdx.x;
     if (v >= N) return;
     const i32 m = mult[v];
     const bool self = mirror[v] == (u32)v;
-    f_self[v] = (self && m != 0) ? 1u : 0u;  // odd out-degree (find_non_eulerian_binodes_with_differences pushes (v, 0))
+    // odd out-degree (find_non_eulerian_binodes_with_differences pushes (v, 0)).  The multiplicity of a self-mirror is its
+    // degree parity, kept up to date by the matching -- unless assumption P2 is flipped and self-mirrors never took part
+    // in it: then the parity of the original degree is the answer.
+    const bool odd = self_by_degree ? (out_deg[v] & 1u) != 0 : m != 0;
+    f_self[v] = (self && odd) ? 1u : 0u;
     f_out[v] = (!self && m < 0) ? 1u : 0u;
     f_in[v] = (!self && m > 0) ? 1u : 0u;
 }
@@ -90,10 +95,10 @@ __device__ __forceinline__ u32 edge_to_of(u32 e, u64 E0, const u32* edge_to, con
 // keys in DESCENDING edge id order: a stable sort by from-node then leaves every row newest edge first
 __global__ void __launch_bounds__(TB)
     edge_sort_keys(u64 E, u64 E0, const u32* __restrict__ edge_from, const u32* __restrict__ pair_out, const u32* __restrict__ pair_in,
-                   const u32* __restrict__ mirror, u32* __restrict__ key, u32* __restrict__ val) {
+                   const u32* __restrict__ mirror, bool oldest_first, u32* __restrict__ key, u32* __restrict__ val) {
     u64 q = (u64)blockIdx.x * TB + threadIdx.x;
     if (q >= E) return;
-    const u32 e = (u32)(E - 1 - q);
+    const u32 e = oldest_first ? (u32)q : (u32)(E - 1 - q);  // assumption P3: newest edge first
     key[q] = edge_from_of(e, E0, edge_from, pair_out, pair_in, mirror);
     val[q] = e;
 }
@@ -192,7 +197,8 @@ void tail_leftover(mtg_ctx* ctx, TailLeftover& lo) {
     DBuf<u32> f_self, f_out, f_in, p_self, p_out, p_in, totals;
     for (DBuf<u32>* b : {&f_self, &f_out, &f_in, &p_self, &p_out, &p_in}) b->resize(N, s);
     totals.resize(4, s);
-    MTG_LAUNCH(ctx, leftover_flags, grid_for(N, TB), TB, 0, ctx->final_mult.p, ctx->mirror.p, N, f_self.p, f_out.p, f_in.p);
+    MTG_LAUNCH(ctx, leftover_flags, grid_for(N, TB), TB, 0, ctx->final_mult.p, ctx->mirror.p, ctx->out_deg.p, ctx->opt.p2_self_mirror_zero != 0, N,
+               f_self.p, f_out.p, f_in.p);
     exclusive_sum_u32(ctx, f_self.p, p_self.p, N, totals.p + 0);
     exclusive_sum_u32(ctx, f_out.p, p_out.p, N, totals.p + 1);
     exclusive_sum_u32(ctx, f_in.p, p_in.p, N, totals.p + 2);
@@ -253,7 +259,7 @@ void tail_build_records(mtg_ctx* ctx, const u32* breaking_pairs, u64 n_break, Ta
     key_b.resize(E, s);
     val_a.resize(E, s);
     val_b.resize(E, s);
-    if (E) MTG_LAUNCH(ctx, edge_sort_keys, grid_for(E, TB), TB, 0, E, E0, ctx->edge_from.p, pair_out.p, pair_in.p, ctx->mirror.p, key_a.p, val_a.p);
+    if (E) MTG_LAUNCH(ctx, edge_sort_keys, grid_for(E, TB), TB, 0, E, E0, ctx->edge_from.p, pair_out.p, pair_in.p, ctx->mirror.p, ctx->opt.p3_oldest_first != 0, key_a.p, val_a.p);
     const int which = radix_sort_pairs_u32(ctx, key_a.p, key_b.p, val_a.p, val_b.p, E, bits_for(N));
     row_ptr.resize(N + 1, s);
     cap.resize(N, s);

@@ -12,7 +12,15 @@
 // traitgraph 8.1.2, petgraph 0.7.1, genome-graph 11.0.0, compact-genome 12.0.1,
 // disjoint-sets 0.4.2).  In-repo logic is restated from the cited file:line; the
 // dependency semantics are restated from their published algorithms (SURVEY.md
-// Appendix A) and every such assumption is named P1..P7 where it is used.
+// Appendix A) and every such assumption is named P1..P7 where it is used.  Each one is a switch
+// (mto_set_option; same names as mtg_ctx_set_option of the product): a golden output of the real
+// reference that contradicts an assumption is then a flag flip on both sides, not a rewrite.
+//   p1_tie_desc, p1_exclusive_bound   Dijkstra settle order / bound        (traitgraph-algo)
+//   p2_self_mirror_zero               imbalance of self-mirror nodes       (bigraph)
+//   p3_oldest_first                   adjacency iteration order            (petgraph)
+//   p4_*, p5_*                        Euler policy, FASTA numbering: registered, no alternative implemented (nonzero is refused)
+//   p6_bcalm_kmer_numbering           bcalm2 reader numbers like the FASTA reader (genome-graph)
+//   p7_first_root_wins                union-find tie rule                  (disjoint-sets)
 //
 // Everything is single-file C++17, no dependencies.  All arithmetic is integer.
 // =====================================================================================
@@ -41,6 +49,11 @@ using u64 = uint64_t;
 using i64 = int64_t;
 constexpr u32 NONE = 0xFFFFFFFFu;
 
+struct Options {
+    int p1_tie_desc = 0, p1_exclusive_bound = 0, p2_self_mirror_zero = 0, p3_oldest_first = 0, p6_bcalm_kmer_numbering = 0,
+        p7_first_root_wins = 0;
+};
+
 struct OracleError {
     std::string msg;
 };
@@ -63,6 +76,8 @@ struct Graph {
     std::vector<u8> forward;              // CliEdgeData.forward (src/bin.rs:227)
     std::vector<u32> unitig;              // sequence handle (unitig index) for original edges
     std::vector<u32> out_deg, in_deg;
+    std::vector<u32> tail_out, tail_in;   // last list element per node (only used with oldest_first)
+    bool oldest_first = false;            // assumption P3 flipped: append at the tail instead of inserting at the head
 
     u32 node_count() const { return (u32)mirror.size(); }
     u32 edge_count() const { return (u32)from.size(); }
@@ -70,6 +85,8 @@ struct Graph {
         mirror.push_back(NONE);
         head_out.push_back(NONE);
         head_in.push_back(NONE);
+        tail_out.push_back(NONE);
+        tail_in.push_back(NONE);
         out_deg.push_back(0);
         in_deg.push_back(0);
         return (u32)mirror.size() - 1;
@@ -83,10 +100,21 @@ struct Graph {
         u32 e = (u32)from.size();
         from.push_back(a);
         to.push_back(b);
-        next_out.push_back(head_out[a]);
-        head_out[a] = e;
-        next_in.push_back(head_in[b]);
-        head_in[b] = e;
+        if (!oldest_first) {
+            next_out.push_back(head_out[a]);
+            head_out[a] = e;
+            next_in.push_back(head_in[b]);
+            head_in[b] = e;
+        } else {
+            next_out.push_back(NONE);
+            next_in.push_back(NONE);
+            if (tail_out[a] == NONE) head_out[a] = e;
+            else next_out[tail_out[a]] = e;
+            tail_out[a] = e;
+            if (tail_in[b] == NONE) head_in[b] = e;
+            else next_in[tail_in[b]] = e;
+            tail_in[b] = e;
+        }
         weight.push_back(w);
         dummy_id.push_back(dummy);
         forward.push_back(fwd ? 1 : 0);
@@ -106,8 +134,8 @@ struct Graph {
 
 // bigraph::algo::eulerian::compute_eulerian_superfluous_out_biedges (assumption P2, SURVEY A.2;
 // call site greedytigs/mod.rs:230).
-inline i64 superfluous_out(const Graph& g, u32 v) {
-    if (g.is_self_mirror(v)) return (i64)(g.out_deg[v] % 2);
+inline i64 superfluous_out(const Graph& g, u32 v, bool self_mirror_zero = false) {
+    if (g.is_self_mirror(v)) return self_mirror_zero ? 0 : (i64)(g.out_deg[v] % 2);
     return (i64)g.out_deg[v] - (i64)g.in_deg[v];
 }
 
@@ -197,6 +225,7 @@ ParsedFasta parse_fasta(const char* text, size_t len, bool bcalm) {
 struct UnionFind {
     std::vector<u32> parent;
     std::vector<u8> rank;
+    bool first_root_wins = false;  // assumption P7 flipped
     explicit UnionFind(size_t n) : parent(n), rank(n, 0) {
         for (size_t i = 0; i < n; i++) parent[i] = (u32)i;
     }
@@ -213,7 +242,10 @@ struct UnionFind {
         if (a == b) return;
         if (rank[a] > rank[b]) parent[b] = a;
         else if (rank[b] > rank[a]) parent[a] = b;
-        else {
+        else if (first_root_wins) {
+            parent[b] = a;
+            rank[a]++;
+        } else {
             parent[a] = b;
             rank[b]++;
         }
@@ -226,6 +258,9 @@ struct Walk {
 
 struct Stats {
     u64 dijkstra_calls = 0, settled = 0, relaxed = 0, heap_pops = 0, candidates = 0;
+    // the reference's DijkstraPerformanceCounter (greedytigs/mod.rs:647-673): iterations = heap pops, unnecessary heap
+    // elements = stale pops, heap / distance-array sizes as maxima per search (max and sum over the searches)
+    u64 stale_pops = 0, max_max_heap = 0, sum_max_heap = 0, max_max_dist_array = 0, sum_max_dist_array = 0;
     u64 sources = 0, in_nodes = 0, self_mirror_unbalanced = 0;
     u64 breaking_edges = 0, cycles = 0;
     double t_parse = 0, t_build = 0, t_scan = 0, t_dijkstra = 0, t_insert = 0, t_eulerise = 0, t_euler = 0, t_break = 0, t_write = 0, t_bitvector = 0;
@@ -248,6 +283,7 @@ struct Oracle {
     std::vector<i64> c_edge_out;
     std::vector<u64> c_insert_out, c_limits;
     Stats st;
+    Options opt;
     std::string err;
     int euler_fast = 0;
     // which outputs run_greedy produces (bench arms produce exactly what the GPU arm produces): 1 GFA, 2 FASTA, 4 bitvector, 8 C API
@@ -313,6 +349,7 @@ inline u32 bwd_out(u32 u) { return u * 4 + 1; }
 void build_from_links(Oracle& o, u32 U, const std::vector<Link>& links, const std::vector<u64>& weights) {
     Graph& g = o.g;
     UnionFind uf((size_t)U * 4);
+    uf.first_root_wins = o.opt.p7_first_root_wins != 0;
     for (const Link& l : links) {
         if (l.a >= U || l.b >= U) fail("link references unknown unitig");
         u32 out_a = l.sa ? fwd_out(l.a) : bwd_out(l.a);
@@ -356,7 +393,8 @@ struct Dijkstra {
     std::vector<u32> epoch_of;
     std::vector<u32> dist;
     u32 epoch = 0;
-    std::priority_queue<std::pair<u64, u32>, std::vector<std::pair<u64, u32>>, std::greater<>> heap;
+    u32 tie_flip = 0;  // assumption P1 flipped (p1_tie_desc): ties inside a distance go to the larger node id
+    std::priority_queue<std::pair<u64, u32>, std::vector<std::pair<u64, u32>>, std::greater<>> heap;  // (weight, node ^ tie_flip)
     explicit Dijkstra(u32 n) : epoch_of(n, 0), dist(n, 0) {}
 
     template <class IsTarget>
@@ -371,13 +409,17 @@ struct Dijkstra {
             dist[v] = (u32)w;
         };
         set(source, 0);
-        heap.push({0, source});
-        u64 settled = 0, relaxed = 0, pops = 0;
+        heap.push({0, source ^ tie_flip});
+        u64 settled = 0, relaxed = 0, pops = 0, stale = 0, labels = 1, max_heap = 1;
         while (!heap.empty()) {
-            auto [w, v] = heap.top();
+            auto [w, vk] = heap.top();
+            const u32 v = vk ^ tie_flip;
             heap.pop();
             pops++;
-            if (get(v) < w) continue;  // stale
+            if (get(v) < w) {  // stale
+                stale++;
+                continue;
+            }
             if (w > max_weight) break;
             settled++;
             if (is_target(v) && !(forbid_source_target && v == source)) {
@@ -389,8 +431,10 @@ struct Dijkstra {
                 u64 nw = w + g.weight[e];
                 u32 u = g.to[e];
                 if (nw < get(u)) {
+                    labels += epoch_of[u] != epoch;
                     set(u, nw);
-                    heap.push({nw, u});
+                    heap.push({nw, u ^ tie_flip});
+                    max_heap = std::max<u64>(max_heap, heap.size());
                 }
             }
         }
@@ -399,6 +443,11 @@ struct Dijkstra {
             st->settled += settled;
             st->relaxed += relaxed;
             st->heap_pops += pops;
+            st->stale_pops += stale;
+            st->max_max_heap = std::max(st->max_max_heap, max_heap);
+            st->sum_max_heap += max_heap;
+            st->max_max_dist_array = std::max(st->max_max_dist_array, labels);
+            st->sum_max_dist_array += labels;
         }
     }
 };
@@ -432,7 +481,7 @@ void greedy_paths(Oracle& o, u32 threads) {
     o.in_node_map0.assign(n, 0);
     o.mult0.assign(n, 0);
     for (u32 v = 0; v < n; v++) {
-        i64 diff = superfluous_out(g, v);
+        i64 diff = superfluous_out(g, v, o.opt.p2_self_mirror_zero != 0);
         if (g.is_self_mirror(v) && diff != 0) {
             o.st.in_nodes++;
             o.in_node_map0[v] = 1;
@@ -464,6 +513,7 @@ void greedy_paths(Oracle& o, u32 threads) {
     const std::vector<u32>& out_nodes = o.out_nodes;
     std::vector<Stats> tstats(threads);
 
+    const u64 max_weight = k - 1 - (o.opt.p1_exclusive_bound ? 1 : 0);
     auto compute_dijkstras = [&](Dijkstra& dj, std::vector<std::pair<u32, u64>>& distances, std::vector<u32>& shortest_paths,
                                  size_t lo, size_t hi, Stats& st) {
         auto is_target = [&](u32 v) { return in_node_map[v].load(std::memory_order_relaxed) != 0; };
@@ -477,7 +527,7 @@ void greedy_paths(Oracle& o, u32 threads) {
             if (m == 0) continue;  // :318-320
             while (m > 0) {        // :322
                 size_t target_amount = (size_t)(m + 1);
-                dj.shortest_path_lens(g, out_node, is_target, target_amount, k - 1, true, distances, &st);
+                dj.shortest_path_lens(g, out_node, is_target, target_amount, max_weight, true, distances, &st);
                 if (distances.empty()) break;  // :338-346
                 bool abort_after_this = distances.size() < target_amount;  // :348
                 for (auto& [in_node, distance] : distances) {              // :350
@@ -545,6 +595,7 @@ void greedy_paths(Oracle& o, u32 threads) {
 
     auto worker = [&](u32 tid) {
         Dijkstra dj(n);
+        dj.tie_flip = o.opt.p1_tie_desc ? 0xFFFFFFFFu : 0u;
         std::vector<std::pair<u32, u64>> distances;
         std::vector<u32> shortest_paths;
         size_t chunk_size = 1024;  // :570
@@ -583,6 +634,11 @@ void greedy_paths(Oracle& o, u32 threads) {
         o.st.settled += s.settled;
         o.st.relaxed += s.relaxed;
         o.st.heap_pops += s.heap_pops;
+        o.st.stale_pops += s.stale_pops;
+        o.st.max_max_heap = std::max(o.st.max_max_heap, s.max_max_heap);
+        o.st.sum_max_heap += s.sum_max_heap;
+        o.st.max_max_dist_array = std::max(o.st.max_max_dist_array, s.max_max_dist_array);
+        o.st.sum_max_dist_array += s.sum_max_dist_array;
     }
     o.st.t_dijkstra += now_s() - t1;
 }
@@ -964,7 +1020,8 @@ void run_greedy(Oracle& o, u32 threads) {
 // entry; it is the same Dijkstra with target_amount = infinity against the initial target map.
 void candidates_of(Oracle& o, Dijkstra& dj, u32 src, std::vector<std::pair<u32, u64>>& out) {
     auto is_target = [&](u32 v) { return o.in_node_map0[v] != 0; };
-    dj.shortest_path_lens(o.g, src, is_target, (size_t)-1, (u64)o.k - 1, true, out, nullptr);
+    dj.tie_flip = o.opt.p1_tie_desc ? 0xFFFFFFFFu : 0u;
+    dj.shortest_path_lens(o.g, src, is_target, (size_t)-1, (u64)o.k - 1 - (o.opt.p1_exclusive_bound ? 1 : 0), true, out, nullptr);
 }
 
 }  // namespace
@@ -993,9 +1050,12 @@ const char* mto_error(void* h) { return ((Oracle*)h)->err.c_str(); }
 
 static void reset_keep_options(Oracle& o) {
     const int ef = o.euler_fast, outs = o.outputs;
+    const Options opt = o.opt;
     o = Oracle();
     o.euler_fast = ef;
     o.outputs = outs;
+    o.opt = opt;
+    o.g.oldest_first = opt.p3_oldest_first != 0;
 }
 
 // mode 0: --fa-in semantics (k-mer hashing); mode 1: --bcalm-in semantics (links, P6).
@@ -1010,7 +1070,7 @@ int mto_load_text(void* h, const char* text, size_t len, int k, int mode) {
         t0 = now_s();
         o.seqs = std::move(pf.seqs);
         o.have_seqs = true;
-        if (mode == 0) {
+        if (mode == 0 || o.opt.p6_bcalm_kmer_numbering) {  // P6 flipped: the bcalm2 reader numbers like the FASTA reader
             build_from_kmers(o);
         } else {
             std::vector<u64> w(o.seqs.size());
@@ -1049,6 +1109,22 @@ int mto_set_option(void* h, const char* name, int value) {
         o.outputs = value;
         return 0;
     }
+    struct {
+        const char* name;
+        int* slot;
+    } table[] = {{"p1_tie_desc", &o.opt.p1_tie_desc},
+                 {"p1_exclusive_bound", &o.opt.p1_exclusive_bound},
+                 {"p2_self_mirror_zero", &o.opt.p2_self_mirror_zero},
+                 {"p3_oldest_first", &o.opt.p3_oldest_first},
+                 {"p6_bcalm_kmer_numbering", &o.opt.p6_bcalm_kmer_numbering},
+                 {"p7_first_root_wins", &o.opt.p7_first_root_wins}};
+    for (auto& t : table)
+        if (!std::strcmp(name, t.name)) {
+            *t.slot = value;
+            return 0;
+        }
+    // registered assumptions without an implemented alternative: only the assumed value is accepted
+    if (!std::strcmp(name, "p4_euler_policy") || !std::strcmp(name, "p5_fasta_numbering")) return value == 0 ? 0 : -1;
     return -1;
 }
 
@@ -1098,7 +1174,12 @@ size_t mto_num(void* h, const char* name) {
     if (n == "dijkstra_calls") return o.st.dijkstra_calls;
     if (n == "settled") return o.st.settled;
     if (n == "relaxed") return o.st.relaxed;
-    if (n == "heap_pops") return o.st.heap_pops;
+    if (n == "heap_pops" || n == "iterations") return o.st.heap_pops;
+    if (n == "unnecessary_heap_elements") return o.st.stale_pops;
+    if (n == "max_max_heap_size") return o.st.max_max_heap;
+    if (n == "sum_max_heap_size") return o.st.sum_max_heap;
+    if (n == "max_max_distance_array_size") return o.st.max_max_dist_array;
+    if (n == "sum_max_distance_array_size") return o.st.sum_max_dist_array;
     if (n == "breaking_edges") return o.st.breaking_edges;
     return (size_t)-1;
 }

@@ -30,8 +30,8 @@ def ctx(mt):
     c.close()
 
 
-def run_oracle(text, k, mode):
-    o = oracle.Oracle()
+def run_oracle(text, k, mode, **opt):
+    o = oracle.Oracle(**opt)
     (o.load_fasta if mode == "fasta" else o.load_bcalm)(text, k)
     return o.run()
 
@@ -42,8 +42,9 @@ def build(mt, ctx, text, k, mode, device_parse=True):
     return mt.read_bigraph_from_bcalm2_as_edge_centric(text, k, ctx, device_parse=device_parse)
 
 
-def compare_all(mt, ctx, text, k, mode, cap=8, dbg_valid=False, check_props=False):
-    o = run_oracle(text, k, mode)
+def compare_all(mt, ctx, text, k, mode, cap=8, dbg_valid=False, check_props=False, opt=None):
+    """`opt`: parity-assumption switches, applied to the oracle here; the caller has set the same ones on `ctx`."""
+    o = run_oracle(text, k, mode, **(opt or {}))
     g = build(mt, ctx, text, k, mode)
     U = o.num("unitigs")
     # --- step 1: graph ---
@@ -400,3 +401,45 @@ def test_cli_end_to_end(mt, tmp_path):
         assert gzip.open(tmp_path / "o.gfa.gz", "rb").read() == o.text("gfa")
         assert (tmp_path / "o.fa").read_bytes() == o.text("fasta")
         assert (tmp_path / "o.bv").read_bytes() == o.text("bitvector")
+
+
+@pytest.mark.parametrize("name", ["p1_tie_desc", "p1_exclusive_bound", "p2_self_mirror_zero", "p3_oldest_first",
+                                  "p6_bcalm_kmer_numbering", "p7_first_root_wins"])
+def test_assumption_switches_flip_both_sides(mt, name):
+    """SURVEY.md Appendix C: every assumption about the un-vendored crates is a switch of the oracle AND of the product;
+    flipped on both sides the CUDA path must again equal the oracle at every stage, on both readers, all search tiers."""
+    c = mt.Context(0)
+    try:
+        c.set_option(name, 1)
+        for seed in range(3):
+            rng = random.Random(31_000 + seed)
+            k = 2 * rng.randint(2, 8) + 1
+            g = tools.genome(rng.randint(500, 6000), 70 + seed, families=rng.randint(1, 5), copies=rng.randint(2, 6), min_len=k,
+                             max_len=rng.randint(k + 1, 150), divergence=rng.choice([0.0, 0.03, 0.1]), tandem_arrays=rng.randint(0, 3))
+            text, _, _ = tools.unitigs(g, k)
+            for mode in ("fasta", "bcalm"):
+                compare_all(mt, c, text, k, mode, cap=rng.choice([2, 8, 16]), dbg_valid=True, check_props=True, opt={name: 1})
+            # dense arbitrary records: long candidate lists, parallel edges, self-mirrors, the warp and CTA search tiers
+            kk = rng.randint(3, 11)
+            text = random_fasta(rng, rng.randint(50, 500), kk, max_extra=rng.choice([0, 4, 20]), pool=rng.choice([2, 4, 9]))
+            compare_all(mt, c, text, kk, "fasta", cap=rng.choice([1, 4, 16]), opt={name: 1})
+        with pytest.raises(mt.MatchtigsError):
+            c.set_option("no_such_assumption", 1)
+    finally:
+        c.close()
+
+
+def test_performance_counters_and_cli_lines(mt, ctx):
+    """--dijkstra-performance-data-type Complete (greedytigs/mod.rs:647-673): the GPU path's counters in the reference's lines."""
+    from matchtigs_b200 import cli
+    g = tools.genome(30_000, 3, families=6, copies=6, min_len=40, max_len=400, divergence=0.03, tandem_arrays=5)
+    text, _, _ = tools.unitigs(g, 21)
+    o, st = compare_all(mt, ctx, text, 21, "fasta", cap=16)
+    assert st["labelled_nodes"] >= st["settled_nodes"] > 0
+    assert 1 <= st["max_open_nodes"] <= st["max_labelled_nodes"] <= st["labelled_nodes"]
+    # the reference's search stops after m+1 targets; the GPU searches to the cap, so it labels at least as much per search
+    assert st["max_labelled_nodes"] >= 1 and o.num("max_max_distance_array_size") >= 1
+    lines = cli.performance_lines(st)
+    assert lines[0] == "Dijkstras had a factor of 0.000 unnecessary heap elements"
+    assert lines[1] == f"Dijktras had a maximum maximum heap size of {st['max_open_nodes']}"
+    assert lines[2] == f"Dijktras had a maximum maximum distance array size of {st['max_labelled_nodes']}"

@@ -128,3 +128,65 @@ def test_capi_encoding_matches_walks():
                 assert eo[pos] == (int(uni[e]) if fwd[e] else -int(uni[e])) and io_[pos] == 0
             pos += 1
         assert lim[i] == pos
+
+
+# ---- parity-assumption switches and the reference's Dijkstra performance counters ----
+ASSUMPTIONS = ("p1_tie_desc", "p1_exclusive_bound", "p2_self_mirror_zero", "p3_oldest_first", "p6_bcalm_kmer_numbering",
+               "p7_first_root_wins")
+
+
+def run_opt(text, k, mode, fast=True, **opt):
+    o = oracle.Oracle(euler_fast=fast, **opt)
+    (o.load_fasta if mode == "fasta" else o.load_bcalm)(text, k)
+    return o.run()
+
+
+@pytest.mark.parametrize("name", ASSUMPTIONS)
+def test_every_assumption_switch_gives_a_valid_tig_set(name):
+    """Whichever way an assumption about the un-vendored crates falls, the result must still be a correct tig set
+    (spectrum preserved, bitvector property, walk invariants); and each switch must be able to change the bytes."""
+    changed = False
+    for seed in range(6):
+        rng = random.Random(4200 + seed)
+        k = rng.choice([5, 7, 9])
+        text = random_fasta(rng, rng.randint(30, 200), k, max_extra=8, pool=rng.choice([3, 6, 12]))
+        mode = "bcalm" if name.startswith(("p6", "p7")) else "fasta"
+        if mode == "bcalm":  # links need a real compacted graph
+            g = tools.genome(3000 + 500 * seed, 900 + seed, families=4, copies=5, min_len=k, max_len=80, divergence=0.05, tandem_arrays=2)
+            text, _, _ = tools.unitigs(g, k)
+        base, alt = run_opt(text, k, mode), run_opt(text, k, mode, **{name: 1})
+        check_tig_invariants(text, k, alt.text("gfa"), alt.text("fasta"), alt.text("bitvector"), dbg_valid=(mode == "bcalm"))
+        changed |= alt.text("gfa") != base.text("gfa")
+    assert changed, f"{name} never changed an output: the switch is not wired"
+
+
+def test_p3_fast_euler_equals_faithful_under_the_switch():
+    for seed in range(4):
+        rng = random.Random(5100 + seed)
+        text = random_fasta(rng, rng.randint(20, 200), 7, max_extra=10, pool=rng.choice([4, 10]))
+        a, b = run_opt(text, 7, "fasta", fast=False, p3_oldest_first=1), run_opt(text, 7, "fasta", fast=True, p3_oldest_first=1)
+        assert a.text("gfa") == b.text("gfa")
+
+
+def test_registered_assumptions_without_alternative_refuse_nonzero():
+    o = oracle.Oracle()
+    o.set_option("p4_euler_policy", 0)
+    o.set_option("p5_fasta_numbering", 0)
+    with pytest.raises(KeyError):
+        o.set_option("p4_euler_policy", 1)
+    with pytest.raises(KeyError):
+        o.set_option("no_such_option", 1)
+
+
+def test_reference_performance_counters():
+    """DijkstraPerformanceCounter semantics (greedytigs/mod.rs:647-673): iterations = heap pops, unnecessary heap elements =
+    stale pops, heap / distance-array sizes as per-search maxima."""
+    g = tools.genome(30_000, 3, families=6, copies=6, min_len=40, max_len=400, divergence=0.03, tandem_arrays=5)
+    text, _, _ = tools.unitigs(g, 21)
+    o = run_opt(text, 21, "fasta")
+    it, un, calls = o.num("iterations"), o.num("unnecessary_heap_elements"), o.num("dijkstra_calls")
+    assert it == o.num("settled") + un or it >= o.num("settled")  # the pop that exceeds the bound is an iteration, not a settle
+    assert 0 <= un < it and calls > 0
+    assert 1 <= o.num("max_max_heap_size") <= o.num("sum_max_heap_size") <= calls * o.num("max_max_heap_size")
+    assert 1 <= o.num("max_max_distance_array_size") <= o.num("sum_max_distance_array_size")
+    assert o.num("max_max_heap_size") <= o.num("sum_max_distance_array_size")
