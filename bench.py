@@ -219,6 +219,13 @@ def run_ours(args):
     text_host = torch.frombuffer(bytearray(text), dtype=torch.uint8).pin_memory()  # the unitig file content, page-locked
     text_dev = text_host.cuda()                                                   # ... and resident in HBM
     ctx = mt.Context(local_rank)
+    if world > 1:
+        # rendezvous of the library's own NCCL communicator: rank 0 creates the id, torch.distributed only carries its bytes
+        uid = [mt.Context.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init(uid[0], rank, world)
+        lo_b, hi_b = sharding.text_slice(text_host.numel(), rank, world)
+        text_part = text_host[lo_b:hi_b].clone().pin_memory()  # this rank's share of the file, page-locked
     ext = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
@@ -258,9 +265,12 @@ def run_ours(args):
             # the file content already in HBM: records parsed on the device -> graph
             call("parse+graph_build", ctx.build_graph_from_text, None, k, bcalm=bcalm, device_ptr=text_dev.data_ptr(),
                  length=text_dev.numel())
-        else:
+        elif world == 1:
             # end to end: raw file bytes in page-locked host memory -> H2D -> parsed on the device -> graph
             call("parse+graph_build", ctx.build_graph_from_text, text_host.numpy(), k, bcalm=bcalm)
+        else:
+            # every rank uploads 1/world of the file over its own PCIe link; the slices are all-gathered over NVLink
+            call("parse+graph_build", ctx.build_graph_from_text_slices, text_part.numpy(), text_host.numel(), k, bcalm)
         dg = ctx.diagnostics()
         phase_s["(parse, device)"] = phase_s.get("(parse, device)", 0.0) + dg["build_ms"]["parse"] * 1e-3
         if world == 1:
@@ -268,14 +278,19 @@ def run_ours(args):
             call("match", ctx.greedy_match)
         else:
             call("dijkstra", ctx.dijkstra_candidates, CAP, rank, world)
-            rec_all, meta_all = call("all_gather", sharding.all_gather_candidates, ctx, dist, torch, world)  # NCCL over NVLink
-            call("match", ctx.greedy_match, rec_all.data_ptr(), meta_all.data_ptr(), world)
+            rec_all, meta_all = call("all_gather", ctx.allgather_candidates)  # ncclAllGather inside the library, over NVLink
+            call("match", ctx.greedy_match, rec_all, meta_all, world)
         if rank == 0:
             call("tail", ctx.finish_walks)
+        if world == 1:
             # results land in page-locked host memory owned by the context (zero-copy views)
             bv = call("emit_bitvector", ctx.dup_bitvector_view)
             return call("emit_gfa", ctx.assemble_tigs_view, "gfa"), bv
-        return None, None
+        # sharded emission: the walks go to every rank, each assembles and downloads its share of the two texts
+        call("broadcast_walks", ctx.broadcast_walks, 0)
+        w_lo, w_hi = sharding.walk_share(ctx.walk_count(), rank, world)
+        bv = call("emit_bitvector", ctx.dup_bitvector_range_view, w_lo, w_hi)
+        return call("emit_gfa", ctx.assemble_tigs_range_view, "gfa", w_lo, w_hi), bv
 
     def timed(resident: bool, steps: int, warmup: int):
         for _ in range(warmup):
@@ -329,10 +344,21 @@ def run_ours(args):
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
     settled, relaxed, cands, searched = (float(x) for x in cnt.cpu())
 
+    parts = None
+    if world > 1:
+        # (offset, length, sha256) of every rank's share of the two texts, for the byte comparison with the oracle on rank 0
+        import hashlib
+        mine = [(int(off), int(v.size), hashlib.sha256(v.tobytes()).hexdigest(), int(tot)) for (v, off, tot) in out]
+        parts = [None] * world
+        dist.all_gather_object(parts, mine)
     if rank == 0:
         gi = ctx.graph_info()
         U = gi["unitigs"]
-        gfa, bv = (x.tobytes() for x in out)
+        if world == 1:
+            gfa, bv = (x.tobytes() for x in out)
+            out_bytes = len(gfa) + len(bv)
+        else:
+            out_bytes = sum(p[0][1] + p[1][1] for p in parts)
         peak, peak_src = load_peaks()
         # algorithmic bytes of the Dijkstra kernel: 12 B per settled node (row_ptr pair + target probe),
         # 5 B per relaxed short edge (col + weight), 8 B per emitted candidate
@@ -347,7 +373,19 @@ def run_ours(args):
         # cpu baseline: the oracle at 1 thread (deterministic reference semantics), whole workload, once; its outputs are
         # also what the GPU arm's bytes are compared with
         o, cpu_s, cpu_ph = oracle_pass(text, k, bcalm, 1)
-        identical = (gfa == o.text("gfa")) and (bv == o.text("bitvector"))
+        if world == 1:
+            identical = (gfa == o.text("gfa")) and (bv == o.text("bitvector"))
+        else:
+            import hashlib
+            ref = (o.text("gfa"), o.text("bitvector"))
+            identical = True
+            for which in (0, 1):
+                covered = 0
+                for p in sorted(parts, key=lambda p: p[which][0]):
+                    off, n, digest, tot = p[which]
+                    identical &= off == covered and tot == len(ref[which]) and hashlib.sha256(ref[which][off:off + n]).hexdigest() == digest
+                    covered += n
+                identical &= covered == len(ref[which])
         ref_settled, ref_dj_s = o.num("settled"), o.time("dijkstra")
         del o
         # T_compute: graph build from parsed records .. bitvector; T_wall adds parse, H2D/D2H and the GFA
@@ -370,7 +408,9 @@ def run_ours(args):
                     "phases_ms_rank0": stats_e2e["phases_ms"], "tail_ms_rank0": stats_e2e["tail_ms"],
                     "h2d_bytes_per_step": int(text_host.numel()), "input": "unitig file content (parsed on the device)",
                     "host_link": link,
-                    "d2h_bytes_per_step": int(len(gfa) + len(bv))},
+                    "d2h_bytes_per_step": int(out_bytes),
+                    "sharded": None if world == 1 else "every rank uploads 1/N of the file (all-gather over NVLink) and downloads "
+                                                       "the output bytes of 1/N of the walks"},
             "gpu_launches": int(launches),
             "settled_nodes": {"gpu_kernel": settled, "reference_semantics": ref_settled,
                               "note": "the GPU searches every source to the candidate cap up front; the reference stops each "

@@ -179,6 +179,42 @@ int mtg_assemble_tigs(mtg_ctx* ctx, int format, char* out, uint64_t cap, uint64_
 int mtg_dup_bitvector_view(mtg_ctx* ctx, const char** out, uint64_t* out_len);
 int mtg_assemble_tigs_view(mtg_ctx* ctx, int format, const char** out, uint64_t* out_len);
 
+/* Shares of the two texts: only the bytes that belong to the walks [walk_lo, walk_hi) (clamped to the walk count; the GFA
+ * header line belongs to the share that starts at walk 0).  *byte_offset = where the share starts inside the whole text,
+ * *total_len = length of the whole text.  With the walks on every rank (mtg_broadcast_walks) each rank assembles its
+ * share on its own GPU and brings it to the host over its own PCIe link. */
+int mtg_dup_bitvector_range_view(mtg_ctx* ctx, uint64_t walk_lo, uint64_t walk_hi, const char** out, uint64_t* out_len,
+                                 uint64_t* byte_offset, uint64_t* total_len);
+int mtg_assemble_tigs_range_view(mtg_ctx* ctx, int format, uint64_t walk_lo, uint64_t walk_hi, const char** out,
+                                 uint64_t* out_len, uint64_t* byte_offset, uint64_t* total_len);
+/* Number of walks resident on the device (after mtg_finish_walks, or mtg_broadcast_walks on the receiving ranks). */
+int mtg_walk_count(mtg_ctx* ctx, uint64_t* n_walks);
+
+/* ---- multi-GPU: one process per GPU, NCCL over NVLink / NVSwitch, bound at run time ----
+ * The reference has no distributed code (its parallelism is the worker pool of greedytigs/mod.rs:557-627); here the
+ * Dijkstra sources are dealt to the ranks (source i belongs to rank i % world), the CSR graph is replicated, and ONE
+ * exchange -- an all-gather of the equally sized candidate slices -- feeds the replicated, deterministic matching.
+ *   rank 0: mtg_comm_get_unique_id(id); ship the MTG_UNIQUE_ID_BYTES bytes to the other ranks (file, pipe, MPI, ...)
+ *   all:    mtg_comm_init(ctx, id, rank, world)
+ *           mtg_build_graph_from_text_slices(...)      (or any mtg_build_graph_* with the whole input on every rank)
+ *           mtg_dijkstra_candidates(ctx, cap, rank, world); mtg_allgather_candidates(ctx, &rec, &meta);
+ *           mtg_greedy_match(ctx, rec, meta, world, &n)
+ *   rank 0: mtg_finish_walks(ctx, ...)                 (the host-sequential tail)
+ *   all:    mtg_broadcast_walks(ctx, 0); mtg_*_range_view(ctx, ..., T * rank / world, T * (rank + 1) / world, ...) */
+#define MTG_UNIQUE_ID_BYTES 128
+int mtg_comm_get_unique_id(void* id_out /* MTG_UNIQUE_ID_BYTES */);
+int mtg_comm_init(mtg_ctx* ctx, const void* unique_id, int rank, int world);
+int mtg_comm_destroy(mtg_ctx* ctx);
+/* Collective.  Returns device pointers (owned by the context) to pass to mtg_greedy_match together with `world`. */
+int mtg_allgather_candidates(mtg_ctx* ctx, void** d_records_all, void** d_meta_all);
+/* Collective.  Every rank supplies bytes [rank * slice, min((rank + 1) * slice, total_len)) of the input file, slice =
+ * mtg_text_slice_bytes(total_len, world): 1/world of the H2D traffic per PCIe link, the rest travels over NVLink. */
+uint64_t mtg_text_slice_bytes(uint64_t total_len, uint32_t world);
+int mtg_build_graph_from_text_slices(mtg_ctx* ctx, const char* part, uint64_t part_len, uint64_t total_len, int bcalm,
+                                     uint32_t k);
+/* Collective.  The walks of `root` (which ran mtg_finish_walks) become resident on every rank's device. */
+int mtg_broadcast_walks(mtg_ctx* ctx, int root);
+
 /* Everything above in order (single GPU): build -> search -> match -> walks. */
 int mtg_compute_greedytigs_from_sequences(mtg_ctx* ctx, const char* seq_ascii, const uint64_t* offsets,
                                           uint64_t unitigs, uint32_t k, uint32_t cap);

@@ -105,7 +105,7 @@ def build_product(force: bool = False, verbose: bool = False, ptxas_info: bool =
     if jobs or not PRODUCT_SO.exists() or not PRODUCT_A.exists():
         cuda_lib = str(Path(_nvcc()).resolve().parent.parent / "lib64")
         _run([_gxx(), "-shared", "-o", str(PRODUCT_SO), *[str(o) for o in objs], "-L", cuda_lib, f"-Wl,-rpath,{cuda_lib}",
-              "-lcudart", "-lgomp", "-lpthread", *NCCL_LINK], verbose)
+              "-lcudart", "-lgomp", "-lpthread", "-ldl", *NCCL_LINK], verbose)
         if PRODUCT_A.exists():
             PRODUCT_A.unlink()
         _run(["ar", "rcs", str(PRODUCT_A), *[str(o) for o in objs]], verbose)

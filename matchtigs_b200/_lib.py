@@ -24,6 +24,9 @@ EXPORTED_SYMBOLS = [
     "mtg_greedy_match", "mtg_triples_export",
     "mtg_finish_walks", "mtg_walks_export", "mtg_walks_export_capi", "mtg_host_tail", "mtg_host_free",
     "mtg_dup_bitvector", "mtg_assemble_tigs", "mtg_dup_bitvector_view", "mtg_assemble_tigs_view",
+    "mtg_dup_bitvector_range_view", "mtg_assemble_tigs_range_view", "mtg_walk_count",
+    "mtg_comm_get_unique_id", "mtg_comm_init", "mtg_comm_destroy", "mtg_allgather_candidates", "mtg_text_slice_bytes",
+    "mtg_build_graph_from_text_slices", "mtg_broadcast_walks",
     "mtg_compute_greedytigs_from_sequences", "mtg_get_search_stats", "mtg_get_diagnostics",
     "mtg_unitigs_parse", "mtg_unitigs_free", "mtg_unitigs_view",
     "matchtigs_initialise", "matchtigs_initialise_graph", "matchtigs_merge_nodes", "matchtigs_build_graph",
@@ -96,6 +99,17 @@ def load() -> C.CDLL:
     l.mtg_assemble_tigs.argtypes = [vp, i32, vp, u64, C.POINTER(u64)]
     l.mtg_dup_bitvector_view.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
     l.mtg_assemble_tigs_view.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(u64)]
+    l.mtg_dup_bitvector_range_view.argtypes = [vp, u64, u64, C.POINTER(vp), C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
+    l.mtg_assemble_tigs_range_view.argtypes = [vp, i32, u64, u64, C.POINTER(vp), C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
+    l.mtg_walk_count.argtypes = [vp, C.POINTER(u64)]
+    l.mtg_comm_get_unique_id.argtypes = [vp]
+    l.mtg_comm_init.argtypes = [vp, vp, i32, i32]
+    l.mtg_comm_destroy.argtypes = [vp]
+    l.mtg_allgather_candidates.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
+    l.mtg_text_slice_bytes.argtypes = [u64, u32]
+    l.mtg_text_slice_bytes.restype = u64
+    l.mtg_build_graph_from_text_slices.argtypes = [vp, vp, u64, u64, i32, u32]
+    l.mtg_broadcast_walks.argtypes = [vp, i32]
     l.mtg_compute_greedytigs_from_sequences.argtypes = [vp, vp, vp, u64, u32, u32]
     l.mtg_get_search_stats.argtypes = [vp, C.POINTER(SearchStats)]
     l.mtg_get_diagnostics.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]

@@ -212,6 +212,55 @@ class Context:
     def assemble_tigs(self, fmt: str = "gfa") -> bytes:
         return self.assemble_tigs_view(fmt).tobytes()
 
+    # ---- multi-GPU (one process per GPU; NCCL inside the library) ----
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """Rank 0 creates the rendezvous id; ship the bytes to the other ranks any way you like."""
+        buf = C.create_string_buffer(128)
+        rc = _lib.load().mtg_comm_get_unique_id(buf)
+        if rc != 0:
+            raise MatchtigsError(rc, "NCCL is not available (mtg_comm_get_unique_id)")
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        self._check(self._l.mtg_comm_init(self._h, C.c_char_p(unique_id), rank, world))
+        self.rank, self.world = rank, world
+
+    def comm_destroy(self):
+        self._check(self._l.mtg_comm_destroy(self._h))
+
+    def allgather_candidates(self):
+        """Collective: all-gather of the candidate slices -> (records ptr, meta ptr) for ``greedy_match(rec, meta, world)``."""
+        rec, meta = C.c_void_p(), C.c_void_p()
+        self._check(self._l.mtg_allgather_candidates(self._h, C.byref(rec), C.byref(meta)))
+        return rec.value, meta.value
+
+    def build_graph_from_text_slices(self, part: np.ndarray, total_len: int, k: int, bcalm: bool):
+        """Collective: every rank supplies its slice of the file (``sharding.text_slice``); the whole text is assembled over NVLink."""
+        part = np.ascontiguousarray(part, np.uint8)
+        self._check(self._l.mtg_build_graph_from_text_slices(self._h, _ptr(part), len(part), total_len, int(bcalm), k))
+
+    def broadcast_walks(self, root: int = 0):
+        self._check(self._l.mtg_broadcast_walks(self._h, root))
+
+    def walk_count(self) -> int:
+        n = C.c_uint64()
+        self._check(self._l.mtg_walk_count(self._h, C.byref(n)))
+        return n.value
+
+    def _range_view(self, fn, *args):
+        p, n, off, tot = C.c_void_p(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._check(fn(self._h, *args, C.byref(p), C.byref(n), C.byref(off), C.byref(tot)))
+        view = np.zeros(0, np.uint8) if n.value == 0 else np.frombuffer((C.c_char * n.value).from_address(p.value), dtype=np.uint8)
+        return view, off.value, tot.value
+
+    def dup_bitvector_range_view(self, walk_lo: int, walk_hi: int):
+        """(bytes of the walks [lo, hi), their offset in the whole bitvector text, length of the whole text)."""
+        return self._range_view(self._l.mtg_dup_bitvector_range_view, walk_lo, walk_hi)
+
+    def assemble_tigs_range_view(self, fmt: str, walk_lo: int, walk_hi: int):
+        return self._range_view(self._l.mtg_assemble_tigs_range_view, 0 if fmt == "gfa" else 1, walk_lo, walk_hi)
+
     def search_stats(self) -> dict:
         st = _lib.SearchStats()
         self._check(self._l.mtg_get_search_stats(self._h, C.byref(st)))

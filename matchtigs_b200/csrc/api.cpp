@@ -106,6 +106,7 @@ int mtg_ctx_create(mtg_ctx** out, int device) {
 void mtg_ctx_destroy(mtg_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    mtg_comm_destroy(ctx);
     cudaStream_t s = ctx->stream;
     ctx->seq_words.release(s);
     ctx->seq_off.release(s);
@@ -307,6 +308,35 @@ int mtg_assemble_tigs_view(mtg_ctx* ctx, int format, const char** out, uint64_t*
     return guarded(ctx, [&] {
         MTG_REQUIRE(out && out_len, MTG_ERR_INVALID, "null output");
         *out_len = assemble_tigs(ctx, format, nullptr, 0, false, out);
+    });
+}
+
+int mtg_dup_bitvector_range_view(mtg_ctx* ctx, uint64_t walk_lo, uint64_t walk_hi, const char** out, uint64_t* out_len, uint64_t* byte_offset,
+                                 uint64_t* total_len) {
+    return guarded(ctx, [&] {
+        MTG_REQUIRE(out && out_len, MTG_ERR_INVALID, "null output");
+        u64 where[2];
+        *out_len = dup_bitvector(ctx, nullptr, 0, false, out, walk_lo, walk_hi, where);
+        if (byte_offset) *byte_offset = where[0];
+        if (total_len) *total_len = where[1];
+    });
+}
+
+int mtg_assemble_tigs_range_view(mtg_ctx* ctx, int format, uint64_t walk_lo, uint64_t walk_hi, const char** out, uint64_t* out_len,
+                                 uint64_t* byte_offset, uint64_t* total_len) {
+    return guarded(ctx, [&] {
+        MTG_REQUIRE(out && out_len, MTG_ERR_INVALID, "null output");
+        u64 where[2];
+        *out_len = assemble_tigs(ctx, format, nullptr, 0, false, out, walk_lo, walk_hi, where);
+        if (byte_offset) *byte_offset = where[0];
+        if (total_len) *total_len = where[1];
+    });
+}
+
+int mtg_walk_count(mtg_ctx* ctx, uint64_t* n_walks) {
+    return guarded(ctx, [&] {
+        MTG_REQUIRE(ctx->have_walks && n_walks, MTG_ERR_INVALID, "no walks resident");
+        *n_walks = ctx->n_walks_dev;
     });
 }
 

@@ -18,6 +18,8 @@ namespace {
 constexpr int TB = 256;
 constexpr int CHUNK = 16;
 
+std::string gfa_header(const mtg_ctx* ctx) { return "H\tKL:Z:" + std::to_string(ctx->k) + "\n"; }  // src/bin.rs:688-693
+
 __device__ __forceinline__ u32 dec_digits(u64 v) {
     u32 d = 1;
     while (v >= 10) {
@@ -93,8 +95,9 @@ __device__ __forceinline__ char decode_base(const u64* __restrict__ words, u64 p
 
 __global__ void __launch_bounds__(TB)
     fill_text(WalkView w, int mode, const u64* __restrict__ seg_off, const u32* __restrict__ seg_len, const u32* __restrict__ seg_tig,
-              const u64* __restrict__ words, u64 total, char* __restrict__ out) {
-    const u64 q0 = ((u64)blockIdx.x * TB + threadIdx.x) * CHUNK;
+              const u64* __restrict__ words, u64 q_base, u64 total, char* __restrict__ out) {
+    // produces bytes [q_base, total) of the text into out[0 ..): a rank's share of the output, or all of it
+    const u64 q0 = q_base + ((u64)blockIdx.x * TB + threadIdx.x) * CHUNK;
     if (q0 >= total) return;
     u64 j = segment_of(seg_off, w.W, q0);
     alignas(16) char buf[CHUNK];
@@ -154,15 +157,25 @@ __global__ void __launch_bounds__(TB)
         }
     }
     if (qend - q0 == CHUNK) {
-        *reinterpret_cast<uint4*>(out + q0) = *reinterpret_cast<const uint4*>(buf);
+        *reinterpret_cast<uint4*>(out + (q0 - q_base)) = *reinterpret_cast<const uint4*>(buf);
     } else {
-        for (u64 i = 0; i < qend - q0; i++) out[q0 + i] = buf[i];
+        for (u64 i = 0; i < qend - q0; i++) out[q0 - q_base + i] = buf[i];
     }
 }
 
-// Produces the text of `mode` into the context's pinned staging buffer (full-speed DMA) and returns its length.
-// out != nullptr: additionally copied to the caller's buffer.  size_only: nothing is materialised.
-u64 emit(mtg_ctx* ctx, int mode, const char* prefix, size_t prefix_len, char* out, u64 cap, bool size_only, const char** view) {
+// byte range of the walks [lo, hi): bounds[0] = first byte, bounds[1] = one past the last, bounds[2] = length of the whole text
+__global__ void range_bounds(const u64* __restrict__ limits, const u64* __restrict__ seg_off, u64 W, u64 lo, u64 hi, u64* __restrict__ bounds) {
+    bounds[0] = lo ? seg_off[limits[lo - 1]] : 0;
+    bounds[1] = hi ? seg_off[limits[hi - 1]] : 0;
+    bounds[2] = seg_off[W];
+}
+
+// Produces the text of `mode` -- or the share of it that belongs to the walks [walk_lo, walk_hi) -- into the context's
+// pinned staging buffer (full-speed DMA) and returns the length of what was produced.  out != nullptr: additionally
+// copied to the caller's buffer.  size_only: nothing is materialised.  `where` (optional): [0] = offset of the produced
+// bytes inside the whole text, [1] = length of the whole text (both including `prefix`).
+u64 emit(mtg_ctx* ctx, int mode, const char* prefix, size_t prefix_len, char* out, u64 cap, bool size_only, const char** view,
+         u64 walk_lo = 0, u64 walk_hi = ~0ull, u64* where = nullptr) {
     MTG_REQUIRE(ctx->have_walks, MTG_ERR_INVALID, "no walks: call mtg_finish_walks first");
     MTG_REQUIRE(mode == 0 || ctx->have_seqs, MTG_ERR_INVALID, "sequences were not supplied: tig strings cannot be assembled");
     cudaStream_t s = ctx->stream;
@@ -172,58 +185,65 @@ u64 emit(mtg_ctx* ctx, int mode, const char* prefix, size_t prefix_len, char* ou
     w.dummy_w = ctx->d_dummy_w.p;
     w.unitig_w = ctx->unitig_w.p;
     w.seq_off = ctx->seq_off.p;
-    w.W = ctx->walk_edges.size();
-    w.T = ctx->walk_limits.size();
+    w.W = ctx->n_walk_edges_dev;
+    w.T = ctx->n_walks_dev;
     w.E = ctx->E;
     w.k = ctx->k;
+    walk_hi = std::min<u64>(walk_hi, w.T);
+    MTG_REQUIRE(walk_lo <= walk_hi, MTG_ERR_INVALID, "bad walk range");
+    if (walk_lo != 0) prefix_len = 0;  // the header line belongs to the share that starts the text
     PinnedBuf& stage = ctx->text_stage[mode];
-    u64 total = 0;
+    u64 h_bounds[3] = {0, 0, 0};
     DBuf<u32> seg_len, seg_tig;
-    DBuf<u64> seg_off;
+    DBuf<u64> seg_off, bounds;
     if (w.W) {
         seg_len.resize(w.W, s);
         seg_tig.resize(w.W, s);
         seg_off.resize(w.W + 1, s);
+        bounds.resize(3, s);
         MTG_LAUNCH(ctx, segment_lengths, grid_for(w.W, TB), TB, 0, w, mode, seg_len.p, seg_tig.p);
         exclusive_sum_u32_to_u64(ctx, seg_len.p, seg_off.p, w.W, seg_off.p + w.W);
-        MTG_CUDA(cudaMemcpyAsync(&total, seg_off.p + w.W, sizeof(u64), cudaMemcpyDeviceToHost, s));
+        MTG_LAUNCH(ctx, range_bounds, 1, 1, 0, w.limits, seg_off.p, w.W, walk_lo, walk_hi, bounds.p);
+        MTG_CUDA(cudaMemcpyAsync(h_bounds, bounds.p, sizeof(h_bounds), cudaMemcpyDeviceToHost, s));
         MTG_CUDA(cudaStreamSynchronize(s));
     }
+    const u64 b0 = h_bounds[0], b1 = h_bounds[1], part = b1 - b0;
+    if (where) {
+        where[0] = walk_lo ? b0 + (mode == 1 ? gfa_header(ctx).size() : 0) : 0;
+        where[1] = h_bounds[2] + (mode == 1 ? gfa_header(ctx).size() : 0);
+    }
     if (!size_only) {
-        MTG_REQUIRE(!out || cap >= total + prefix_len, MTG_ERR_INVALID, "output buffer too small");
-        stage.ensure(total + prefix_len + 1);
+        MTG_REQUIRE(!out || cap >= part + prefix_len, MTG_ERR_INVALID, "output buffer too small");
+        stage.ensure(part + prefix_len + 1);
         if (prefix_len) memcpy(stage.p, prefix, prefix_len);
-        if (total) {
+        if (part) {
             char* d_out = nullptr;
-            MTG_CUDA(cudaMallocAsync((void**)&d_out, total + CHUNK, s));
-            u64 chunks = (total + CHUNK - 1) / CHUNK;
-            MTG_LAUNCH(ctx, fill_text, grid_for(chunks, TB), TB, 0, w, mode, seg_off.p, seg_len.p, seg_tig.p, ctx->seq_words.p, total, d_out);
-            MTG_CUDA(cudaMemcpyAsync(stage.p + prefix_len, d_out, total, cudaMemcpyDeviceToHost, s));
+            MTG_CUDA(cudaMallocAsync((void**)&d_out, part + CHUNK, s));
+            u64 chunks = (part + CHUNK - 1) / CHUNK;
+            MTG_LAUNCH(ctx, fill_text, grid_for(chunks, TB), TB, 0, w, mode, seg_off.p, seg_len.p, seg_tig.p, ctx->seq_words.p, b0, b1, d_out);
+            MTG_CUDA(cudaMemcpyAsync(stage.p + prefix_len, d_out, part, cudaMemcpyDeviceToHost, s));
             MTG_CUDA(cudaStreamSynchronize(s));
             MTG_CUDA(cudaFreeAsync(d_out, s));
         }
-        if (out && total + prefix_len) memcpy(out, stage.p, total + prefix_len);
+        if (out && part + prefix_len) memcpy(out, stage.p, part + prefix_len);
         if (view) *view = stage.p;
     }
-    seg_len.release(s);
-    seg_tig.release(s);
-    seg_off.release(s);
-    return total + prefix_len;
+    return part + prefix_len;
 }
 
 }  // namespace
 
-u64 dup_bitvector(mtg_ctx* ctx, char* out, u64 cap, bool size_only, const char** view) {
-    return emit(ctx, 0, nullptr, 0, out, cap, size_only, view);
+u64 dup_bitvector(mtg_ctx* ctx, char* out, u64 cap, bool size_only, const char** view, u64 walk_lo, u64 walk_hi, u64* where) {
+    return emit(ctx, 0, nullptr, 0, out, cap, size_only, view, walk_lo, walk_hi, where);
 }
 
-u64 assemble_tigs(mtg_ctx* ctx, int format, char* out, u64 cap, bool size_only, const char** view) {
+u64 assemble_tigs(mtg_ctx* ctx, int format, char* out, u64 cap, bool size_only, const char** view, u64 walk_lo, u64 walk_hi, u64* where) {
     MTG_REQUIRE(format == MTG_FORMAT_GFA || format == MTG_FORMAT_FASTA, MTG_ERR_INVALID, "unknown text format");
     if (format == MTG_FORMAT_GFA) {
-        std::string header = "H\tKL:Z:" + std::to_string(ctx->k) + "\n";  // src/bin.rs:688-693
-        return emit(ctx, 1, header.data(), header.size(), out, cap, size_only, view);
+        const std::string header = gfa_header(ctx);
+        return emit(ctx, 1, header.data(), header.size(), out, cap, size_only, view, walk_lo, walk_hi, where);
     }
-    return emit(ctx, 2, nullptr, 0, out, cap, size_only, view);
+    return emit(ctx, 2, nullptr, 0, out, cap, size_only, view, walk_lo, walk_hi, where);
 }
 
 }  // namespace mtg

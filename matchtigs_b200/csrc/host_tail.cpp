@@ -726,6 +726,8 @@ static void finish_walks_host_prep(mtg_ctx* ctx) {
     ctx->d_walk_edges.upload(ctx->walk_edges.data(), ctx->walk_edges.size(), s);
     ctx->d_walk_limits.upload(ctx->walk_limits.data(), ctx->walk_limits.size(), s);
     ctx->d_dummy_w.upload(ctx->h_dummy_w.data(), ctx->h_dummy_w.size(), s);  // pageable sources: staged before the call returns
+    ctx->n_walk_edges_dev = ctx->walk_edges.size();
+    ctx->n_walks_dev = ctx->walk_limits.size();
     ctx->have_walks = true;
 }
 
@@ -800,6 +802,8 @@ void finish_walks(mtg_ctx* ctx) {
     ctx->d_walk_limits.upload(ctx->walk_limits.data(), ctx->walk_limits.size(), s);
     ctx->d_dummy_w.upload(ctx->h_dummy_w.data(), ctx->h_dummy_w.size(), s);
     MTG_CUDA(cudaStreamSynchronize(s));
+    ctx->n_walk_edges_dev = ctx->walk_edges.size();
+    ctx->n_walks_dev = ctx->walk_limits.size();
     ctx->have_walks = true;
 }
 

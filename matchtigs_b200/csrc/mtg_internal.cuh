@@ -283,6 +283,14 @@ struct mtg_ctx {
     mtg::DBuf<mtg::u32> d_walk_edges;
     mtg::DBuf<mtg::u64> d_walk_limits;
     mtg::DBuf<mtg::u32> d_dummy_w;    // weights of dummy edges, index = edge id - 2U
+    uint64_t n_walk_edges_dev = 0, n_walks_dev = 0;  // lengths of d_walk_edges / d_walk_limits (ranks that received the walks hold no host copy)
+
+    // ---- multi-GPU (comm.cpp) ----
+    void* comm = nullptr;             // ncclComm_t
+    uint32_t comm_rank = 0, comm_world = 1;
+    mtg::DBuf<mtg::u64> gathered_rec;   // candidate slices of all ranks: [rank][local source][cap]
+    mtg::DBuf<mtg::u32> gathered_meta;
+    bool text_event_recorded = false;   // the start of the last text build was already recorded by the caller (sliced upload)
 
     mtg::PinnedBuf text_stage[3];     // bitvector / GFA / FASTA bytes, valid until the next call of the same kind
     mtg::PinnedBuf tail_stage[6];     // DMA targets of the host tail (graph arrays for the host-prepared path; walk records,
@@ -338,8 +346,11 @@ void dijkstra_candidates(mtg_ctx* ctx, u32 cap, u32 shard_rank, u32 shard_count)
 void greedy_match(mtg_ctx* ctx, const u64* d_records_all, const u32* d_meta_all, u32 shard_count);
 
 // ---- outputs (emit.cu) ----
-u64 dup_bitvector(mtg_ctx* ctx, char* out, u64 cap, bool size_only, const char** view);
-u64 assemble_tigs(mtg_ctx* ctx, int format, char* out, u64 cap, bool size_only, const char** view);
+// walk_lo / walk_hi: only the share of the text that belongs to these walks; where[0] = its offset in the whole text, where[1] = whole length
+u64 dup_bitvector(mtg_ctx* ctx, char* out, u64 cap, bool size_only, const char** view, u64 walk_lo = 0, u64 walk_hi = ~0ull,
+                  u64* where = nullptr);
+u64 assemble_tigs(mtg_ctx* ctx, int format, char* out, u64 cap, bool size_only, const char** view, u64 walk_lo = 0, u64 walk_hi = ~0ull,
+                  u64* where = nullptr);
 
 // ---- host tail (host_tail.cpp) and its device-side preparation (tail_prep.cu) ----
 void finish_walks(mtg_ctx* ctx);

@@ -175,7 +175,8 @@ void build_graph_from_text(mtg_ctx* ctx, const char* text, u64 L, bool bcalm, u3
     MTG_REQUIRE(L == 0 || text, MTG_ERR_INVALID, "null text");
     MTG_REQUIRE(L < 0xFFFFFFF0ull, MTG_ERR_UNSUPPORTED, "text of 4 GiB or more: parse it in pieces with the host reader");
     cudaStream_t s = ctx->stream;
-    MTG_CUDA(cudaEventRecord(ctx->ev_build[0], s));
+    if (!ctx->text_event_recorded) MTG_CUDA(cudaEventRecord(ctx->ev_build[0], s));
+    ctx->text_event_recorded = false;
     auto& ws = ctx->parse_ws;
     DBuf<u32>& totals = ws.totals;
     const char* d_text = text;

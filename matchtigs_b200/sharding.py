@@ -24,14 +24,14 @@ def gathered_slot(i: int, n_sources: int, world: int) -> int:
     return (i % world) * padded_slice(n_sources, world) + i // world
 
 
-def all_gather_candidates(ctx, dist, torch, world: int):
-    """NCCL all-gather of this rank's candidate slice; returns (records[R*padded,cap], meta[R*padded]) device tensors."""
-    from .api import device_tensor
-    prec, pmeta, _n_local, cap = ctx.candidates_local()
-    padded = padded_slice(ctx.graph_info()["sources"], world)
-    rec_all = torch.empty((world * padded, cap), dtype=torch.int64, device="cuda")
-    meta_all = torch.empty((world * padded,), dtype=torch.int32, device="cuda")
-    dist.all_gather_into_tensor(rec_all, device_tensor(prec, (padded, cap), "<i8"))
-    dist.all_gather_into_tensor(meta_all, device_tensor(pmeta, (padded,), "<i4"))
-    torch.cuda.synchronize()
-    return rec_all, meta_all
+def text_slice(total_len: int, rank: int, world: int) -> tuple[int, int]:
+    """Byte range [lo, hi) of the input file that `rank` uploads (mtg_text_slice_bytes: ceil(len / world), 16-byte aligned)."""
+    sl = (total_len + world - 1) // world
+    sl = (sl + 15) // 16 * 16
+    lo = min(rank * sl, total_len)
+    return lo, min(lo + sl, total_len)
+
+
+def walk_share(n_walks: int, rank: int, world: int) -> tuple[int, int]:
+    """Walks [lo, hi) whose output bytes `rank` assembles and downloads (sharded emission)."""
+    return n_walks * rank // world, n_walks * (rank + 1) // world

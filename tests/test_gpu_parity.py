@@ -443,3 +443,39 @@ def test_performance_counters_and_cli_lines(mt, ctx):
     assert lines[0] == "Dijkstras had a factor of 0.000 unnecessary heap elements"
     assert lines[1] == f"Dijktras had a maximum maximum heap size of {st['max_open_nodes']}"
     assert lines[2] == f"Dijktras had a maximum maximum distance array size of {st['max_labelled_nodes']}"
+
+
+def test_library_nccl_entry_points_and_sharded_emission(mt):
+    """The multi-GPU entry points of the C ABI on a one-rank communicator (the driver's test box has one GPU; N > 1 runs
+    through bench.py): rendezvous, sliced upload + all-gather, candidate all-gather, walk broadcast, and the output texts
+    assembled in shares -- every share at the offset it reports, the concatenation byte-identical to the oracle."""
+    from matchtigs_b200 import sharding
+    g = tools.genome(60_000, 8, families=8, copies=6, min_len=40, max_len=400, divergence=0.03, tandem_arrays=6)
+    text, _, _ = tools.unitigs(g, 21)
+    c = mt.Context(0)
+    try:
+        c.comm_init(mt.Context.comm_unique_id(), 0, 1)
+        for mode, bcalm in (("bcalm", True), ("fasta", False)):
+            lo, hi = sharding.text_slice(len(text), 0, 1)
+            c.build_graph_from_text_slices(np.frombuffer(text, np.uint8)[lo:hi], len(text), 21, bcalm)
+            c.dijkstra_candidates(8, 0, 1)
+            rec, meta = c.allgather_candidates()
+            c.greedy_match(rec, meta, 1)
+            c.finish_walks()
+            c.broadcast_walks(0)
+            o = run_oracle(text, 21, mode)
+            T = c.walk_count()
+            assert T == o.num("walks")
+            for fmt, ref in (("gfa", o.text("gfa")), ("fasta", o.text("fasta")), (None, o.text("bitvector"))):
+                for world in (1, 3, 7):
+                    pieces, expect = [], 0
+                    for r in range(world):
+                        w_lo, w_hi = sharding.walk_share(T, r, world)
+                        v, off, tot = (c.dup_bitvector_range_view(w_lo, w_hi) if fmt is None else c.assemble_tigs_range_view(fmt, w_lo, w_hi))
+                        assert off == expect and tot == len(ref), (fmt, world, r)
+                        pieces.append(v.tobytes())
+                        expect += len(pieces[-1])
+                    assert b"".join(pieces) == ref, (fmt, world)
+        c.comm_destroy()
+    finally:
+        c.close()

@@ -46,6 +46,19 @@ def _worker(rank, world, port, text, k, cap, ret):
         got = flat_rec[slot, :c].numpy()
         ok &= np.array_equal(got & 0xFFFFFFFF, nodes[i, :c].astype(np.int64)) and np.array_equal(got >> 32, dists[i, :c].astype(np.int64))
     ok &= sum(sharding.local_count(S, r, world) for r in range(world)) == S
+    # sliced upload (mtg_build_graph_from_text_slices): equal-sized, 16-byte aligned slices, all-gathered back into the file
+    lo, hi = sharding.text_slice(len(text), rank, world)
+    sl = sharding.text_slice(len(text), 0, world)[1]
+    ok &= sl % 16 == 0 and sl * world >= len(text) and hi - lo <= sl
+    part = torch.zeros(sl, dtype=torch.uint8)
+    part[:hi - lo] = torch.frombuffer(bytearray(text[lo:hi]), dtype=torch.uint8)
+    whole = torch.empty(sl * world, dtype=torch.uint8)
+    dist.all_gather_into_tensor(whole, part)
+    ok &= whole[:len(text)].numpy().tobytes() == text
+    # sharded emission: the walk shares partition [0, T)
+    T = o.num("walks")
+    shares = [sharding.walk_share(T, r, world) for r in range(world)]
+    ok &= shares[0][0] == 0 and shares[-1][1] == T and all(shares[r][1] == shares[r + 1][0] for r in range(world - 1))
     t = torch.tensor([1 if ok else 0])
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:
