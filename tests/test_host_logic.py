@@ -159,3 +159,26 @@ def test_cli_flag_surface(mt, tmp_path):
         with pytest.raises(SystemExit) as e:
             cli.main(bad)
         assert e.value.code not in (0, None)
+
+
+def test_rust_shim_declares_exported_symbols():
+    """rust/b200.rs (the binding a maintainer of the Rust host would add) and the built library agree on symbol names."""
+    import ctypes
+    import re
+    from pathlib import Path
+    from matchtigs_b200 import _lib
+    root = Path(__file__).resolve().parent.parent
+    src = (root / "rust" / "b200.rs").read_text()
+    block = src[src.index('extern "C" {'):]
+    block = block[:block.index("\n}\n")]
+    names = re.findall(r"pub fn (mtg_\w+)\(", block)
+    assert len(names) >= 30
+    lib = ctypes.CDLL(str(_lib.SO_PATH))
+    for n in names:
+        assert hasattr(lib, n), f"rust shim declares {n}, the library does not export it"
+    header = (root / "include" / "matchtigs_b200.h").read_text()
+    for n in names:
+        assert re.search(rf"\b{n}\(", header), f"{n} is not declared in include/matchtigs_b200.h"
+    # the #[repr(C)] stats struct has the fields of the C struct, in order
+    fields_rs = re.findall(r"pub (\w+): [uf]\d+,", src[src.index("pub struct mtg_search_stats"):src.index('#[link(name')])
+    assert fields_rs == [n for n, _ in _lib.SearchStats._fields_]
