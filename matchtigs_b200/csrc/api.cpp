@@ -388,8 +388,11 @@ struct MatchtigsData {
     size_t unitig_amount = 0;
     std::vector<u64> a, b;
     std::vector<u8> sa, sb;
-    std::vector<u64> weights;
+    mtg_ctx* ctx = nullptr;  // owns the device graph between matchtigs_build_graph and matchtigs_compute_tigs
     bool built = false;
+    ~MatchtigsData() {
+        if (ctx) mtg_ctx_destroy(ctx);
+    }
 };
 
 static bool g_initialised = false;
@@ -423,8 +426,20 @@ void matchtigs_merge_nodes(MatchtigsData* d, size_t unitig_a, bool strand_a, siz
 void matchtigs_build_graph(MatchtigsData* d, const size_t* unitig_weights) {
     if (!d) clib_panic("matchtigs_build_graph: null handle");
     if (!unitig_weights) clib_panic("matchtigs_build_graph: unitig_weights is null");  // assert! src/clib.rs:188
-    d->weights.assign(unitig_weights, unitig_weights + d->unitig_amount);
-    d->built = true;  // the device graph is built by matchtigs_compute_tigs, which knows k
+    if (d->built) clib_panic("matchtigs_build_graph called twice");
+    // Like the reference this call builds the graph -- union-find numbering, edges, mirror table -- and asserts
+    // verify_node_pairing / verify_edge_mirror_property (src/clib.rs:251-252): inconsistent links abort HERE, not one call
+    // later.  Only what depends on k (weights against k-1, short-edge CSR) waits for matchtigs_compute_tigs.
+    int dev = 0;
+    if (const char* e = getenv("MTG_DEVICE")) dev = atoi(e);
+    if (mtg_ctx_create(&d->ctx, dev) != MTG_OK) clib_panic("no usable CUDA device (there is no CPU fallback)");
+    std::vector<u64> w(unitig_weights, unitig_weights + d->unitig_amount);
+    const int rc = guarded(d->ctx, [&] {
+        build_graph_from_links(d->ctx, d->unitig_amount, w.data(), d->a.size(), d->a.data(), d->sa.data(), d->b.data(), d->sb.data(), 0,
+                               nullptr, nullptr, false);
+    });
+    if (rc != MTG_OK) clib_panic(mtg_last_error(d->ctx));
+    d->built = true;
 }
 
 size_t matchtigs_compute_tigs(MatchtigsData* d, size_t tig_algorithm, size_t threads, size_t k, const char* matching_file_prefix,
@@ -450,25 +465,20 @@ size_t matchtigs_compute_tigs(MatchtigsData* d, size_t tig_algorithm, size_t thr
             clib_panic("tig algorithms 2 (pathtigs), 3 (eulertigs) and 4 (matchtigs) are reference-only; this library serves 1 and 5");
         clib_panic("Unknown tigs algorithm identifier");  // src/clib.rs:390
     }
-    mtg_ctx* ctx = nullptr;
-    int dev = 0;
-    if (const char* e = getenv("MTG_DEVICE")) dev = atoi(e);
-    if (mtg_ctx_create(&ctx, dev) != MTG_OK) clib_panic("no usable CUDA device (there is no CPU fallback)");
+    mtg_ctx* ctx = d->ctx;
     auto check = [&](int rc) {
         if (rc != MTG_OK) {
             fprintf(stderr, "matchtigs (b200): %s\n", mtg_last_error(ctx));
             abort();
         }
     };
-    check(mtg_build_graph_from_links(ctx, U, d->weights.data(), d->a.size(), d->a.data(), d->sa.data(), d->b.data(), d->sb.data(),
-                                     (uint32_t)k, nullptr, nullptr));
+    check(guarded(ctx, [&] { finish_deferred_graph(ctx, (u32)k); }));
     check(mtg_dijkstra_candidates(ctx, 8, 0, 1));
     uint64_t nt = 0, nw = 0, nwe = 0;
     check(mtg_greedy_match(ctx, nullptr, nullptr, 1, &nt));
     check(mtg_finish_walks(ctx, &nw, &nwe));
     check(mtg_walks_export_capi(ctx, tigs_edge_out, tigs_insert_out, tigs_out_limits));
-    mtg_ctx_destroy(ctx);
-    return (size_t)nw;
+    return (size_t)nw;  // `owned` releases the handle and its context
 }
 
 }  // extern "C"

@@ -609,9 +609,11 @@ void build_graph_from_sequences(mtg_ctx* ctx, const char* seq, const u64* offset
     finish_graph(ctx);
 }
 
+// k == 0: only the part that does not depend on k (union-find numbering, edges, mirror table, pairing check -- what
+// matchtigs_build_graph does, src/clib.rs:180-259); finish_deferred_graph(ctx, k) completes the graph once k is known.
 void build_graph_from_links(mtg_ctx* ctx, u64 U, const u64* weights, u64 n_links, const u64* a, const u8* sa, const u64* b,
                             const u8* sb, u32 k, const char* seq, const u64* offsets, bool on_device, u64 total_bases) {
-    MTG_REQUIRE(k >= 2 && k <= 64, MTG_ERR_INVALID, "k must be in [2, 64]");
+    MTG_REQUIRE(k == 0 || (k >= 2 && k <= 64), MTG_ERR_INVALID, "k must be in [2, 64]");
     MTG_REQUIRE(U < (1ull << 30), MTG_ERR_UNSUPPORTED, "more than 2^30 unitigs");
     MTG_REQUIRE(U == 0 || weights, MTG_ERR_INVALID, "null weights");
     MTG_REQUIRE(n_links == 0 || (a && sa && b && sb), MTG_ERR_INVALID, "null links");
@@ -700,6 +702,15 @@ void build_graph_from_links(mtg_ctx* ctx, u64 U, const u64* weights, u64 n_links
     for (DBuf<u64>* x : {&d_w, &d_a, &d_b}) x->release(s);
     for (DBuf<u8>* x : {&d_sa, &d_sb, &rank}) x->release(s);
     for (DBuf<u32>* x : {&cc, &key_a, &key_b, &op_a, &op_b, &parent, &rep, &is_rep, &node_of_rep}) x->release(s);
+    ctx->graph_needs_k = k == 0;
+    if (k) finish_graph(ctx);
+}
+
+void finish_deferred_graph(mtg_ctx* ctx, u32 k) {
+    MTG_REQUIRE(ctx->graph_needs_k, MTG_ERR_INVALID, "no graph is waiting for its k");
+    MTG_REQUIRE(k >= 2 && k <= 64, MTG_ERR_INVALID, "k must be in [2, 64]");
+    ctx->k = k;
+    ctx->graph_needs_k = false;
     finish_graph(ctx);
 }
 

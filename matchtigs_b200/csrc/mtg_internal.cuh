@@ -245,6 +245,7 @@ struct mtg_ctx {
     bool tail_inputs_staged = false;  // host copies of edge_from/edge_to/unitig_w/mirror are in tail_stage[0..3]
     uint64_t target_mult_total = 0;  // sum of the targets' multiplicities = upper bound for the number of matches
     bool have_graph = false, have_seqs = false;
+    bool graph_needs_k = false;  // links graph built without k (matchtigs_build_graph): finish_deferred_graph completes it
     mtg::DBuf<mtg::u64> seq_words;    // 2-bit store: base i at bits [2(i%32), 2(i%32)+1] of word i/32; A0 C1 T2 G3
     mtg::DBuf<mtg::u64> seq_off;      // [U+1] base offsets
     uint64_t total_bases = 0;
@@ -334,6 +335,7 @@ void build_graph_from_sequences(mtg_ctx* ctx, const char* seq, const u64* offset
 void build_graph_from_links(mtg_ctx* ctx, u64 U, const u64* weights, u64 n_links, const u64* a, const u8* sa, const u64* b,
                             const u8* sb, u32 k, const char* seq, const u64* offsets, bool on_device,
                             u64 total_bases = UNKNOWN_TOTAL);
+void finish_deferred_graph(mtg_ctx* ctx, u32 k);
 // device-side FASTA / bcalm2 record parser feeding the two builders (parse.cu)
 void build_graph_from_text(mtg_ctx* ctx, const char* text, u64 len, bool bcalm, u32 k, bool text_on_device);
 

@@ -479,3 +479,4 @@ def test_library_nccl_entry_points_and_sharded_emission(mt):
         c.comm_destroy()
     finally:
         c.close()
+
