@@ -528,10 +528,11 @@ void finish_graph(mtg_ctx* ctx) {
 
 }  // namespace
 
-void build_graph_from_sequences(mtg_ctx* ctx, const char* seq, const u64* offsets, u64 U, u32 k, bool on_device, u64 total_bases) {
+void build_graph_from_sequences(mtg_ctx* ctx, const char* seq, const u64* offsets, u64 U, u32 k, bool on_device, u64 total_bases,
+                                bool prepacked) {
     MTG_REQUIRE(k >= 2 && k <= 64, MTG_ERR_INVALID, "k must be in [2, 64]");
     MTG_REQUIRE(U < (1ull << 30), MTG_ERR_UNSUPPORTED, "more than 2^30 unitigs");
-    MTG_REQUIRE(U == 0 || (seq && offsets), MTG_ERR_INVALID, "null sequence input");
+    MTG_REQUIRE(U == 0 || prepacked || (seq && offsets), MTG_ERR_INVALID, "null sequence input");
     cudaStream_t s = ctx->stream;
     ctx->have_graph = false;
     ctx->build_timed = false;
@@ -546,7 +547,9 @@ void build_graph_from_sequences(mtg_ctx* ctx, const char* seq, const u64* offset
     MTG_CUDA(cudaMallocAsync((void**)&d_err, sizeof(int), s));
     MTG_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), s));
     u64 zero_off = 0;
-    if (U == 0) {
+    if (prepacked) {
+        ctx->have_seqs = true;
+    } else if (U == 0) {
         ctx->seq_off.upload(&zero_off, 1, s);
         ctx->seq_words.resize(2, s);
         ctx->seq_words.zero(s);
@@ -612,14 +615,14 @@ void build_graph_from_sequences(mtg_ctx* ctx, const char* seq, const u64* offset
 // k == 0: only the part that does not depend on k (union-find numbering, edges, mirror table, pairing check -- what
 // matchtigs_build_graph does, src/clib.rs:180-259); finish_deferred_graph(ctx, k) completes the graph once k is known.
 void build_graph_from_links(mtg_ctx* ctx, u64 U, const u64* weights, u64 n_links, const u64* a, const u8* sa, const u64* b,
-                            const u8* sb, u32 k, const char* seq, const u64* offsets, bool on_device, u64 total_bases) {
+                            const u8* sb, u32 k, const char* seq, const u64* offsets, bool on_device, u64 total_bases, bool prepacked) {
     MTG_REQUIRE(k == 0 || (k >= 2 && k <= 64), MTG_ERR_INVALID, "k must be in [2, 64]");
     MTG_REQUIRE(U < (1ull << 30), MTG_ERR_UNSUPPORTED, "more than 2^30 unitigs");
     MTG_REQUIRE(U == 0 || weights, MTG_ERR_INVALID, "null weights");
     MTG_REQUIRE(n_links == 0 || (a && sa && b && sb), MTG_ERR_INVALID, "null links");
     MTG_REQUIRE(2 * n_links < 0xFFFFFFFFull, MTG_ERR_UNSUPPORTED, "too many links");
-    if (ctx->opt.p6_bcalm_kmer_numbering && seq && offsets)  // assumption P6 flipped: the links are ignored, nodes come from the k-mer join
-        return build_graph_from_sequences(ctx, seq, offsets, U, k, on_device, total_bases);
+    if (ctx->opt.p6_bcalm_kmer_numbering && ((seq && offsets) || prepacked))  // assumption P6 flipped: the links are ignored, nodes come from the k-mer join
+        return build_graph_from_sequences(ctx, seq, offsets, U, k, on_device, total_bases, prepacked);
     cudaStream_t s = ctx->stream;
     ctx->have_graph = false;
     ctx->build_timed = false;
@@ -627,14 +630,14 @@ void build_graph_from_links(mtg_ctx* ctx, u64 U, const u64* weights, u64 n_links
         MTG_CUDA(cudaEventRecord(ctx->ev_build[0], s));
         MTG_CUDA(cudaEventRecord(ctx->ev_build[1], s));
     }
-    ctx->have_seqs = false;
+    ctx->have_seqs = prepacked;
     ctx->k = k;
     ctx->U = U;
     ctx->E = 2 * U;
     int* d_err = nullptr;
     MTG_CUDA(cudaMallocAsync((void**)&d_err, sizeof(int), s));
     MTG_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), s));
-    if (seq && offsets && U) upload_and_pack(ctx, seq, offsets, U, on_device, total_bases, d_err);
+    if (!prepacked && seq && offsets && U) upload_and_pack(ctx, seq, offsets, U, on_device, total_bases, d_err);
     DBuf<u64> d_w, d_a, d_b;
     DBuf<u8> d_sa, d_sb, rank;
     DBuf<u32> cc, key_a, key_b, op_a, op_b, parent, rep, is_rep, node_of_rep;

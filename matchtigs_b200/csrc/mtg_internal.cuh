@@ -330,11 +330,12 @@ int radix_sort_pairs_u32(mtg_ctx* ctx, u32* k_a, u32* k_b, u32* v_a, u32* v_b, s
 // ---- graph construction (graph.cu) ----
 // total_bases: offsets[U] if the caller already knows it (saves a round trip when the offsets live on the device)
 constexpr u64 UNKNOWN_TOTAL = ~0ull;
+// prepacked: ctx->seq_words / seq_off / total_bases already hold the sequences (device-side parser); seq and offsets are unused
 void build_graph_from_sequences(mtg_ctx* ctx, const char* seq, const u64* offsets, u64 U, u32 k, bool on_device,
-                                u64 total_bases = UNKNOWN_TOTAL);
+                                u64 total_bases = UNKNOWN_TOTAL, bool prepacked = false);
 void build_graph_from_links(mtg_ctx* ctx, u64 U, const u64* weights, u64 n_links, const u64* a, const u8* sa, const u64* b,
                             const u8* sb, u32 k, const char* seq, const u64* offsets, bool on_device,
-                            u64 total_bases = UNKNOWN_TOTAL);
+                            u64 total_bases = UNKNOWN_TOTAL, bool prepacked = false);
 void finish_deferred_graph(mtg_ctx* ctx, u32 k);
 // device-side FASTA / bcalm2 record parser feeding the two builders (parse.cu)
 void build_graph_from_text(mtg_ctx* ctx, const char* text, u64 len, bool bcalm, u32 k, bool text_on_device);
