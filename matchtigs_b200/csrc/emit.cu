@@ -5,7 +5,8 @@
 //
 // Both are prefix-sum + fill: every walk edge becomes a segment of the output text, an exclusive
 // scan of segment lengths gives its byte offset, and each thread then produces 16 consecutive
-// output bytes (one 128-bit store) after locating its first segment by binary search.
+// output bytes (one 128-bit store): the segments of a CTA's 4 KiB of output are looked up once and staged in
+// shared memory, bases are decoded from 64-bit reads of the 2-bit store.
 #include <algorithm>
 #include <memory>
 
@@ -87,19 +88,57 @@ __device__ __forceinline__ u64 segment_of(const u64* __restrict__ seg_off, u64 W
     return lo - 1;
 }
 
-__device__ __forceinline__ char decode_base(const u64* __restrict__ words, u64 pos, bool complement) {
-    u32 c = (u32)(words[pos >> 5] >> ((pos & 31) * 2)) & 3u;
-    if (complement) c ^= 2u;
-    return (char)((0x47544341u >> (8 * c)) & 0xFFu);  // "ACTG"
+// up to 32 consecutive bases starting at `pos`, base i at bits [2i, 2i+2)
+__device__ __forceinline__ u64 read_bases64(const u64* __restrict__ words, u64 pos) {
+    const u64 w = pos >> 5;
+    const u32 s = (u32)(pos & 31) * 2;
+    u64 x = words[w] >> s;
+    if (s) x |= words[w + 1] << (64 - s);
+    return x;
 }
+__device__ __forceinline__ char base_char(u32 c) { return (char)((0x47544341u >> (8 * (c & 3u))) & 0xFFu); }  // "ACTG"
 
+constexpr int SEG_CACHE = 1024;  // segment offsets of one CTA's output range kept in shared memory
+
+// Every CTA produces TB * CHUNK consecutive output bytes.  The segments that intersect that range are found once per CTA
+// (two binary searches) and their offsets staged in shared memory; a thread then locates its first segment there and decodes
+// its 16 bytes from 64-bit reads of the 2-bit store (up to 32 bases per read) instead of one global load per base.
 __global__ void __launch_bounds__(TB)
     fill_text(WalkView w, int mode, const u64* __restrict__ seg_off, const u32* __restrict__ seg_len, const u32* __restrict__ seg_tig,
               const u64* __restrict__ words, u64 q_base, u64 total, char* __restrict__ out) {
     // produces bytes [q_base, total) of the text into out[0 ..): a rank's share of the output, or all of it
-    const u64 q0 = q_base + ((u64)blockIdx.x * TB + threadIdx.x) * CHUNK;
+    __shared__ u64 s_off[SEG_CACHE];
+    __shared__ u64 s_j0;
+    __shared__ u32 s_n;
+    const u64 cta_q0 = q_base + (u64)blockIdx.x * TB * CHUNK;
+    const u64 cta_q1 = min(cta_q0 + (u64)TB * CHUNK, total);
+    if (threadIdx.x == 0) {
+        const u64 j0 = segment_of(seg_off, w.W, cta_q0);
+        const u64 j1 = segment_of(seg_off, w.W, cta_q1 - 1);
+        s_j0 = j0;
+        s_n = (u32)min((u64)SEG_CACHE + 1, j1 - j0 + 1);
+    }
+    __syncthreads();
+    const u64 j0 = s_j0;
+    const u32 n_seg = s_n;
+    const bool cached = n_seg <= SEG_CACHE;
+    if (cached)
+        for (u32 i = threadIdx.x; i < n_seg; i += TB) s_off[i] = seg_off[j0 + i];
+    __syncthreads();
+    const u64 q0 = cta_q0 + (u64)threadIdx.x * CHUNK;
     if (q0 >= total) return;
-    u64 j = segment_of(seg_off, w.W, q0);
+    u64 j;
+    if (cached) {  // last cached segment with offset <= q0
+        u32 lo = 0, hi = n_seg;
+        while (lo < hi) {
+            const u32 mid = (lo + hi) >> 1;
+            if (s_off[mid] <= q0) lo = mid + 1;
+            else hi = mid;
+        }
+        j = j0 + lo - 1;
+    } else {
+        j = segment_of(seg_off, w.W, q0);
+    }
     alignas(16) char buf[CHUNK];
     u64 q = q0;
     const u64 qend = min(q0 + (u64)CHUNK, total);
@@ -120,40 +159,48 @@ __global__ void __launch_bounds__(TB)
                 skip = pe >= w.E ? w.k - 1 - w.dummy_w[pe - w.E] : w.k - 1;
             }
         }
-        const u64 u = e >> 1;
-        const u64 sbeg = dummy ? 0 : w.seq_off[u], send = dummy ? 0 : w.seq_off[u + 1];
-        const bool fwd = !(e & 1);
         const u64 seg_end = s0 + len;
-        for (; q < qend && q < seg_end; q++) {
+        const u64 stop = min(qend, seg_end);  // this thread's bytes of the segment: [q, stop)
+        const u32 body_end = len - (last ? 1u : 0u);  // segment-relative index of the trailing '\n', if any
+        // header characters
+        for (; q < stop && (u32)(q - s0) < hdr; q++) {
             const u32 c = (u32)(q - s0);
             char ch;
-            if (last && c == len - 1) {
-                ch = '\n';
-            } else if (mode == 0) {
-                ch = dummy ? '0' : '1';
-            } else if (c < hdr) {
-                if (mode == 1) {
-                    if (c == 0) ch = 'S';
-                    else if (c == 1 || c == hdr - 1) ch = '\t';
-                    else {
-                        u64 v = t + 1;
-                        for (u32 r = hdr - 2 - c; r > 0; r--) v /= 10;
-                        ch = (char)('0' + v % 10);
-                    }
-                } else {
-                    if (c == 0) ch = '>';
-                    else if (c == hdr - 1) ch = '\n';
-                    else {
-                        u64 v = t + 1;
-                        for (u32 r = hdr - 2 - c; r > 0; r--) v /= 10;
-                        ch = (char)('0' + v % 10);
-                    }
-                }
-            } else {
-                const u64 b = (u64)(c - hdr) + skip;  // index into the oriented unitig string
-                ch = fwd ? decode_base(words, sbeg + b, false) : decode_base(words, send - 1 - b, true);
+            if (c == 0) ch = mode == 1 ? 'S' : '>';
+            else if (c == hdr - 1) ch = mode == 1 ? '\t' : '\n';
+            else if (mode == 1 && c == 1) ch = '\t';
+            else {
+                u64 v = t + 1;
+                for (u32 r = hdr - 2 - c; r > 0; r--) v /= 10;
+                ch = (char)('0' + v % 10);
             }
             buf[q - q0] = ch;
+        }
+        // body: '1' / '0' of the bitvector, or bases of the oriented unitig
+        if (q < stop && (u32)(q - s0) < body_end) {
+            const u32 c0 = (u32)(q - s0);
+            const u32 nb = (u32)(min(stop, s0 + body_end) - q);  // 1..16 body characters
+            if (mode == 0) {
+                const char ch = dummy ? '0' : '1';
+                for (u32 i = 0; i < nb; i++) buf[q - q0 + i] = ch;
+            } else {
+                const u64 u = e >> 1;
+                const u64 b0 = (u64)(c0 - hdr) + skip;  // index of the first character inside the oriented unitig string
+                if (!(e & 1)) {
+                    u64 bits = read_bases64(words, w.seq_off[u] + b0);
+                    for (u32 i = 0; i < nb; i++, bits >>= 2) buf[q - q0 + i] = base_char((u32)bits);
+                } else {
+                    // reverse complement: oriented index b <-> stored position send - 1 - b, complement = code ^ 2
+                    const u64 lo = w.seq_off[u + 1] - b0 - nb;  // stored position of the LAST character of this run
+                    u64 bits = read_bases64(words, lo);
+                    for (u32 i = 0; i < nb; i++, bits >>= 2) buf[q - q0 + (nb - 1 - i)] = base_char((u32)bits ^ 2u);
+                }
+            }
+            q += nb;
+        }
+        if (q < stop) {  // only the newline is left
+            buf[q - q0] = '\n';
+            q++;
         }
     }
     if (qend - q0 == CHUNK) {
