@@ -420,7 +420,8 @@ def run_ours(args):
             "dijkstra": {"ms_per_step": dj_ms, "settled_nodes": settled, "relaxed_edges": relaxed, "candidates": cands,
                          "sources_searched": searched, "kernel_ms_per_step": djk_ms, "match_ms_per_step": match_ms,
                          "match_kernel_ms_per_step": stats["match_kernel_ms"], "match_blocked_retries": stats["match_rounds"],
-                         "requery_phases": stats["requery_phases"], "overflow_sources": stats["overflow_sources"]},
+                         "requery_phases": stats["requery_phases"], "overflow_sources": stats["overflow_sources"],
+                         "truncated_sources": stats["truncated_sources"], "preextended_sources": stats["preextended_sources"]},
             "roofline": {"kernel": SEARCH_KERNEL, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes / world,

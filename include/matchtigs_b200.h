@@ -75,6 +75,7 @@ typedef struct mtg_search_stats {
     uint64_t labelled_nodes;      /* labelled nodes summed over the searches */
     uint64_t max_labelled_nodes;  /* most labelled nodes in one search ("maximum maximum distance array size") */
     uint64_t max_open_nodes;      /* most open labels at once in one thread-tier search ("maximum maximum heap size") */
+    uint64_t preextended_sources; /* truncated lists that mtg_greedy_match searched again with 8x cap before matching */
 } mtg_search_stats;
 
 /* ---- lifecycle ---- */

@@ -49,7 +49,7 @@ class SearchStats(C.Structure):
                 ("match_rounds", C.c_uint64), ("requery_phases", C.c_uint64), ("matched", C.c_uint64),
                 ("dijkstra_ms", C.c_float), ("match_ms", C.c_float), ("dijkstra_kernel_ms", C.c_float),
                 ("match_kernel_ms", C.c_float), ("labelled_nodes", C.c_uint64), ("max_labelled_nodes", C.c_uint64),
-                ("max_open_nodes", C.c_uint64)]
+                ("max_open_nodes", C.c_uint64), ("preextended_sources", C.c_uint64)]
 
     def as_dict(self) -> dict:
         return {n: (float(getattr(self, n)) if t is C.c_float else int(getattr(self, n))) for n, t in self._fields_}

@@ -339,6 +339,7 @@ void greedy_match(mtg_ctx* ctx, const u64* d_records_all, const u32* d_meta_all,
     ctx->h_triples.clear();
     ctx->stats.match_rounds = 0;
     ctx->stats.requery_phases = 0;
+    ctx->stats.preextended_sources = 0;
     ctx->final_mult.resize(N, s);
     if (N) MTG_CUDA(cudaMemcpyAsync(ctx->final_mult.p, ctx->imbalance.p, N * sizeof(i32), cudaMemcpyDeviceToDevice, s));
     if (S == 0) {
@@ -383,6 +384,31 @@ void greedy_match(mtg_ctx* ctx, const u64* d_records_all, const u32* d_meta_all,
     int occ = 0;
     MTG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, match_dataflow_kernel, TB, 0));
     if (occ < 1) occ = 1;
+
+    // Truncated lists get a deeper second search up front (8x cap, against the initial target map, so the result is a
+    // longer prefix of the same list).  They are a few percent of the sources, so this costs a fraction of the main
+    // search -- and it makes "a truncated list ran dry", which throws away everything from that source on and costs a
+    // whole extra search + matching phase, a rare event instead of the rule on repeat-rich graphs.
+    if (cap < 4096 && !getenv("MTG_NO_PREEXTEND")) {
+        MTG_LAUNCH(ctx, flag_requery, grid_for(S, TB), TB, 0, list_meta.p, S, (u64)0, flag.p);
+        exclusive_sum_u32(ctx, flag.p, pos.p, S, small.p + 7);
+        work_list.resize(S, s);
+        MTG_LAUNCH(ctx, compact_indices, grid_for(S, TB), TB, 0, flag.p, pos.p, S, work_list.p);
+        u32 n_trunc = 0;
+        MTG_CUDA(cudaMemcpyAsync(&n_trunc, small.p + 7, sizeof(u32), cudaMemcpyDeviceToHost, s));
+        MTG_CUDA(cudaStreamSynchronize(s));
+        if (n_trunc && (u64)n_trunc * 4 <= S) {
+            const u32 cap2 = std::min<u32>(cap * 8, 4096);
+            pools.emplace_back();
+            pools.back().resize((u64)n_trunc * cap2, s);
+            pool_meta.resize(n_trunc, s);
+            run_searches(ctx, ctx->target_bits.p, work_list.p, n_trunc, 0, 1, cap2, pools.back().p, pool_meta.p);
+            MTG_LAUNCH(ctx, adopt_requery, grid_for(n_trunc, TB), TB, 0, work_list.p, (u64)n_trunc, pools.back().p, pool_meta.p, cap2, list_addr.p,
+                       list_meta.p);
+            cap = cap2;
+            ctx->stats.preextended_sources = n_trunc;
+        }
+    }
 
     u64 lo = 0, n_final = 0, retries_total = 0;
     bool copied_out = false;  // triples + counters already fetched with the last phase's round trip
@@ -509,6 +535,9 @@ void greedy_match(mtg_ctx* ctx, const u64* d_records_all, const u32* d_meta_all,
     ctx->stats.settled_nodes = h.settled;
     ctx->stats.relaxed_edges = h.relaxed;
     ctx->stats.overflow_sources = h.overflow;
+    ctx->stats.labelled_nodes = h.labels;
+    ctx->stats.max_labelled_nodes = h.max_labels;
+    ctx->stats.max_open_nodes = h.max_open;
     for (auto& p : pools) p.release(s);
     list_addr.release(s);
     big.release(s);

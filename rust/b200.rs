@@ -67,6 +67,7 @@ pub struct mtg_search_stats {
     pub labelled_nodes: u64,
     pub max_labelled_nodes: u64,
     pub max_open_nodes: u64,
+    pub preextended_sources: u64,
 }
 
 #[link(name = "matchtigs_b200")]

@@ -351,7 +351,9 @@ def test_reference_c_api(mt):
 def test_other_configs_scaled(mt, ctx, name, scale):
     """BASELINE configs 3-5 at a scale the oracle finishes in seconds (repeat-rich, high-branching, k=51)."""
     text, k, info = tools.config_unitigs(name, scale)
-    compare_all(mt, ctx, text, k, "fasta", cap=16)
+    _, st = compare_all(mt, ctx, text, k, "fasta", cap=16)
+    if name == "chr1":  # a few percent of its lists are longer than 16: searched again with 8x cap before the matching
+        assert 0 < st["preextended_sources"] < info["unitigs"]
     compare_all(mt, ctx, text, k, "bcalm", cap=4)
 
 
