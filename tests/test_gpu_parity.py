@@ -482,3 +482,20 @@ def test_library_nccl_entry_points_and_sharded_emission(mt):
     finally:
         c.close()
 
+
+
+@pytest.mark.parametrize("force_host", ["0", "1"])
+def test_both_tail_preparations_on_the_same_inputs(mt, ctx, force_host, monkeypatch):
+    """The walk records are built on the device for big graphs and on the host for small ones (< 2^17 nodes); MTG_TAIL_HOST
+    forces either, so both builders see the inputs that stress them: nodes with more than four out-edges (header
+    records), odd degrees (padding slots), self-mirrors, parallel edges, many components."""
+    monkeypatch.setenv("MTG_TAIL_HOST", force_host)
+    for seed in range(10):
+        rng = random.Random(61_000 + seed)
+        k = rng.randint(3, 11)
+        text = random_fasta(rng, rng.randint(1, 700), k, max_extra=rng.choice([0, 2, 8]), pool=rng.choice([2, 3, 5, 9, 40, None]))
+        compare_all(mt, ctx, text, k, "fasta", cap=rng.choice([2, 8, 16]))
+    g = tools.genome(120_000, 77, families=10, copies=8, min_len=40, max_len=600, divergence=0.05, tandem_arrays=10)
+    text, _, _ = tools.unitigs(g, 21)
+    for mode in ("fasta", "bcalm"):
+        compare_all(mt, ctx, text, 21, mode, cap=16, dbg_valid=True, check_props=True)
