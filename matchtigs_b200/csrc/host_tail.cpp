@@ -774,7 +774,8 @@ void finish_walks(mtg_ctx* ctx) {
     }
     const size_t used_bytes = (tr.n_slots / 64 + 2) * sizeof(u64);
     u64* used = static_cast<u64*>(scratch.used.ensure(used_bytes));
-    memcpy(used, tr.used0, used_bytes);
+    if (tr.used0) memcpy(used, tr.used0, used_bytes);
+    else memset(used, 0, used_bytes);  // empty graph
     // dummy weights: matching dummies carry their distance, breaking dummies weigh k
     TailOutput out;
     out.dummy_w.resize(2 * P);
