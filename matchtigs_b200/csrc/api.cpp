@@ -85,6 +85,7 @@ int mtg_ctx_create(mtg_ctx** out, int device) {
         MTG_CUDA(cudaEventCreate(&ctx->ev2));
         MTG_CUDA(cudaEventCreate(&ctx->ev3));
         for (auto& e : ctx->ev_build) MTG_CUDA(cudaEventCreate(&e));
+        for (auto& e : ctx->tail_events) MTG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         cudaDeviceProp prop{};
         MTG_CUDA(cudaGetDeviceProperties(&prop, device));
         ctx->num_sms = prop.multiProcessorCount;
@@ -146,6 +147,8 @@ void mtg_ctx_destroy(mtg_ctx* ctx) {
     if (ctx->ev2) cudaEventDestroy(ctx->ev2);
     if (ctx->ev3) cudaEventDestroy(ctx->ev3);
     for (auto& e : ctx->ev_build)
+        if (e) cudaEventDestroy(e);
+    for (auto& e : ctx->tail_events)
         if (e) cudaEventDestroy(e);
     delete ctx;
 }

@@ -760,23 +760,13 @@ void finish_walks(mtg_ctx* ctx) {
     auto warm_copy = [](void* dst, const void* src, size_t bytes) {
         const size_t chunk = 256 << 10;
         const i64 n_chunks = (i64)((bytes + chunk - 1) / chunk);
-#pragma omp parallel for schedule(static) num_threads(4) if (bytes > (96u << 20))
+#pragma omp parallel for schedule(static) num_threads(4) if (bytes > (8u << 20))
         for (i64 c = 0; c < n_chunks; c++) {
             const size_t o = (size_t)c * chunk;
             memcpy((char*)dst + o, (const char*)src + o, std::min(chunk, bytes - o));
         }
     };
-    const WalkRec* recs = tr.recs;
-    if (!getenv("MTG_TAIL_NOCOPY")) {
-        WalkRec* arena = static_cast<WalkRec*>(scratch.recs.ensure(std::max<u64>(tr.n_slots, 1) * sizeof(WalkRec)));
-        warm_copy(arena, tr.recs, tr.n_slots * sizeof(WalkRec));
-        recs = arena;
-    }
-    const size_t used_bytes = (tr.n_slots / 64 + 2) * sizeof(u64);
-    u64* used = static_cast<u64*>(scratch.used.ensure(used_bytes));
-    if (tr.used0) memcpy(used, tr.used0, used_bytes);
-    else memset(used, 0, used_bytes);  // empty graph
-    // dummy weights: matching dummies carry their distance, breaking dummies weigh k
+    // while the records are in flight: dummy weights (matching dummies carry their distance, breaking dummies weigh k)
     TailOutput out;
     out.dummy_w.resize(2 * P);
     const u32* trp = ctx->h_triples.data();
@@ -786,6 +776,21 @@ void finish_walks(mtg_ctx* ctx) {
         max_matching_w = std::max(max_matching_w, trp[3 * j + 2]);
     }
     for (u64 j = ctx->n_triples; j < P; j++) out.dummy_w[2 * j] = out.dummy_w[2 * j + 1] = ctx->k;
+    const WalkRec* recs = tr.recs;
+    if (!getenv("MTG_TAIL_NOCOPY")) {
+        WalkRec* arena = static_cast<WalkRec*>(scratch.recs.ensure(std::max<u64>(tr.n_slots, 1) * sizeof(WalkRec)));
+        for (int c = 0; c < TAIL_DMA_CHUNKS && tr.n_slots; c++) {  // piece c is copied while piece c+1 is still on the link
+            const u64 lo = std::min<u64>((u64)c * tr.chunk_slots, tr.n_slots), hi = std::min<u64>(lo + tr.chunk_slots, tr.n_slots);
+            MTG_CUDA(cudaEventSynchronize(ctx->tail_events[c]));
+            if (hi > lo) warm_copy(arena + lo, tr.recs + lo, (hi - lo) * sizeof(WalkRec));
+        }
+        recs = arena;
+    }
+    MTG_CUDA(cudaStreamSynchronize(s));  // the small tables
+    const size_t used_bytes = (tr.n_slots / 64 + 2) * sizeof(u64);
+    u64* used = static_cast<u64*>(scratch.used.ensure(used_bytes));
+    if (tr.used0) memcpy(used, tr.used0, used_bytes);
+    else memset(used, 0, used_bytes);  // empty graph
     double t2 = now_ms();
     WalkInput w{ctx->k, N, E0, E0 + 2 * P, tr.n_slots, recs, used, nullptr, tr.slot_edge, tr.slot_of_edge, nullptr, tr.handle,
                 out.dummy_w.data(), max_matching_w < ctx->k};

@@ -20,6 +20,7 @@ using i32 = int32_t;
 using i64 = int64_t;
 
 constexpr u32 NONE32 = 0xFFFFFFFFu;
+constexpr int TAIL_DMA_CHUNKS = 8;  // pieces in which the walk records travel to the host
 constexpr int NUM_SMS_B200 = 148;
 
 struct Error {
@@ -224,6 +225,7 @@ struct mtg_ctx {
     mtg_options opt;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    cudaEvent_t tail_events[mtg::TAIL_DMA_CHUNKS] = {};  // DMA progress of the walk records
     cudaEvent_t ev_build[3] = {nullptr, nullptr, nullptr};  // start of the last graph build, end of its parsing, end of the build
     bool build_timed = false, in_text_build = false;
     float last_kernel_ms = 0;  // tier-0 search kernel of the last run_searches call
@@ -362,6 +364,8 @@ void tail_leftover(mtg_ctx* ctx, TailLeftover& lo);
 // initial used-slot bitset) into the page-locked staging buffers of the context.
 struct TailRecords {
     u64 n_slots = 0, n_pairs = 0;
+    u64 chunk_slots = 0;  // the records arrive in TAIL_DMA_CHUNKS pieces of this many slots; piece c is complete once
+                          // ctx->tail_events[c] has fired (the other arrays: once the stream is idle)
     WalkRec* recs = nullptr;
     u32 *slot_edge = nullptr, *slot_of_edge = nullptr, *handle = nullptr;
     u64* used0 = nullptr;

@@ -304,14 +304,21 @@ void tail_build_records(mtg_ctx* ctx, const u32* breaking_pairs, u64 n_break, Ta
     out->slot_of_edge = ctx->tail_stage[2].as<u32>(E0 + 1);
     out->handle = ctx->tail_stage[3].as<u32>(E0 + 1);  // handle of the from-node of every original edge
     out->slot_edge = ctx->tail_stage[4].as<u32>(n_slots + 1);
-    MTG_CUDA(cudaMemcpyAsync(out->recs, recs.p, n_slots * sizeof(WalkRec), cudaMemcpyDeviceToHost, s));
+    // in pieces, each followed by an event: the host copies piece c into the walk's arena while piece c+1 is in flight
+    out->chunk_slots = (n_slots + TAIL_DMA_CHUNKS - 1) / TAIL_DMA_CHUNKS;
+    for (int c = 0; c < TAIL_DMA_CHUNKS; c++) {
+        const u64 lo = std::min<u64>((u64)c * out->chunk_slots, n_slots), hi = std::min<u64>(lo + out->chunk_slots, n_slots);
+        if (hi > lo) MTG_CUDA(cudaMemcpyAsync(out->recs + lo, recs.p + lo, (hi - lo) * sizeof(WalkRec), cudaMemcpyDeviceToHost, s));
+        MTG_CUDA(cudaEventRecord(ctx->tail_events[c], s));
+    }
     MTG_CUDA(cudaMemcpyAsync(out->used0, used0.p, used_words32 * sizeof(u32), cudaMemcpyDeviceToHost, s));
     if (E0) {
         MTG_CUDA(cudaMemcpyAsync(out->slot_of_edge, slot_of_edge.p, E0 * sizeof(u32), cudaMemcpyDeviceToHost, s));
         MTG_CUDA(cudaMemcpyAsync(out->handle, from_handle.p, E0 * sizeof(u32), cudaMemcpyDeviceToHost, s));
     }
     MTG_CUDA(cudaMemcpyAsync(out->slot_edge, slot_edge.p, n_slots * sizeof(u32), cudaMemcpyDeviceToHost, s));
-    MTG_CUDA(cudaStreamSynchronize(s));
+    // no synchronisation here: the caller overlaps its own work with the copies.  The device buffers are released in
+    // stream order behind them.
 }
 
 }  // namespace mtg
