@@ -529,14 +529,16 @@ void run_searches(mtg_ctx* ctx, const u32* bitmap, const u32* work_list, u64 n_w
     if (n_work == 0) return;
     cudaStream_t s = ctx->stream;
     MTG_REQUIRE(n_work < 0xFFFFFFFFull, MTG_ERR_UNSUPPORTED, "too many sources");
-    u32 *list0 = nullptr, *list1 = nullptr;  // work items leaving tier 0 / tier 1
-    u32* counts = nullptr;                   // [0] |list0|, [1] |list1|
-    unsigned long long* work_counter = nullptr;
-    MTG_CUDA(cudaMallocAsync((void**)&list0, n_work * sizeof(u32), s));
-    MTG_CUDA(cudaMallocAsync((void**)&counts, 2 * sizeof(u32), s));
-    MTG_CUDA(cudaMallocAsync((void**)&work_counter, sizeof(unsigned long long), s));
-    MTG_CUDA(cudaMemsetAsync(counts, 0, 2 * sizeof(u32), s));
-    MTG_CUDA(cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), s));
+    // owning buffers: released on every exit path, including the throwing ones
+    DBuf<u32> list0_buf, list1_buf, counts_buf;  // work items leaving tier 0 / tier 1; [0] |list0|, [1] |list1|
+    DBuf<unsigned long long> work_counter_buf;
+    list0_buf.resize(n_work, s);
+    counts_buf.resize(2, s);
+    counts_buf.zero(s);
+    work_counter_buf.resize(1, s);
+    work_counter_buf.zero(s);
+    u32 *list0 = list0_buf.p, *list1 = nullptr, *counts = counts_buf.p;
+    unsigned long long* work_counter = work_counter_buf.p;
     SearchArgs a{};
     a.row_s = ctx->row_s.p;
     a.col_s = ctx->col_s.p;
@@ -576,7 +578,8 @@ void run_searches(mtg_ctx* ctx, const u32* bitmap, const u32* work_list, u64 n_w
     // ---- tier 1: warp per source, for searches with more than T0_ENTRIES labelled nodes ----
     if (h_counts[0]) {
         const u64 n1 = h_counts[0];
-        MTG_CUDA(cudaMallocAsync((void**)&list1, n1 * sizeof(u32), s));
+        list1_buf.resize(n1, s);
+        list1 = list1_buf.p;
         MTG_CUDA(cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), s));
         a.todo = list0;
         a.n_items = n1;
@@ -597,14 +600,16 @@ void run_searches(mtg_ctx* ctx, const u32* bitmap, const u32* work_list, u64 n_w
         MTG_CUDA(cudaMemGetInfo(&free_b, &total_b));
         u64 per_slot = N * 12;  // labels + visited + level targets
         u64 slots = std::min<u64>(std::min<u64>((u64)n_ovf, (u64)ctx->num_sms * 2), std::max<u64>(1, (free_b / 2) / std::max<u64>(per_slot, 1)));
-        u32 *labels = nullptr, *visited = nullptr, *lvl = nullptr;
-        int* d_err = nullptr;
-        MTG_CUDA(cudaMallocAsync((void**)&labels, slots * N * sizeof(u32), s));
-        MTG_CUDA(cudaMallocAsync((void**)&visited, slots * N * sizeof(u32), s));
-        MTG_CUDA(cudaMallocAsync((void**)&lvl, slots * N * sizeof(u32), s));
-        MTG_CUDA(cudaMallocAsync((void**)&d_err, sizeof(int), s));
-        MTG_CUDA(cudaMemsetAsync(labels, 0xFF, slots * N * sizeof(u32), s));
-        MTG_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), s));
+        DBuf<u32> labels_buf, visited_buf, lvl_buf;
+        DBuf<int> err_buf;
+        labels_buf.resize(slots * N, s);
+        visited_buf.resize(slots * N, s);
+        lvl_buf.resize(slots * N, s);
+        err_buf.resize(1, s);
+        labels_buf.fill_ff(s);
+        err_buf.zero(s);
+        u32 *labels = labels_buf.p, *visited = visited_buf.p, *lvl = lvl_buf.p;
+        int* d_err = err_buf.p;
         BigArgs b{};
         b.s = a;
         b.todo = list1;
@@ -619,16 +624,8 @@ void run_searches(mtg_ctx* ctx, const u32* bitmap, const u32* work_list, u64 n_w
         int h_err = 0;
         MTG_CUDA(cudaMemcpyAsync(&h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, s));
         MTG_CUDA(cudaStreamSynchronize(s));
-        MTG_CUDA(cudaFreeAsync(labels, s));
-        MTG_CUDA(cudaFreeAsync(visited, s));
-        MTG_CUDA(cudaFreeAsync(lvl, s));
-        MTG_CUDA(cudaFreeAsync(d_err, s));
         MTG_REQUIRE(h_err == 0, MTG_ERR_INTERNAL, "tier-2 search exceeded its visited list");
     }
-    MTG_CUDA(cudaFreeAsync(list0, s));
-    if (list1) MTG_CUDA(cudaFreeAsync(list1, s));
-    MTG_CUDA(cudaFreeAsync(counts, s));
-    MTG_CUDA(cudaFreeAsync(work_counter, s));
 }
 
 void dijkstra_candidates(mtg_ctx* ctx, u32 cap, u32 shard_rank, u32 shard_count) {

@@ -264,13 +264,13 @@ u64 emit(mtg_ctx* ctx, int mode, const char* prefix, size_t prefix_len, char* ou
         stage.ensure(part + prefix_len + 1);
         if (prefix_len) memcpy(stage.p, prefix, prefix_len);
         if (part) {
-            char* d_out = nullptr;
-            MTG_CUDA(cudaMallocAsync((void**)&d_out, part + CHUNK, s));
+            DBuf<char> out_buf;
+            out_buf.resize(part + CHUNK, s);
+            char* d_out = out_buf.p;
             u64 chunks = (part + CHUNK - 1) / CHUNK;
             MTG_LAUNCH(ctx, fill_text, grid_for(chunks, TB), TB, 0, w, mode, seg_off.p, seg_len.p, seg_tig.p, ctx->seq_words.p, b0, b1, d_out);
             MTG_CUDA(cudaMemcpyAsync(stage.p + prefix_len, d_out, part, cudaMemcpyDeviceToHost, s));
             MTG_CUDA(cudaStreamSynchronize(s));
-            MTG_CUDA(cudaFreeAsync(d_out, s));
         }
         if (out && part + prefix_len) memcpy(out, stage.p, part + prefix_len);
         if (view) *view = stage.p;

@@ -442,14 +442,13 @@ void upload_and_pack(mtg_ctx* ctx, const char* seq, const u64* offsets, u64 U, b
     ctx->seq_words.resize(nwords + 2, s);
     MTG_CUDA(cudaMemsetAsync(ctx->seq_words.p + nwords, 0, 2 * sizeof(u64), s));
     const char* d_seq = seq;
-    char* staged = nullptr;
+    DBuf<char> staged;
     if (!on_device && total) {
-        MTG_CUDA(cudaMallocAsync((void**)&staged, total + 32, s));
-        MTG_CUDA(cudaMemcpyAsync(staged, seq, total, cudaMemcpyHostToDevice, s));
-        d_seq = staged;
+        staged.resize(total + 32, s);
+        MTG_CUDA(cudaMemcpyAsync(staged.p, seq, total, cudaMemcpyHostToDevice, s));
+        d_seq = staged.p;
     }
     if (nwords) MTG_LAUNCH(ctx, pack_sequences, grid_for(nwords, TB), TB, 0, d_seq, ctx->seq_words.p, total, nwords, d_err);
-    if (staged) MTG_CUDA(cudaFreeAsync(staged, s));
     ctx->have_seqs = true;
 }
 
@@ -470,9 +469,10 @@ void finish_graph(mtg_ctx* ctx) {
     ctx->target_bits.resize((N + 31) / 32 + 1, s);
     ctx->target_bits.zero(s);
     src_flag.resize(N, s);
-    unsigned long long* d_counters = nullptr;
-    MTG_CUDA(cudaMallocAsync((void**)&d_counters, 4 * sizeof(unsigned long long), s));
-    MTG_CUDA(cudaMemsetAsync(d_counters, 0, 4 * sizeof(unsigned long long), s));
+    DBuf<unsigned long long> counters_buf;  // owning buffers: released on every exit path, including the throwing ones
+    counters_buf.resize(4, s);
+    counters_buf.zero(s);
+    unsigned long long* d_counters = counters_buf.p;
     if (N) {
         u64 padded = (N + 31) / 32 * 32;
         MTG_LAUNCH(ctx, classify_nodes, grid_for(padded, TB), TB, 0, ctx->out_deg.p, ctx->mirror.p, N, ctx->opt.p2_self_mirror_zero != 0, ctx->imbalance.p, src_flag.p,
@@ -481,9 +481,10 @@ void finish_graph(mtg_ctx* ctx) {
     // source positions, short-edge rows and short-edge positions: three scans, then ONE round trip for all totals
     pos.resize(N + 1, s);
     pos_e.resize(E + 1, s);
-    u32* d_tot = nullptr;
-    MTG_CUDA(cudaMallocAsync((void**)&d_tot, 2 * sizeof(u32), s));
-    MTG_CUDA(cudaMemsetAsync(d_tot, 0, 2 * sizeof(u32), s));
+    DBuf<u32> tot_buf;
+    tot_buf.resize(2, s);
+    tot_buf.zero(s);
+    u32* d_tot = tot_buf.p;
     exclusive_sum_u32(ctx, src_flag.p, pos.p, N, d_tot);
     ctx->row_s.resize(N + 1, s);
     exclusive_sum_u32(ctx, deg_s.p, ctx->row_s.p, N, ctx->row_s.p + N);
@@ -514,8 +515,6 @@ void finish_graph(mtg_ctx* ctx) {
         MTG_LAUNCH(ctx, fill_short_csr, grid_for(Es, TB), TB, 0, which ? eid_b.p : eid_a.p, ctx->edge_to.p, ctx->unitig_w.p, Es,
                    ctx->col_s.p, ctx->w_s.p);
     }
-    MTG_CUDA(cudaFreeAsync(d_counters, s));
-    MTG_CUDA(cudaFreeAsync(d_tot, s));
     for (DBuf<u32>* b : {&deg_s, &short_flag, &pos, &pos_e, &from_a, &from_b, &eid_a, &eid_b, &src_flag}) b->release(s);
     MTG_CUDA(cudaEventRecord(ctx->ev_build[2], s));
     ctx->build_timed = true;
@@ -543,9 +542,10 @@ void build_graph_from_sequences(mtg_ctx* ctx, const char* seq, const u64* offset
     ctx->k = k;
     ctx->U = U;
     ctx->E = 2 * U;
-    int* d_err = nullptr;
-    MTG_CUDA(cudaMallocAsync((void**)&d_err, sizeof(int), s));
-    MTG_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), s));
+    DBuf<int> err_buf;
+    err_buf.resize(1, s);
+    err_buf.zero(s);
+    int* d_err = err_buf.p;
     u64 zero_off = 0;
     if (prepacked) {
         ctx->have_seqs = true;
@@ -585,9 +585,10 @@ void build_graph_from_sequences(mtg_ctx* ctx, const char* seq, const u64* offset
     base.resize(n, s);
     node_ep.resize(n, s);
     mirror_ep.resize(n, s);
-    u32* d_tot = nullptr;
-    MTG_CUDA(cudaMallocAsync((void**)&d_tot, sizeof(u32), s));
-    MTG_CUDA(cudaMemsetAsync(d_tot, 0, sizeof(u32), s));
+    DBuf<u32> tot_buf;
+    tot_buf.resize(1, s);
+    tot_buf.zero(s);
+    u32* d_tot = tot_buf.p;
     if (n) {
         MTG_LAUNCH(ctx, mark_groups, grid_for(n, TB), TB, 0, klo, khi, val, n, L, head_idx.p, created.p);
         inclusive_max_u32(ctx, head_idx.p, head_idx.p, n);
@@ -599,8 +600,6 @@ void build_graph_from_sequences(mtg_ctx* ctx, const char* seq, const u64* offset
     MTG_CUDA(cudaMemcpyAsync(&h_n, d_tot, sizeof(u32), cudaMemcpyDeviceToHost, s));
     MTG_CUDA(cudaMemcpyAsync(&h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, s));
     MTG_CUDA(cudaStreamSynchronize(s));
-    MTG_CUDA(cudaFreeAsync(d_tot, s));
-    MTG_CUDA(cudaFreeAsync(d_err, s));
     throw_on_err_flag(h_err);
     ctx->N = h_n;
     ctx->edge_from.resize(n, s);
@@ -634,9 +633,10 @@ void build_graph_from_links(mtg_ctx* ctx, u64 U, const u64* weights, u64 n_links
     ctx->k = k;
     ctx->U = U;
     ctx->E = 2 * U;
-    int* d_err = nullptr;
-    MTG_CUDA(cudaMallocAsync((void**)&d_err, sizeof(int), s));
-    MTG_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), s));
+    DBuf<int> err_buf;
+    err_buf.resize(1, s);
+    err_buf.zero(s);
+    int* d_err = err_buf.p;
     if (!prepacked && seq && offsets && U) upload_and_pack(ctx, seq, offsets, U, on_device, total_bases, d_err);
     DBuf<u64> d_w, d_a, d_b;
     DBuf<u8> d_sa, d_sb, rank;
@@ -681,9 +681,10 @@ void build_graph_from_links(mtg_ctx* ctx, u64 U, const u64* weights, u64 n_links
     rep.resize(nslots, s);
     is_rep.resize(nslots, s);
     node_of_rep.resize(nslots, s);
-    u32* d_tot = nullptr;
-    MTG_CUDA(cudaMallocAsync((void**)&d_tot, sizeof(u32), s));
-    MTG_CUDA(cudaMemsetAsync(d_tot, 0, sizeof(u32), s));
+    DBuf<u32> tot_buf;
+    tot_buf.resize(1, s);
+    tot_buf.zero(s);
+    u32* d_tot = tot_buf.p;
     if (nslots) {
         MTG_LAUNCH(ctx, find_representatives, grid_for(nslots, TB), TB, 0, parent.p, nslots, rep.p, is_rep.p);
         exclusive_sum_u32(ctx, is_rep.p, node_of_rep.p, nslots, d_tot);
@@ -700,8 +701,6 @@ void build_graph_from_links(mtg_ctx* ctx, u64 U, const u64* weights, u64 n_links
         MTG_LAUNCH(ctx, verify_pairing, grid_for(U, TB), TB, 0, ctx->edge_from.p, ctx->edge_to.p, ctx->mirror.p, U, d_err);
     }
     check_err_flag(ctx, d_err);
-    MTG_CUDA(cudaFreeAsync(d_tot, s));
-    MTG_CUDA(cudaFreeAsync(d_err, s));
     for (DBuf<u64>* x : {&d_w, &d_a, &d_b}) x->release(s);
     for (DBuf<u8>* x : {&d_sa, &d_sb, &rank}) x->release(s);
     for (DBuf<u32>* x : {&cc, &key_a, &key_b, &op_a, &op_b, &parent, &rep, &is_rep, &node_of_rep}) x->release(s);

@@ -46,6 +46,7 @@ constexpr int TB = 256;
 constexpr u32 META_TRUNC = 0x80000000u;
 constexpr u32 META_COUNT = 0x00FFFFFFu;
 constexpr u32 NO_INDEX = 0xFFFFFFFFu;
+constexpr unsigned long long MATCH_SPIN_LIMIT = 1ull << 26;  // blocked attempts of one source (each >= 100 ns) before giving up: minutes
 
 struct MatchArgs {
     const u32* sources;
@@ -181,15 +182,27 @@ __global__ void __launch_bounds__(TB) match_dataflow_kernel(MatchArgs a) {
         const unsigned long long idx = base + lane;
         if (idx >= a.n_pend) continue;
         const u32 i = a.pend[idx];
-        for (;;) {
-            if (i > ((volatile u32*)a.min_insufficient)[0]) break;  // everything above the smallest insufficient source is redone
-            const TryResult r = try_source(a, i);
-            if (r == TRY_INSUFFICIENT) atomicMin(a.min_insufficient, i);
-            if (r != TRY_BLOCKED) break;
+        // The release store that publishes this source's commit sits INSIDE the loop, on the path that leaves it: lanes of
+        // one warp wait for each other here, so the store must be issued before any point where the compiler could make
+        // the finished lanes wait for the spinning ones.  The spin is bounded: a dependency that never resolves (an
+        // invariant violation, not a legal state) raises the error flag instead of hanging the device.
+        for (unsigned long long spins = 0;; spins++) {
+            TryResult r = TRY_DONE;
+            if (i <= ((volatile u32*)a.min_insufficient)[0]) {  // everything above the smallest insufficient source is redone
+                r = try_source(a, i);
+                if (r == TRY_INSUFFICIENT) atomicMin(a.min_insufficient, i);
+                if (r == TRY_BLOCKED && spins > MATCH_SPIN_LIMIT) {
+                    atomicExch(a.error, 2u);
+                    r = TRY_DONE;
+                }
+            }
+            if (r != TRY_BLOCKED) {
+                st_release(&a.done[i], 1u);  // publishes the commit (release) to the sources waiting behind this one
+                break;
+            }
             retries++;
             __nanosleep(100);
         }
-        st_release(&a.done[i], 1u);  // publishes the commit (release) to the sources waiting behind this one
     }
     for (int o = 16; o > 0; o >>= 1) retries += __shfl_down_sync(0xffffffffu, retries, o);
     if (lane == 0 && retries) atomicAdd(a.retries, retries);
@@ -314,6 +327,20 @@ __global__ void __launch_bounds__(TB)
     list_meta[i] = pool_meta[t];
 }
 
+__global__ void __launch_bounds__(1024) sum_u32_to_u64(const u32* __restrict__ in, u64 n, unsigned long long* __restrict__ out) {
+    __shared__ unsigned long long part[32];
+    unsigned long long acc = 0;
+    for (u64 i = threadIdx.x; i < n; i += 1024) acc += in[i];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int w = 0; w < 32; w++) t += part[w];
+        *out = t;
+    }
+}
+
 int bits_for(u64 n) {
     int b = 1;
     while (b < 32 && (1ull << b) < n) b++;
@@ -371,7 +398,7 @@ void greedy_match(mtg_ctx* ctx, const u64* d_records_all, const u32* d_meta_all,
     cur.resize(N + 1, s);
     small.resize(16, s);  // [0] pending count, [3] min_insufficient, [5..7] scan totals, [8] error
     small.zero(s);
-    big.resize(2, s);
+    big.resize(3, s);
     MTG_LAUNCH(ctx, init_lists, grid_for(S, TB), TB, 0, ctx->sources.p, ctx->mirror.p, ctx->imbalance.p, d_records_all, d_meta_all, S,
                shard_count, padded, cap, list_addr.p, list_meta.p, max_trip.p);
     exclusive_sum_u32(ctx, max_trip.p, trip_off.p, S, small.p + 5);
@@ -421,9 +448,13 @@ void greedy_match(mtg_ctx* ctx, const u64* d_records_all, const u32* d_meta_all,
         // wait lists: (node, source) pairs written in source order, stable sort by node => ascending sources per node
         MTG_LAUNCH(ctx, count_waits, grid_for(S, TB), TB, 0, pend.p, small.p + 0, S, list_addr.p, list_meta.p, mult.p, wait_cnt.p);
         exclusive_sum_u32(ctx, wait_cnt.p, wait_off.p, S, small.p + 6);
+        MTG_LAUNCH(ctx, sum_u32_to_u64, 1, 1024, 0, wait_cnt.p, S, big.p + 2);  // the same total in 64 bits: guards the 32-bit offsets
         u32 h_np[7];
+        unsigned long long h_total64 = 0;
         MTG_CUDA(cudaMemcpyAsync(h_np, small.p, sizeof(h_np), cudaMemcpyDeviceToHost, s));
+        MTG_CUDA(cudaMemcpyAsync(&h_total64, big.p + 2, sizeof(h_total64), cudaMemcpyDeviceToHost, s));
         MTG_CUDA(cudaStreamSynchronize(s));
+        MTG_REQUIRE(h_total64 < 0xFFFFFFF0ull, MTG_ERR_UNSUPPORTED, "wait lists exceed 2^32 entries (candidate lists too deep for this many sources)");
         const u32 n_pend = h_np[0], P = h_np[6];
         trip_cnt.zero(s);
         u32 min_insuff = NO_INDEX;
@@ -470,6 +501,7 @@ void greedy_match(mtg_ctx* ctx, const u64* d_records_all, const u32* d_meta_all,
             MTG_CUDA(cudaMemcpyAsync(h_small, small.p, sizeof(h_small), cudaMemcpyDeviceToHost, s));
             MTG_CUDA(cudaMemcpyAsync(h_big, big.p, sizeof(h_big), cudaMemcpyDeviceToHost, s));
             MTG_CUDA(cudaStreamSynchronize(s));
+            MTG_REQUIRE(h_small[8] != 2, MTG_ERR_INTERNAL, "matching did not make progress (a source waited for a dependency that never resolved)");
             MTG_REQUIRE(h_small[8] == 0, MTG_ERR_INTERNAL, "matching invariant violated (second Dijkstra call for one source)");
             if (phase == 0) MTG_CUDA(cudaEventElapsedTime(&ctx->stats.match_kernel_ms, ctx->ev2, ctx->ev3));
             min_insuff = h_small[3];

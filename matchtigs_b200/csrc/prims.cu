@@ -159,12 +159,12 @@ void scan_impl(mtg_ctx* ctx, const TIn* in, TOut* out, size_t n, TOut* d_total) 
         MTG_LAUNCH(ctx, (scan_single_cta<TIn, TOut, Op, INCLUSIVE>), 1, SCAN1_THREADS, 0, in, out, n, d_total);
         return;
     }
-    TOut* agg = nullptr;
-    MTG_CUDA(cudaMallocAsync((void**)&agg, tiles * sizeof(TOut), ctx->stream));
+    DBuf<TOut> agg_buf;
+    agg_buf.resize(tiles, ctx->stream);
+    TOut* agg = agg_buf.p;
     MTG_LAUNCH(ctx, (scan_reduce_tiles<TIn, TOut, Op>), (unsigned)tiles, SCAN_THREADS, 0, in, agg, n);
     scan_impl<TOut, TOut, Op, false>(ctx, agg, agg, tiles, nullptr);  // in-place exclusive scan of the tile aggregates
     MTG_LAUNCH(ctx, (scan_tiles<TIn, TOut, Op, INCLUSIVE>), (unsigned)tiles, SCAN_THREADS, 0, in, out, (const TOut*)agg, n, d_total);
-    MTG_CUDA(cudaFreeAsync(agg, ctx->stream));
 }
 
 }  // namespace
@@ -315,8 +315,9 @@ int radix_sort_impl(mtg_ctx* ctx, KW* k0_a, KW* k0_b, KW* k1_a, KW* k1_b, u32* v
     MTG_REQUIRE(n < (size_t)0xFFFFFFFFu, MTG_ERR_UNSUPPORTED, "radix sort: more than 2^32-1 elements");
     const int word_bits = (int)sizeof(KW) * 8;
     u32 tiles = (u32)((n + RS_TILE - 1) / RS_TILE);
-    u32* hist = nullptr;
-    MTG_CUDA(cudaMallocAsync((void**)&hist, (size_t)256 * tiles * sizeof(u32), ctx->stream));
+    DBuf<u32> hist_buf;
+    hist_buf.resize((size_t)256 * tiles, ctx->stream);
+    u32* hist = hist_buf.p;
     int cur = 0;
     for (int bit = 0; bit < key_bits; bit += 8) {
         int word = bit / word_bits, shift = bit % word_bits;
@@ -333,7 +334,6 @@ int radix_sort_impl(mtg_ctx* ctx, KW* k0_a, KW* k0_b, KW* k1_a, KW* k1_b, u32* v
         }
         cur ^= 1;
     }
-    MTG_CUDA(cudaFreeAsync(hist, ctx->stream));
     return cur;
 }
 
