@@ -334,6 +334,10 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     ms_res, dj_ms, match_ms, stats, launches, _ = timed(True, args.steps, args.warmup)
+    if args.profile:
+        print(json.dumps({"profile_run": True, "ms_per_step": ms_res, "phases_ms": stats["phases_ms"], "tail_ms": stats["tail_ms"]}), flush=True)
+        ctx.close()
+        return
     ms_e2e, _, _, stats_e2e, _, out = timed(False, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
 
@@ -464,6 +468,7 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--scale", type=float, default=None)
     ap.add_argument("--ref-scale", type=float, default=None, help="--impl reference: recipe scale of the timed sample")
+    ap.add_argument("--profile", action="store_true", help="profiling runs (ncu): one leg, no CPU pass, no bench line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
