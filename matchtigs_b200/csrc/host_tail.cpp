@@ -455,25 +455,27 @@ void walk_and_break(const WalkInput& in, TailOutput& out, TailScratch& scratch) 
                 cand.n += more;
                 // The steps after it are worked out from the used bits of the nodes ahead, whose handles this record
                 // carries: one prefetch per level instead of a fan-out over all candidates.
-                const u32 j1 = nxt - (c & H_BASE);  // garbage for NONE32: >= 2
-                if (use_hints && j1 < 2 && !(c & H_BIG)) {
+                const u32 j1 = nxt - (c & H_BASE);  // garbage for NONE32 and for big nodes
+                const bool four = (c & H_FOUR) != 0;
+                if (use_hints && nxt != NONE32 && !(c & H_BIG) && (four || j1 < 2)) {
                     u32 s2, s3 = NONE32, s4 = NONE32, j2 = 2, j3 = 2, j4 = 2;
-                    if (nxt == S2 && S3 != NONE32 && S4 != NONE32 && (J3 | J4) < 2) {
+                    if (!four && nxt == S2 && S3 != NONE32 && S4 != NONE32 && (J3 | J4) < 2) {
                         s2 = S3, j2 = J3, s3 = S4, j3 = J4;
                     } else {
                         __builtin_prefetch(&recs[nxt]);
-                        s2 = peek(r.h2[j1], &j2);
+                        s2 = peek(r.h[j1], &j2);
                         if (s2 != NONE32) {
                             __builtin_prefetch(&recs[s2]);
-                            if (j2 < 2) {
-                                s3 = peek(r.h3[2 * j1 + j2], &j3);
+                            const u32 at = (four ? WALK_H3_FOUR : WALK_H3_TWO) + 2 * j1 + j2;
+                            if (j2 < 2 && at < sizeof(r.h) / sizeof(u32)) {
+                                s3 = peek(r.h[at], &j3);
                                 if (s3 != NONE32) __builtin_prefetch(&recs[s3]);
                             }
                         }
                     }
 #if MTG_WALK_DEPTH >= 4
-                    if (s3 != NONE32 && j3 < 2 && j2 < 2) {
-                        s4 = peek(r.h4[4 * j1 + 2 * j2 + j3], &j4);
+                    if (!four && s3 != NONE32 && j3 < 2 && j2 < 2) {
+                        s4 = peek(r.h[WALK_H4_TWO + 4 * j1 + 2 * j2 + j3], &j4);
                         if (s4 != NONE32) __builtin_prefetch(&recs[s4]);
                     }
 #endif

@@ -142,30 +142,43 @@ constexpr u32 SLOT_MASK = 0x3FFFFFFFu, SLOT_DUMMY = 0x40000000u, SLOT_BREAK = 0x
 struct alignas(MTG_WALK_DEPTH >= 4 ? 64 : 32) WalkRec {
     u32 to;     // handle of the node this edge leads to
     u32 mslot;  // slot of the mirror edge | SLOT_DUMMY | SLOT_BREAK (dummy of weight >= k)
-    u32 h2[2];  // handles two steps ahead: `to`'s slots 0 and 1
-    u32 h3[4];  // three steps ahead: [2 * j1 + j2]
-#if MTG_WALK_DEPTH >= 4
-    u32 h4[8];  // four steps ahead: [4 * j1 + 2 * j2 + j3]
-#endif
+    // Handles of the nodes ahead.  Two layouts, told apart by the node `to` (which the walk knows anyway):
+    //   `to` owns two slots (H_FOUR clear):  h[0..1]  two steps ahead   = where `to`'s slots j1 = 0, 1 lead
+    //                                        h[2..5]  three steps ahead  [2 + 2 j1 + j2]
+    //                                        h[6..13] four steps ahead   [6 + 4 j1 + 2 j2 + j3]      (depth 4 only)
+    //   `to` owns four slots (H_FOUR set):   h[0..3]  two steps ahead   = where `to`'s slots j1 = 0 .. 3 lead
+    //                                        h[4..11] three steps ahead  [4 + 2 j1 + j2]             (depth 4 only; else h[4..5]
+    //                                                                                                 cover j1 = 0 only)
+    // Behind `to` only the first two slots of every node are followed (j2, j3 < 2).  h[0], h[1] mean the same in both layouts.
+    u32 h[MTG_WALK_DEPTH >= 4 ? 14 : 6];
 };
 static_assert(sizeof(WalkRec) == (MTG_WALK_DEPTH >= 4 ? 64 : 32), "record size");
+constexpr u32 WALK_H3_TWO = 2, WALK_H4_TWO = 6, WALK_H3_FOUR = 4;
 __host__ __device__ inline u32 walk_cap(u32 d) { return d <= 2 ? 2u : d <= 4 ? 4u : 2u + ((d + 1) & ~1u); }
 __host__ __device__ inline u32 walk_handle(u32 base, u32 d) { return base | ((d > 2 && d <= 4) ? H_FOUR : 0u) | (d > 4 ? H_BIG : 0u); }
 // first entry slot and entry count of node h given its degree (entries of a big node sit behind its header pair)
 __host__ __device__ inline u32 walk_first_slot(u32 h) { return (h & H_BASE) + ((h & H_BIG) ? 2u : 0u); }
-// Level t+1 of the hints of record r from level t of the records of `to`'s first two slots (levels are built one
-// after the other over all records).  `to_deg` = out-degree of the node r leads to.
+// Level t+1 of the hints of record r from level t of the records of `to`'s slots (levels are built one after the other
+// over all records).  `to_deg` = out-degree of the node r leads to.
 __host__ __device__ inline void walk_fill_hints(WalkRec* recs, u32 s, u32 to_deg, u32 level) {
     WalkRec& r = recs[s];
     const u32 c0 = walk_first_slot(r.to);
-    for (u32 j = 0; j < 2; j++) {
+    const bool four = (r.to & (H_FOUR | H_BIG)) == H_FOUR;
+    const u32 fan = four ? 4u : 2u;  // slots of `to` this record follows
+    for (u32 j = 0; j < fan; j++) {
         const bool have = j < to_deg;
         const WalkRec& c = recs[c0 + (have ? j : 0u)];
-        if (level == 2) r.h2[j] = have ? c.to : r.to;
-        if (level == 3) r.h3[2 * j] = c.h2[0], r.h3[2 * j + 1] = c.h2[1];
+        if (level == 2) r.h[j] = have ? c.to : r.to;
+        if (level == 3) {
+            const u32 at = (four ? WALK_H3_FOUR : WALK_H3_TWO) + 2 * j;
+            if (at + 1 < sizeof(r.h) / sizeof(u32)) r.h[at] = c.h[0], r.h[at + 1] = c.h[1];
+        }
 #if MTG_WALK_DEPTH >= 4
-        if (level == 4)
-            for (u32 x = 0; x < 4; x++) r.h4[4 * j + x] = c.h3[x];
+        if (level == 4 && !four) {  // the child's level 3 sits where ITS layout puts it
+            const bool c_four = (c.to & (H_FOUR | H_BIG)) == H_FOUR;
+            const u32 from = c_four ? WALK_H3_FOUR : WALK_H3_TWO;
+            for (u32 x = 0; x < 4; x++) r.h[WALK_H4_TWO + 4 * j + x] = c.h[from + x];
+        }
 #endif
     }
 }
