@@ -106,7 +106,8 @@ def config_unitigs(name: str, scale: float = 1.0, threads: int = 0) -> tuple[byt
 def cache_dir() -> Path:
     import os
     d = os.environ.get("MTG_CACHE_DIR")
-    cands = [Path(d)] if d else [Path(__file__).resolve().parent.parent / ".cache", Path("/tmp/mtg_cache")]
+    # outside the repository: gpurun ships the whole tree to the GPU box, half a gigabyte of unitigs must not ride along
+    cands = [Path(d)] if d else [Path("/tmp/mtg_cache"), Path(__file__).resolve().parent.parent / ".cache"]
     for c in cands:
         try:
             c.mkdir(parents=True, exist_ok=True)
