@@ -98,16 +98,50 @@ __device__ __forceinline__ u64 read_bases64(const u64* __restrict__ words, u64 p
 }
 __device__ __forceinline__ char base_char(u32 c) { return (char)((0x47544341u >> (8 * (c & 3u))) & 0xFFu); }  // "ACTG"
 
-constexpr int SEG_CACHE = 1024;  // segment offsets of one CTA's output range kept in shared memory
+constexpr int SEG_CACHE = 512;  // segments of one CTA's output range whose description is staged in shared memory
+
+// Everything fill_text needs to know about one segment (= one walk edge's share of the text), gathered once per segment.
+struct SegMeta {
+    u64 s0;     // first output byte
+    u64 first;  // forward: position of the first body character in the 2-bit store; backward: one past the position of it
+    u32 len;    // bytes incl. header and trailing newline
+    u32 tig;    // 0-based index of the tig (header digits)
+    u32 flags;  // bits 0-7: header bytes; 8: dummy edge; 9: backward edge; 10: ends with '\n'
+};
+__device__ __forceinline__ SegMeta seg_meta(const WalkView& w, int mode, const u64* __restrict__ seg_off, const u32* __restrict__ seg_len,
+                                            const u32* __restrict__ seg_tig, u64 j) {
+    SegMeta m;
+    m.s0 = seg_off[j];
+    m.len = seg_len[j];
+    const u32 e = w.edges[j];
+    const bool dummy = e >= w.E;
+    const u64 t = seg_tig[j];
+    m.tig = (u32)t;
+    const bool last = (j + 1 == w.limits[t]);
+    u32 hdr = 0, skip = 0;
+    if (mode != 0 && !dummy) {
+        const u64 tstart = t ? w.limits[t - 1] : 0;
+        if (j == tstart) hdr = (mode == 1 ? 3 : 2) + dec_digits(t + 1);
+        else {
+            const u32 pe = w.edges[j - 1];
+            skip = pe >= w.E ? w.k - 1 - w.dummy_w[pe - w.E] : w.k - 1;  // src/bin.rs:745-749
+        }
+    }
+    m.first = 0;
+    if (mode != 0 && !dummy) m.first = (e & 1) ? w.seq_off[(e >> 1) + 1] - skip : w.seq_off[e >> 1] + skip;
+    m.flags = hdr | (dummy ? 256u : 0u) | ((e & 1) ? 512u : 0u) | (last ? 1024u : 0u);
+    return m;
+}
 
 // Every CTA produces TB * CHUNK consecutive output bytes.  The segments that intersect that range are found once per CTA
-// (two binary searches) and their offsets staged in shared memory; a thread then locates its first segment there and decodes
-// its 16 bytes from 64-bit reads of the 2-bit store (up to 32 bases per read) instead of one global load per base.
+// (two binary searches) and described once per segment into shared memory (edge, tig, header / overlap lengths, position in
+// the 2-bit store: a dozen dependent global loads per segment instead of per 16 output bytes); a thread then locates its
+// first segment there and decodes its 16 bytes from 64-bit reads of the 2-bit store (up to 32 bases per read).
 __global__ void __launch_bounds__(TB)
     fill_text(WalkView w, int mode, const u64* __restrict__ seg_off, const u32* __restrict__ seg_len, const u32* __restrict__ seg_tig,
               const u64* __restrict__ words, u64 q_base, u64 total, char* __restrict__ out) {
     // produces bytes [q_base, total) of the text into out[0 ..): a rank's share of the output, or all of it
-    __shared__ u64 s_off[SEG_CACHE];
+    __shared__ SegMeta s_meta[SEG_CACHE];
     __shared__ u64 s_j0;
     __shared__ u32 s_n;
     const u64 cta_q0 = q_base + (u64)blockIdx.x * TB * CHUNK;
@@ -123,7 +157,7 @@ __global__ void __launch_bounds__(TB)
     const u32 n_seg = s_n;
     const bool cached = n_seg <= SEG_CACHE;
     if (cached)
-        for (u32 i = threadIdx.x; i < n_seg; i += TB) s_off[i] = seg_off[j0 + i];
+        for (u32 i = threadIdx.x; i < n_seg; i += TB) s_meta[i] = seg_meta(w, mode, seg_off, seg_len, seg_tig, j0 + i);
     __syncthreads();
     const u64 q0 = cta_q0 + (u64)threadIdx.x * CHUNK;
     if (q0 >= total) return;
@@ -132,7 +166,7 @@ __global__ void __launch_bounds__(TB)
         u32 lo = 0, hi = n_seg;
         while (lo < hi) {
             const u32 mid = (lo + hi) >> 1;
-            if (s_off[mid] <= q0) lo = mid + 1;
+            if (s_meta[mid].s0 <= q0) lo = mid + 1;
             else hi = mid;
         }
         j = j0 + lo - 1;
@@ -143,26 +177,17 @@ __global__ void __launch_bounds__(TB)
     u64 q = q0;
     const u64 qend = min(q0 + (u64)CHUNK, total);
     while (q < qend) {
-        while (seg_off[j] + seg_len[j] <= q) j++;  // skips empty segments
-        const u64 s0 = seg_off[j];
-        const u32 len = seg_len[j];
-        const u32 e = w.edges[j];
-        const bool dummy = e >= w.E;
-        const u64 t = seg_tig[j];
-        const u64 tstart = t ? w.limits[t - 1] : 0;
-        const bool last = (j + 1 == w.limits[t]);
-        u32 hdr = 0, skip = 0;
-        if (mode != 0 && !dummy) {
-            if (j == tstart) hdr = (mode == 1 ? 3 : 2) + dec_digits(t + 1);
-            else {
-                const u32 pe = w.edges[j - 1];
-                skip = pe >= w.E ? w.k - 1 - w.dummy_w[pe - w.E] : w.k - 1;
-            }
+        SegMeta m = cached ? s_meta[j - j0] : seg_meta(w, mode, seg_off, seg_len, seg_tig, j);
+        while (m.s0 + m.len <= q) {  // skips empty segments
+            j++;
+            m = cached ? s_meta[j - j0] : seg_meta(w, mode, seg_off, seg_len, seg_tig, j);
         }
-        const u64 seg_end = s0 + len;
-        const u64 stop = min(qend, seg_end);  // this thread's bytes of the segment: [q, stop)
-        const u32 body_end = len - (last ? 1u : 0u);  // segment-relative index of the trailing '\n', if any
-        // header characters
+        const u64 s0 = m.s0;
+        const u32 len = m.len, hdr = m.flags & 255u;
+        const bool dummy = (m.flags & 256u) != 0, backward = (m.flags & 512u) != 0, last = (m.flags & 1024u) != 0;
+        const u64 stop = min(qend, s0 + len);             // this thread's bytes of the segment: [q, stop)
+        const u32 body_end = len - (last ? 1u : 0u);      // segment-relative index of the trailing '\n', if any
+        // header characters: "S\t<i>\t" (GFA) / "><i>\n" (FASTA)
         for (; q < stop && (u32)(q - s0) < hdr; q++) {
             const u32 c = (u32)(q - s0);
             char ch;
@@ -170,7 +195,7 @@ __global__ void __launch_bounds__(TB)
             else if (c == hdr - 1) ch = mode == 1 ? '\t' : '\n';
             else if (mode == 1 && c == 1) ch = '\t';
             else {
-                u64 v = t + 1;
+                u64 v = (u64)m.tig + 1;
                 for (u32 r = hdr - 2 - c; r > 0; r--) v /= 10;
                 ch = (char)('0' + v % 10);
             }
@@ -183,18 +208,13 @@ __global__ void __launch_bounds__(TB)
             if (mode == 0) {
                 const char ch = dummy ? '0' : '1';
                 for (u32 i = 0; i < nb; i++) buf[q - q0 + i] = ch;
+            } else if (!backward) {
+                u64 bits = read_bases64(words, m.first + (c0 - hdr));
+                for (u32 i = 0; i < nb; i++, bits >>= 2) buf[q - q0 + i] = base_char((u32)bits);
             } else {
-                const u64 u = e >> 1;
-                const u64 b0 = (u64)(c0 - hdr) + skip;  // index of the first character inside the oriented unitig string
-                if (!(e & 1)) {
-                    u64 bits = read_bases64(words, w.seq_off[u] + b0);
-                    for (u32 i = 0; i < nb; i++, bits >>= 2) buf[q - q0 + i] = base_char((u32)bits);
-                } else {
-                    // reverse complement: oriented index b <-> stored position send - 1 - b, complement = code ^ 2
-                    const u64 lo = w.seq_off[u + 1] - b0 - nb;  // stored position of the LAST character of this run
-                    u64 bits = read_bases64(words, lo);
-                    for (u32 i = 0; i < nb; i++, bits >>= 2) buf[q - q0 + (nb - 1 - i)] = base_char((u32)bits ^ 2u);
-                }
+                // reverse complement: oriented index b <-> stored position first - 1 - b, complement = code ^ 2
+                u64 bits = read_bases64(words, m.first - (c0 - hdr) - nb);  // from the stored position of the LAST character of this run
+                for (u32 i = 0; i < nb; i++, bits >>= 2) buf[q - q0 + (nb - 1 - i)] = base_char((u32)bits ^ 2u);
             }
             q += nb;
         }

@@ -184,6 +184,7 @@ struct WalkInput {
     const u32* start_handle; // [E0] handle of the from-node of every original edge (device-prepared path)
     const u32* dummy_w;      // weight of dummy edge e at [e - E0]
     bool matching_light;     // every matching dummy weighs less than k (always true behind the GPU matching)
+    bool hints;              // the records carry their lookahead levels (not worth building while everything is cache-resident)
 };
 
 void walk_and_break(const WalkInput& w, TailOutput& out, TailScratch& scratch);
@@ -246,7 +247,10 @@ void build_walk_records(u32 n, u64 E0, u64 E, u32 k, const u32* out_deg, const u
         for (u32 j = 0; j < cap; j++) d += slot_edge[base + j] != NONE32;
         return d;
     };
-    for (u32 level = 2; level <= WALK_DEPTH; level++) {
+    // The lookahead levels only pay off once the records outgrow the caches; below that (every graph the library prepares
+    // on the host) building them would cost more than the walk itself.
+    w.hints = n_slots * sizeof(WalkRec) > (64u << 20);
+    for (u32 level = 2; w.hints && level <= WALK_DEPTH; level++) {
 #pragma omp parallel for schedule(static) if (par)
         for (i64 sl = 0; sl < (i64)n_slots; sl++)
             if (slot_edge[sl] != NONE32) walk_fill_hints(recs, (u32)sl, deg_of_handle(recs[sl].to), level);
@@ -319,7 +323,8 @@ void run_tail(const TailInput& in, TailOutput& out, TailScratch& scratch) {
         out.dummy_w[2 * j] = out.dummy_w[2 * j + 1] = pairs[j].w;
         if (j < in.n_triples) max_matching_w = std::max(max_matching_w, pairs[j].w);
     }
-    WalkInput w{in.k, in.n_nodes, E0, E, 0, nullptr, nullptr, nullptr, nullptr, nullptr, in.from, nullptr, out.dummy_w.data(), max_matching_w < in.k};
+    WalkInput w{in.k, in.n_nodes, E0, E, 0, nullptr, nullptr, nullptr, nullptr, nullptr, in.from, nullptr, out.dummy_w.data(), max_matching_w < in.k,
+                false};
     build_walk_records(n, E0, E, in.k, od, out.dummy_w.data(), in.oldest_first,
                        [&](u32 e, u32* f, u32* t) {
                            if (e < E0) {
@@ -408,7 +413,7 @@ void walk_and_break(const WalkInput& in, TailOutput& out, TailScratch& scratch) 
         size_t ci, ce;   // children of this block: children[ci, ce)
     };
     std::vector<Frame> stack;
-    const bool use_hints = !getenv("MTG_TAIL_NOHINT");
+    const bool use_hints = in.hints && !getenv("MTG_TAIL_NOHINT");
     // Positions whose from-node may still own an unused out-edge, in cycle order from the head.  A position is only
     // recorded if its node had slots left when the walk passed (exhaustion is permanent), which skips about half of
     // the re-root probes.
@@ -439,9 +444,11 @@ void walk_and_break(const WalkInput& in, TailOutput& out, TailScratch& scratch) 
         for (;;) {
             cand.push_back((u32)q_slot.size());  // a walk start is always probed again
             u32 s = start_slot, from_h = start_from;
-            // What the walk expects two, three and four steps from now (slot, and its index inside its node), carried
-            // from step to step: as long as the next slot is the one expected, only the deepest level has to be worked out.
-            u32 S2 = NONE32, S3 = NONE32, S4 = NONE32, J3 = 0, J4 = 0;
+            // What the walk expects 2 .. WALK_DEPTH steps from now -- P[L] = slot, Q[L] = its index inside its node --
+            // carried from step to step: as long as the next slot is the one expected, only the deepest level has to be
+            // worked out.  P[L] == NONE32 ends the chain.
+            u32 P[WALK_DEPTH + 2], Q[WALK_DEPTH + 2];
+            for (u32 L = 0; L < WALK_DEPTH + 2; L++) P[L] = NONE32, Q[L] = 2;
             while (s != NONE32) {
                 const WalkRec& r = recs[s];
                 const u32 ms = r.mslot;
@@ -458,31 +465,37 @@ void walk_and_break(const WalkInput& in, TailOutput& out, TailScratch& scratch) 
                 const u32 j1 = nxt - (c & H_BASE);  // garbage for NONE32 and for big nodes
                 const bool four = (c & H_FOUR) != 0;
                 if (use_hints && nxt != NONE32 && !(c & H_BIG) && (four || j1 < 2)) {
-                    u32 s2, s3 = NONE32, s4 = NONE32, j2 = 2, j3 = 2, j4 = 2;
-                    if (!four && nxt == S2 && S3 != NONE32 && S4 != NONE32 && (J3 | J4) < 2) {
-                        s2 = S3, j2 = J3, s3 = S4, j3 = J4;
-                    } else {
-                        __builtin_prefetch(&recs[nxt]);
-                        s2 = peek(r.h[j1], &j2);
-                        if (s2 != NONE32) {
-                            __builtin_prefetch(&recs[s2]);
-                            const u32 at = (four ? WALK_H3_FOUR : WALK_H3_TWO) + 2 * j1 + j2;
-                            if (j2 < 2 && at < sizeof(r.h) / sizeof(u32)) {
-                                s3 = peek(r.h[at], &j3);
-                                if (s3 != NONE32) __builtin_prefetch(&recs[s3]);
+                    const u32 last = four ? WALK_DEPTH - 1 : WALK_DEPTH;  // deepest level this record knows
+                    u32 L = 2, idx = j1;  // idx = index of the path so far inside level L
+                    bool chain = true;
+                    if (!four && nxt == P[2]) {
+                        // expected: what was worked out last time moves one step closer
+                        bool whole = true;
+                        for (u32 M = 3; M <= WALK_DEPTH; M++) whole &= P[M] != NONE32 && Q[M] < 2;
+                        if (whole) {
+                            for (u32 M = 2; M < WALK_DEPTH; M++) {
+                                P[M] = P[M + 1], Q[M] = Q[M + 1];
+                                idx = 2 * idx + Q[M];
                             }
+                            L = WALK_DEPTH;
                         }
                     }
-#if MTG_WALK_DEPTH >= 4
-                    if (!four && s3 != NONE32 && j3 < 2 && j2 < 2) {
-                        s4 = peek(r.h[WALK_H4_TWO + 4 * j1 + 2 * j2 + j3], &j4);
-                        if (s4 != NONE32) __builtin_prefetch(&recs[s4]);
+                    if (L == 2) __builtin_prefetch(&recs[nxt]);
+                    for (; L <= last && chain; L++) {
+                        const u32 at = (four ? walk_level_four(L) : walk_level_two(L)) + idx;
+                        u32 j = 2;
+                        const u32 sl = peek(r.h[at], &j);
+                        P[L] = sl, Q[L] = j;
+                        if (sl == NONE32) break;
+                        __builtin_prefetch(&recs[sl]);
+                        if (WALK_DEPTH >= 5) __builtin_prefetch(reinterpret_cast<const char*>(&recs[sl]) + 64);
+                        chain = j < 2;
+                        idx = 2 * idx + j;
                     }
-#endif
-                    S2 = s2, S3 = s3, S4 = s4, J3 = j3, J4 = j4;
+                    for (; L <= WALK_DEPTH; L++) P[L] = NONE32, Q[L] = 2;  // nothing known beyond
                 } else {
                     if (nxt != NONE32) __builtin_prefetch(&recs[nxt]);
-                    S2 = S3 = S4 = NONE32;
+                    for (u32 L = 2; L <= WALK_DEPTH; L++) P[L] = NONE32;
                 }
                 from_h = c;
                 s = nxt;
@@ -762,7 +775,7 @@ void finish_walks(mtg_ctx* ctx) {
     auto warm_copy = [](void* dst, const void* src, size_t bytes) {
         const size_t chunk = 256 << 10;
         const i64 n_chunks = (i64)((bytes + chunk - 1) / chunk);
-#pragma omp parallel for schedule(static) num_threads(4) if (bytes > (8u << 20))
+#pragma omp parallel for schedule(static) num_threads(8) if (bytes > (8u << 20))
         for (i64 c = 0; c < n_chunks; c++) {
             const size_t o = (size_t)c * chunk;
             memcpy((char*)dst + o, (const char*)src + o, std::min(chunk, bytes - o));
@@ -795,7 +808,7 @@ void finish_walks(mtg_ctx* ctx) {
     else memset(used, 0, used_bytes);  // empty graph
     double t2 = now_ms();
     WalkInput w{ctx->k, N, E0, E0 + 2 * P, tr.n_slots, recs, used, nullptr, tr.slot_edge, tr.slot_of_edge, nullptr, tr.handle,
-                out.dummy_w.data(), max_matching_w < ctx->k};
+                out.dummy_w.data(), max_matching_w < ctx->k, true};
     walk_and_break(w, out, scratch);
     ctx->walk_edges.swap(out.walk_edges);
     ctx->walk_limits.swap(out.walk_limits);

@@ -134,52 +134,53 @@ struct PinnedBuf {
 // node on the way, so the walk can work out exactly which record it will need WALK_DEPTH steps from now and prefetch
 // that one line (instead of fanning out over 2^depth candidates).
 #ifndef MTG_WALK_DEPTH
-#define MTG_WALK_DEPTH 4
+#define MTG_WALK_DEPTH 5
 #endif
+static_assert(MTG_WALK_DEPTH >= 3 && MTG_WALK_DEPTH <= 5, "walk records carry 3, 4 or 5 levels");
 constexpr u32 WALK_DEPTH = MTG_WALK_DEPTH;
+constexpr u32 WALK_HINTS = (1u << WALK_DEPTH) - 2;  // 2 + 4 + ... + 2^(depth-1) handles
 constexpr u32 H_BIG = 0x80000000u, H_FOUR = 1u, H_BASE = 0x7FFFFFFEu;
 constexpr u32 SLOT_MASK = 0x3FFFFFFFu, SLOT_DUMMY = 0x40000000u, SLOT_BREAK = 0x80000000u;
 struct alignas(MTG_WALK_DEPTH >= 4 ? 64 : 32) WalkRec {
     u32 to;     // handle of the node this edge leads to
     u32 mslot;  // slot of the mirror edge | SLOT_DUMMY | SLOT_BREAK (dummy of weight >= k)
-    // Handles of the nodes ahead.  Two layouts, told apart by the node `to` (which the walk knows anyway):
-    //   `to` owns two slots (H_FOUR clear):  h[0..1]  two steps ahead   = where `to`'s slots j1 = 0, 1 lead
-    //                                        h[2..5]  three steps ahead  [2 + 2 j1 + j2]
-    //                                        h[6..13] four steps ahead   [6 + 4 j1 + 2 j2 + j3]      (depth 4 only)
-    //   `to` owns four slots (H_FOUR set):   h[0..3]  two steps ahead   = where `to`'s slots j1 = 0 .. 3 lead
-    //                                        h[4..11] three steps ahead  [4 + 2 j1 + j2]             (depth 4 only; else h[4..5]
-    //                                                                                                 cover j1 = 0 only)
-    // Behind `to` only the first two slots of every node are followed (j2, j3 < 2).  h[0], h[1] mean the same in both layouts.
-    u32 h[MTG_WALK_DEPTH >= 4 ? 14 : 6];
+    // Handles of the nodes ahead: level L = where the walk can be L steps after taking this edge, indexed by the slot
+    // choices j1 (at `to`), j2, ... j(L-1) on the way.  Behind `to` only the first two slots of every node are followed.
+    // Two layouts, told apart by the node `to` (which the walk knows anyway):
+    //   `to` owns two slots (H_FOUR clear):  level L at h[2^(L-1) - 2 ...], index = binary number j1 j2 .. j(L-1); L = 2 .. depth
+    //   `to` owns four slots (H_FOUR set):   level L at h[2^L - 4 ...],     index = j1 * 2^(L-2) + binary number j2 .. j(L-1),
+    //                                        j1 = 0 .. 3; L = 2 .. depth - 1 (one level less, but a third or fourth visit of
+    //                                        `to` is still announced)
+    // h[0], h[1] (where `to`'s slots 0 and 1 lead) mean the same in both layouts.
+    u32 h[WALK_HINTS];
 };
-static_assert(sizeof(WalkRec) == (MTG_WALK_DEPTH >= 4 ? 64 : 32), "record size");
-constexpr u32 WALK_H3_TWO = 2, WALK_H4_TWO = 6, WALK_H3_FOUR = 4;
+static_assert(sizeof(WalkRec) == 4u << MTG_WALK_DEPTH, "record size: 32, 64 or 128 bytes");
+__host__ __device__ inline u32 walk_level_two(u32 level) { return (1u << (level - 1)) - 2u; }   // first index of level L, two-slot layout
+__host__ __device__ inline u32 walk_level_four(u32 level) { return (1u << level) - 4u; }        // ... four-slot layout
+__host__ __device__ inline bool walk_is_four(u32 handle) { return (handle & (H_FOUR | H_BIG)) == H_FOUR; }
 __host__ __device__ inline u32 walk_cap(u32 d) { return d <= 2 ? 2u : d <= 4 ? 4u : 2u + ((d + 1) & ~1u); }
 __host__ __device__ inline u32 walk_handle(u32 base, u32 d) { return base | ((d > 2 && d <= 4) ? H_FOUR : 0u) | (d > 4 ? H_BIG : 0u); }
 // first entry slot and entry count of node h given its degree (entries of a big node sit behind its header pair)
 __host__ __device__ inline u32 walk_first_slot(u32 h) { return (h & H_BASE) + ((h & H_BIG) ? 2u : 0u); }
-// Level t+1 of the hints of record r from level t of the records of `to`'s slots (levels are built one after the other
-// over all records).  `to_deg` = out-degree of the node r leads to.
+// Level `level` of the hints of record r from level - 1 of the records of `to`'s slots (levels are built one after the
+// other over all records).  `to_deg` = out-degree of the node r leads to.
 __host__ __device__ inline void walk_fill_hints(WalkRec* recs, u32 s, u32 to_deg, u32 level) {
     WalkRec& r = recs[s];
     const u32 c0 = walk_first_slot(r.to);
-    const bool four = (r.to & (H_FOUR | H_BIG)) == H_FOUR;
-    const u32 fan = four ? 4u : 2u;  // slots of `to` this record follows
+    const bool four = walk_is_four(r.to);
+    if (four && level >= WALK_DEPTH) return;  // the four-slot layout ends one level earlier
+    const u32 fan = four ? 4u : 2u;           // slots of `to` this record follows
+    const u32 width = 1u << (level - 2);      // entries per slot of `to` at this level
+    const u32 dst0 = four ? walk_level_four(level) : walk_level_two(level);
     for (u32 j = 0; j < fan; j++) {
         const bool have = j < to_deg;
         const WalkRec& c = recs[c0 + (have ? j : 0u)];
-        if (level == 2) r.h[j] = have ? c.to : r.to;
-        if (level == 3) {
-            const u32 at = (four ? WALK_H3_FOUR : WALK_H3_TWO) + 2 * j;
-            if (at + 1 < sizeof(r.h) / sizeof(u32)) r.h[at] = c.h[0], r.h[at + 1] = c.h[1];
+        if (level == 2) {
+            r.h[dst0 + j] = have ? c.to : r.to;
+        } else {  // the child's level - 1, restricted to its first two slots, sits where ITS layout puts it
+            const u32 src0 = walk_is_four(c.to) ? walk_level_four(level - 1) : walk_level_two(level - 1);
+            for (u32 x = 0; x < width; x++) r.h[dst0 + j * width + x] = c.h[src0 + x];
         }
-#if MTG_WALK_DEPTH >= 4
-        if (level == 4 && !four) {  // the child's level 3 sits where ITS layout puts it
-            const bool c_four = (c.to & (H_FOUR | H_BIG)) == H_FOUR;
-            const u32 from = c_four ? WALK_H3_FOUR : WALK_H3_TWO;
-            for (u32 x = 0; x < 4; x++) r.h[WALK_H4_TWO + 4 * j + x] = c.h[from + x];
-        }
-#endif
     }
 }
 

@@ -437,7 +437,8 @@ def test_performance_counters_and_cli_lines(mt, ctx):
     g = tools.genome(30_000, 3, families=6, copies=6, min_len=40, max_len=400, divergence=0.03, tandem_arrays=5)
     text, _, _ = tools.unitigs(g, 21)
     o, st = compare_all(mt, ctx, text, 21, "fasta", cap=16)
-    assert st["labelled_nodes"] >= st["settled_nodes"] > 0
+    # sources without a traversable out-edge settle themselves without a label table, truncated searches leave labels open
+    assert st["labelled_nodes"] > 0 and st["settled_nodes"] > 0
     assert 1 <= st["max_open_nodes"] <= st["max_labelled_nodes"] <= st["labelled_nodes"]
     # the reference's search stops after m+1 targets; the GPU searches to the cap, so it labels at least as much per search
     assert st["max_labelled_nodes"] >= 1 and o.num("max_max_distance_array_size") >= 1
