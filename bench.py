@@ -297,10 +297,11 @@ def run_ours(args):
             step(resident)
         barrier()
         total_ms, dj_ms, mt_ms, djk_ms, mtk_ms, stats, out = 0.0, 0.0, 0.0, 0.0, 0.0, None, None
-        per_step, tail = [], {}
+        per_step, tail, per_step_phases = [], {}, []
         launches0 = ctx.kernel_launches
         phase_s.clear()
         for _ in range(steps):
+            before = dict(phase_s)
             with torch.cuda.stream(ext):
                 flush.zero_()  # evict L2 between timed iterations (outside the event pair)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -310,6 +311,7 @@ def run_ours(args):
             e1.record(ext)
             barrier()
             per_step.append(e0.elapsed_time(e1))
+            per_step_phases.append({n: round(1e3 * (v - before.get(n, 0.0)), 2) for n, v in phase_s.items()})
             total_ms += per_step[-1]
             stats = ctx.search_stats()
             dj_ms += stats["dijkstra_ms"]
@@ -324,9 +326,11 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms, dj_ms, mt_ms, djk_ms, mtk_ms = (float(x) for x in t.cpu())
+        slowest = max(range(steps), key=lambda i: per_step[i])
+        slow_info = {"step": slowest, "ms": per_step[slowest], "phases_ms": per_step_phases[slowest]}
         per_step.sort()
         stats = dict(stats, dijkstra_kernel_ms=djk_ms / steps, match_kernel_ms=mtk_ms / steps,
-                     spread={"min": per_step[0], "median": per_step[len(per_step) // 2], "max": per_step[-1]},
+                     spread={"min": per_step[0], "median": per_step[len(per_step) // 2], "max": per_step[-1], "slowest": slow_info},
                      phases_ms={n: 1e3 * v / steps for n, v in phase_s.items()}, tail_ms=tail)
         return total_ms / steps, dj_ms / steps, mt_ms / steps, stats, launches, out
 
