@@ -133,28 +133,33 @@ __device__ __forceinline__ SegMeta seg_meta(const WalkView& w, int mode, const u
     return m;
 }
 
-// Every CTA produces TB * CHUNK consecutive output bytes.  The segments that intersect that range are found once per CTA
-// (two binary searches) and described once per segment into shared memory (edge, tig, header / overlap lengths, position in
+// first[b] = the segment that holds the first output byte of CTA b of fill_text (byte q_base + b * TB * CHUNK): every
+// non-empty segment announces itself to the CTAs that start inside it (almost always none or one), so that no CTA has to
+// binary-search the offsets -- a chain of ~20 dependent global loads in front of a barrier, which used to BE the kernel.
+__global__ void __launch_bounds__(TB)
+    cta_first_segments(const u64* __restrict__ seg_off, const u32* __restrict__ seg_len, u64 W, u64 q_base, u64 q_end, u32* __restrict__ first) {
+    const u64 j = (u64)blockIdx.x * TB + threadIdx.x;
+    if (j >= W) return;
+    const u64 s0 = seg_off[j], s1 = s0 + seg_len[j];
+    if (s1 <= s0 || s1 <= q_base || s0 >= q_end) return;
+    const u64 span = (u64)TB * CHUNK;
+    u64 b = s0 <= q_base ? 0 : (s0 - q_base + span - 1) / span;
+    for (; q_base + b * span < s1 && q_base + b * span < q_end; b++) first[b] = (u32)j;
+}
+
+// Every CTA produces TB * CHUNK consecutive output bytes.  The segments that intersect that range (from the first segment
+// of this CTA to the first segment of the next) are described once per segment into shared memory (edge, tig, header / overlap lengths, position in
 // the 2-bit store: a dozen dependent global loads per segment instead of per 16 output bytes); a thread then locates its
 // first segment there and decodes its 16 bytes from 64-bit reads of the 2-bit store (up to 32 bases per read).
 __global__ void __launch_bounds__(TB)
     fill_text(WalkView w, int mode, const u64* __restrict__ seg_off, const u32* __restrict__ seg_len, const u32* __restrict__ seg_tig,
-              const u64* __restrict__ words, u64 q_base, u64 total, char* __restrict__ out) {
+              const u32* __restrict__ first, const u64* __restrict__ words, u64 q_base, u64 total, char* __restrict__ out) {
     // produces bytes [q_base, total) of the text into out[0 ..): a rank's share of the output, or all of it
     __shared__ SegMeta s_meta[SEG_CACHE];
-    __shared__ u64 s_j0;
-    __shared__ u32 s_n;
     const u64 cta_q0 = q_base + (u64)blockIdx.x * TB * CHUNK;
-    const u64 cta_q1 = min(cta_q0 + (u64)TB * CHUNK, total);
-    if (threadIdx.x == 0) {
-        const u64 j0 = segment_of(seg_off, w.W, cta_q0);
-        const u64 j1 = segment_of(seg_off, w.W, cta_q1 - 1);
-        s_j0 = j0;
-        s_n = (u32)min((u64)SEG_CACHE + 1, j1 - j0 + 1);
-    }
-    __syncthreads();
-    const u64 j0 = s_j0;
-    const u32 n_seg = s_n;
+    const u64 j0 = first[blockIdx.x];
+    const u64 j1 = blockIdx.x + 1 < gridDim.x ? (u64)first[blockIdx.x + 1] : w.W - 1;
+    const u32 n_seg = (u32)min((u64)SEG_CACHE + 1, j1 - j0 + 1);
     const bool cached = n_seg <= SEG_CACHE;
     if (cached)
         for (u32 i = threadIdx.x; i < n_seg; i += TB) s_meta[i] = seg_meta(w, mode, seg_off, seg_len, seg_tig, j0 + i);
@@ -288,7 +293,11 @@ u64 emit(mtg_ctx* ctx, int mode, const char* prefix, size_t prefix_len, char* ou
             out_buf.resize(part + CHUNK, s);
             char* d_out = out_buf.p;
             u64 chunks = (part + CHUNK - 1) / CHUNK;
-            MTG_LAUNCH(ctx, fill_text, grid_for(chunks, TB), TB, 0, w, mode, seg_off.p, seg_len.p, seg_tig.p, ctx->seq_words.p, b0, b1, d_out);
+            const dim3 grid = grid_for(chunks, TB);
+            DBuf<u32> first;
+            first.resize(grid.x + 1, s);
+            MTG_LAUNCH(ctx, cta_first_segments, grid_for(w.W, TB), TB, 0, seg_off.p, seg_len.p, w.W, b0, b1, first.p);
+            MTG_LAUNCH(ctx, fill_text, grid, TB, 0, w, mode, seg_off.p, seg_len.p, seg_tig.p, first.p, ctx->seq_words.p, b0, b1, d_out);
             MTG_CUDA(cudaMemcpyAsync(stage.p + prefix_len, d_out, part, cudaMemcpyDeviceToHost, s));
             MTG_CUDA(cudaStreamSynchronize(s));
         }

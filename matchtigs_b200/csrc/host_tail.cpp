@@ -444,11 +444,13 @@ void walk_and_break(const WalkInput& in, TailOutput& out, TailScratch& scratch) 
         for (;;) {
             cand.push_back((u32)q_slot.size());  // a walk start is always probed again
             u32 s = start_slot, from_h = start_from;
-            // What the walk expects 2 .. WALK_DEPTH steps from now -- P[L] = slot, Q[L] = its index inside its node --
-            // carried from step to step: as long as the next slot is the one expected, only the deepest level has to be
-            // worked out.  P[L] == NONE32 ends the chain.
+            // What the walk expects 2 .. `have` steps from now -- P[L] = slot, Q[L] = its index inside its node -- carried
+            // from step to step: as long as the next slot is the one expected, everything moves one step closer and only
+            // the far end of the chain has to be extended (normally by one level: one look at the used bits, one prefetch).
+            // The chain ends at a node that will be left through its third or fourth slot (the records follow two slots
+            // per node behind their own target) and grows again once that node is the next one.
             u32 P[WALK_DEPTH + 2], Q[WALK_DEPTH + 2];
-            for (u32 L = 0; L < WALK_DEPTH + 2; L++) P[L] = NONE32, Q[L] = 2;
+            u32 have = 1;  // deepest level known
             while (s != NONE32) {
                 const WalkRec& r = recs[s];
                 const u32 ms = r.mslot;
@@ -460,42 +462,36 @@ void walk_and_break(const WalkInput& in, TailOutput& out, TailScratch& scratch) 
                 const u32 nxt = first_unused(c);  // the next step is certain
                 cand.p[cand.n] = (u32)q_slot.size();
                 cand.n += more;
-                // The steps after it are worked out from the used bits of the nodes ahead, whose handles this record
-                // carries: one prefetch per level instead of a fan-out over all candidates.
-                const u32 j1 = nxt - (c & H_BASE);  // garbage for NONE32 and for big nodes
-                const bool four = (c & H_FOUR) != 0;
-                if (use_hints && nxt != NONE32 && !(c & H_BIG) && (four || j1 < 2)) {
-                    const u32 last = four ? WALK_DEPTH - 1 : WALK_DEPTH;  // deepest level this record knows
-                    u32 L = 2, idx = j1;  // idx = index of the path so far inside level L
-                    bool chain = true;
-                    if (!four && nxt == P[2]) {
-                        // expected: what was worked out last time moves one step closer
-                        bool whole = true;
-                        for (u32 M = 3; M <= WALK_DEPTH; M++) whole &= P[M] != NONE32 && Q[M] < 2;
-                        if (whole) {
-                            for (u32 M = 2; M < WALK_DEPTH; M++) {
-                                P[M] = P[M + 1], Q[M] = Q[M + 1];
-                                idx = 2 * idx + Q[M];
-                            }
-                            L = WALK_DEPTH;
-                        }
+                if (use_hints && nxt != NONE32 && !(c & H_BIG)) {
+                    if (have >= 2 && nxt == P[2]) {  // as expected
+                        for (u32 M = 2; M < have; M++) P[M] = P[M + 1], Q[M] = Q[M + 1];
+                        have--;
+                    } else {
+                        __builtin_prefetch(&recs[nxt]);
+                        have = 1;
                     }
-                    if (L == 2) __builtin_prefetch(&recs[nxt]);
-                    for (; L <= last && chain; L++) {
-                        const u32 at = (four ? walk_level_four(L) : walk_level_two(L)) + idx;
+                    // extend the chain as far as this record's layout and the path allow
+                    const bool four = (c & H_FOUR) != 0;
+                    const u32 last = four ? WALK_DEPTH - 1 : WALK_DEPTH;  // deepest level this record knows
+                    u32 idx = nxt - (c & H_BASE);                       // slot choice at `to`: 0 .. 3
+                    bool open_end = true;
+                    for (u32 M = 2; M <= have; M++) {
+                        open_end = Q[M] < 2;
+                        idx = 2 * idx + Q[M];
+                    }
+                    for (u32 L = have + 1; open_end && L <= last; L++) {
                         u32 j = 2;
-                        const u32 sl = peek(r.h[at], &j);
-                        P[L] = sl, Q[L] = j;
+                        const u32 sl = peek(r.h[(four ? walk_level_four(L) : walk_level_two(L)) + idx], &j);
                         if (sl == NONE32) break;
                         __builtin_prefetch(&recs[sl]);
                         if (WALK_DEPTH >= 5) __builtin_prefetch(reinterpret_cast<const char*>(&recs[sl]) + 64);
-                        chain = j < 2;
+                        P[L] = sl, Q[L] = j, have = L;
+                        open_end = j < 2;
                         idx = 2 * idx + j;
                     }
-                    for (; L <= WALK_DEPTH; L++) P[L] = NONE32, Q[L] = 2;  // nothing known beyond
                 } else {
                     if (nxt != NONE32) __builtin_prefetch(&recs[nxt]);
-                    for (u32 L = 2; L <= WALK_DEPTH; L++) P[L] = NONE32;
+                    have = 1;
                 }
                 from_h = c;
                 s = nxt;

@@ -448,7 +448,10 @@ void greedy_match(mtg_ctx* ctx, const u64* d_records_all, const u32* d_meta_all,
         // wait lists: (node, source) pairs written in source order, stable sort by node => ascending sources per node
         MTG_LAUNCH(ctx, count_waits, grid_for(S, TB), TB, 0, pend.p, small.p + 0, S, list_addr.p, list_meta.p, mult.p, wait_cnt.p);
         exclusive_sum_u32(ctx, wait_cnt.p, wait_off.p, S, small.p + 6);
-        MTG_LAUNCH(ctx, sum_u32_to_u64, 1, 1024, 0, wait_cnt.p, S, big.p + 2);  // the same total in 64 bits: guards the 32-bit offsets
+        // the 32-bit offsets are safe if even the worst case fits; otherwise the same total is taken in 64 bits
+        const bool need_guard = (u64)S * ((u64)cap + 1) >= 0xFFFFFFF0ull;
+        if (need_guard) MTG_LAUNCH(ctx, sum_u32_to_u64, 1, 1024, 0, wait_cnt.p, S, big.p + 2);
+        else MTG_CUDA(cudaMemsetAsync(big.p + 2, 0, sizeof(unsigned long long), s));
         u32 h_np[7];
         unsigned long long h_total64 = 0;
         MTG_CUDA(cudaMemcpyAsync(h_np, small.p, sizeof(h_np), cudaMemcpyDeviceToHost, s));

@@ -134,7 +134,7 @@ struct PinnedBuf {
 // node on the way, so the walk can work out exactly which record it will need WALK_DEPTH steps from now and prefetch
 // that one line (instead of fanning out over 2^depth candidates).
 #ifndef MTG_WALK_DEPTH
-#define MTG_WALK_DEPTH 5
+#define MTG_WALK_DEPTH 4
 #endif
 static_assert(MTG_WALK_DEPTH >= 3 && MTG_WALK_DEPTH <= 5, "walk records carry 3, 4 or 5 levels");
 constexpr u32 WALK_DEPTH = MTG_WALK_DEPTH;
@@ -357,7 +357,7 @@ void finish_deferred_graph(mtg_ctx* ctx, u32 k);
 void build_graph_from_text(mtg_ctx* ctx, const char* text, u64 len, bool bcalm, u32 k, bool text_on_device);
 
 // Graphs below this node count prepare the sequential tail on the host (fewer round trips than launches).
-constexpr u64 TAIL_HOST_PREP_MAX_NODES = 1u << 17;
+constexpr u64 TAIL_HOST_PREP_MAX_NODES = 1u << 12;
 void stage_tail_inputs(mtg_ctx* ctx);  // host_tail.cpp
 
 // ---- search + matching (dijkstra.cu, match.cu) ----

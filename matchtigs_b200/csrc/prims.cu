@@ -94,54 +94,36 @@ __global__ void __launch_bounds__(SCAN_THREADS)
     }
 }
 
-// Small inputs: one 1024-thread CTA walks the array in chunks of 8192 carrying the running prefix -- one launch
-// instead of three, which is what matters when the whole step is launch-bound (E. coli-sized inputs).
+// Small inputs: one 1024-thread CTA, one launch instead of three -- what matters when the whole step is launch-bound
+// (E. coli-sized inputs).  Every thread owns a span of consecutive elements: it reduces the span, the 1024 partial results
+// are scanned across the block (two barriers in all), and the span is read again (from L1 / L2) to write its prefixes.
 constexpr int SCAN1_THREADS = 1024;
-constexpr int SCAN1_CHUNK = SCAN1_THREADS * SCAN_ITEMS;
-constexpr size_t SCAN1_MAX = 6 * SCAN1_CHUNK;
+constexpr size_t SCAN1_MAX = 64 * SCAN1_THREADS;
 
 template <class TIn, class TOut, class Op, bool INCLUSIVE>
 __global__ void __launch_bounds__(SCAN1_THREADS) scan_single_cta(const TIn* in, TOut* out, size_t n, TOut* d_total) {
     __shared__ TOut warp_tot[SCAN1_THREADS / 32];
-    __shared__ TOut carry_s;
     Op op;
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) carry_s = 0;
+    const size_t span = (n + SCAN1_THREADS - 1) / SCAN1_THREADS;
+    const size_t lo = min((size_t)threadIdx.x * span, n), hi = min(lo + span, n);
+    TOut acc = 0;
+    for (size_t i = lo; i < hi; i++) acc = op(acc, (TOut)in[i]);
+    const TOut inc = warp_inclusive(acc, op);
+    if (lane == 31) warp_tot[warp] = inc;
     __syncthreads();
-    for (size_t c0 = 0; c0 < n; c0 += SCAN1_CHUNK) {
-        const size_t base = c0 + (size_t)threadIdx.x * SCAN_ITEMS;
-        TOut v[SCAN_ITEMS];
-        TOut acc = 0;
-#pragma unroll
-        for (int i = 0; i < SCAN_ITEMS; i++) {
-            v[i] = (base + i < n) ? (TOut)in[base + i] : (TOut)0;
-            acc = op(acc, v[i]);
-        }
-        TOut inc = warp_inclusive(acc, op);
-        if (lane == 31) warp_tot[warp] = inc;
-        __syncthreads();
-        TOut prefix = carry_s, all = 0;
-        for (int w = 0; w < SCAN1_THREADS / 32; w++) {
-            TOut t = warp_tot[w];
-            if ((unsigned)w < warp) prefix = op(prefix, t);
-            all = op(all, t);
-        }
-        TOut exc = __shfl_up_sync(0xffffffffu, inc, 1);
-        if (lane == 0) exc = 0;
-        TOut run = op(prefix, exc);
-#pragma unroll
-        for (int i = 0; i < SCAN_ITEMS; i++) {
-            TOut next = op(run, v[i]);
-            if (base + i < n) {
-                out[base + i] = INCLUSIVE ? next : run;
-                if (d_total && base + i == n - 1) *d_total = next;
-            }
-            run = next;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) carry_s = op(carry_s, all);
-        __syncthreads();
+    TOut prefix = 0;
+    for (unsigned w = 0; w < warp; w++) prefix = op(prefix, warp_tot[w]);
+    TOut exc = __shfl_up_sync(0xffffffffu, inc, 1);
+    if (lane == 0) exc = 0;
+    TOut run = op(prefix, exc);
+    // in-place use (in == out) is safe: a thread only ever reads and writes its own span, reading each element before writing it
+    for (size_t i = lo; i < hi; i++) {
+        const TOut next = op(run, (TOut)in[i]);
+        out[i] = INCLUSIVE ? next : run;
+        run = next;
     }
+    if (d_total && hi == n && lo < n) *d_total = run;
 }
 
 template <class TIn, class TOut, class Op, bool INCLUSIVE>
