@@ -192,13 +192,19 @@ void walk_and_break(const WalkInput& w, TailOutput& out, TailScratch& scratch);
 // Host-side record builder (small graphs, the host-only entry, tests): same records as tail_prep.cu builds on the device.
 // `edge_end(e, &from, &to)` yields the end nodes of any original or dummy edge.
 template <class EdgeEnds>
-void build_walk_records(u32 n, u64 E0, u64 E, u32 k, const u32* out_deg, const u32* dummy_w, bool oldest_first, EdgeEnds&& edge_ends,
-                        TailScratch& scratch, WalkInput& w) {
+void build_walk_records(u32 n, u64 E0, u64 E, u32 k, const u32* out_deg, const u32* mirror, const u32* dummy_w, bool oldest_first,
+                        EdgeEnds&& edge_ends, TailScratch& scratch, WalkInput& w) {
     u32* handle = static_cast<u32*>(scratch.handle.ensure(std::max<size_t>(n, 1) * sizeof(u32)));
     u64 n_slots = 0;
-    for (u32 v = 0; v < n; v++) {
+    for (u32 v = 0; v < n; v++) {  // binode by binode: a node and its mirror own neighbouring slots (see tail_prep.cu)
+        const u32 m = mirror[v];
+        if (m < v) continue;
         handle[v] = walk_handle((u32)n_slots, out_deg[v]);
         n_slots += walk_cap(out_deg[v]);
+        if (m > v) {
+            handle[m] = walk_handle((u32)n_slots, out_deg[m]);
+            n_slots += walk_cap(out_deg[m]);
+        }
     }
     MTG_REQUIRE(n_slots < SLOT_MASK, MTG_ERR_UNSUPPORTED, "more than 2^30 edge slots");
     WalkRec* recs = static_cast<WalkRec*>(scratch.recs.ensure(std::max<u64>(n_slots, 1) * sizeof(WalkRec)));
@@ -325,7 +331,7 @@ void run_tail(const TailInput& in, TailOutput& out, TailScratch& scratch) {
     }
     WalkInput w{in.k, in.n_nodes, E0, E, 0, nullptr, nullptr, nullptr, nullptr, nullptr, in.from, nullptr, out.dummy_w.data(), max_matching_w < in.k,
                 false};
-    build_walk_records(n, E0, E, in.k, od, out.dummy_w.data(), in.oldest_first,
+    build_walk_records(n, E0, E, in.k, od, in.mirror, out.dummy_w.data(), in.oldest_first,
                        [&](u32 e, u32* f, u32* t) {
                            if (e < E0) {
                                *f = in.from[e], *t = in.to[e];
@@ -414,6 +420,24 @@ void walk_and_break(const WalkInput& in, TailOutput& out, TailScratch& scratch) 
     };
     std::vector<Frame> stack;
     const bool use_hints = in.hints && !getenv("MTG_TAIL_NOHINT");
+    const char* pf_env = getenv("MTG_WALK_PREFETCH");  // experiments: nta / t2 instead of t0
+    const int pf_kind = pf_env ? (pf_env[0] == 'n' ? 1 : pf_env[0] == '2' ? 2 : 0) : 0;
+    const bool nt_store = getenv("MTG_WALK_NTSTORE") != nullptr;  // experiment: queue appends with non-temporal stores
+    auto append = [&](HVec<u32>& v, u32 x) {
+#if defined(__x86_64__)
+        if (nt_store) {
+            __builtin_ia32_movnti(reinterpret_cast<int*>(v.p + v.n), (int)x);
+            v.n++;
+            return;
+        }
+#endif
+        v.p[v.n++] = x;
+    };
+    auto prefetch_rec = [&](const void* p) {
+        if (pf_kind == 1) __builtin_prefetch(p, 0, 0);
+        else if (pf_kind == 2) __builtin_prefetch(p, 0, 1);
+        else __builtin_prefetch(p, 0, 3);
+    };
     // Positions whose from-node may still own an unused out-edge, in cycle order from the head.  A position is only
     // recorded if its node had slots left when the walk passed (exhaustion is permanent), which skips about half of
     // the re-root probes.
@@ -456,18 +480,17 @@ void walk_and_break(const WalkInput& in, TailOutput& out, TailScratch& scratch) 
                 const u32 ms = r.mslot;
                 mark(s);
                 mark(ms & SLOT_MASK);
-                q_slot.push_back(s | (ms & ~SLOT_MASK));
-                q_from.push_back(from_h);
+                append(q_slot, s | (ms & ~SLOT_MASK));
+                append(q_from, from_h);
                 const u32 c = r.to;
                 const u32 nxt = first_unused(c);  // the next step is certain
-                cand.p[cand.n] = (u32)q_slot.size();
-                cand.n += more;
+                if (more) append(cand, (u32)q_slot.size());
                 if (use_hints && nxt != NONE32 && !(c & H_BIG)) {
                     if (have >= 2 && nxt == P[2]) {  // as expected
                         for (u32 M = 2; M < have; M++) P[M] = P[M + 1], Q[M] = Q[M + 1];
                         have--;
                     } else {
-                        __builtin_prefetch(&recs[nxt]);
+                        prefetch_rec(&recs[nxt]);
                         have = 1;
                     }
                     // extend the chain as far as this record's layout and the path allow
@@ -483,14 +506,14 @@ void walk_and_break(const WalkInput& in, TailOutput& out, TailScratch& scratch) 
                         u32 j = 2;
                         const u32 sl = peek(r.h[(four ? walk_level_four(L) : walk_level_two(L)) + idx], &j);
                         if (sl == NONE32) break;
-                        __builtin_prefetch(&recs[sl]);
+                        prefetch_rec(&recs[sl]);
                         if (WALK_DEPTH >= 5) __builtin_prefetch(reinterpret_cast<const char*>(&recs[sl]) + 64);
                         P[L] = sl, Q[L] = j, have = L;
                         open_end = j < 2;
                         idx = 2 * idx + j;
                     }
                 } else {
-                    if (nxt != NONE32) __builtin_prefetch(&recs[nxt]);
+                    if (nxt != NONE32) prefetch_rec(&recs[nxt]);
                     have = 1;
                 }
                 from_h = c;
@@ -764,6 +787,7 @@ void finish_walks(mtg_ctx* ctx) {
     // walk records on the device (includes the Eulerian check), DMA into page-locked staging
     TailRecords tr;
     tail_build_records(ctx, breaking.data(), n_break, &tr);
+    double t1b = now_ms();  // kernels launched (one round trip for the totals in between), DMA queued behind them
     const u64 P = tr.n_pairs;
     (void)N;
     // The walk works on a copy inside its huge-page arena (page-locking the arena itself loses the huge pages); copied in
@@ -809,9 +833,9 @@ void finish_walks(mtg_ctx* ctx) {
     ctx->walk_edges.swap(out.walk_edges);
     ctx->walk_limits.swap(out.walk_limits);
     ctx->h_dummy_w.swap(out.dummy_w);
-    ctx->tail_ms[0] = 0;
+    ctx->tail_ms[0] = t1b - t1;  // device-prepared path: record kernels up to the point where the DMA is queued
     ctx->tail_ms[1] = t1 - t0;
-    ctx->tail_ms[2] = t2 - t1;
+    ctx->tail_ms[2] = t2 - t1b;  // records arriving and being copied into the walk's arena
     ctx->tail_ms[3] = out.ms_walk;
     ctx->tail_ms[4] = out.ms_break;
     // device copies for the output kernels

@@ -103,18 +103,25 @@ __global__ void __launch_bounds__(TB)
     val[q] = e;
 }
 
-__global__ void __launch_bounds__(TB) slot_caps(const u32* __restrict__ deg, u64 N, u32* __restrict__ cap) {
+// Slots are handed out binode by binode: a node and its mirror sit next to each other, because taking an edge into node c
+// marks its mirror edge used, and that one leaves mirror(c) -- so both marks and the look at c's used bits hit the same
+// cache line of the bitset, whatever the node numbering (first-seen ids pair mirrors up, union-find ranks do not).
+// cap[v] = slots of v and of its mirror, counted at the smaller id of the two (0 at the larger).
+__global__ void __launch_bounds__(TB) slot_caps(const u32* __restrict__ deg, const u32* __restrict__ mirror, u64 N, u32* __restrict__ cap) {
     u64 v = (u64)blockIdx.x * TB + threadIdx.x;
-    if (v < N) cap[v] = walk_cap(deg[v]);
+    if (v >= N) return;
+    const u32 m = mirror[v];
+    cap[v] = m < v ? 0u : walk_cap(deg[v]) + (m > v ? walk_cap(deg[m]) : 0u);
 }
 
 // handles, headers of big nodes and the initial used-slot bitset (padding slots and header pairs are never handed out)
 __global__ void __launch_bounds__(TB)
-    node_handles(const u32* __restrict__ deg, const u32* __restrict__ base, u64 N, u32* __restrict__ handle, WalkRec* __restrict__ recs,
-                 u32* __restrict__ used0) {
+    node_handles(const u32* __restrict__ deg, const u32* __restrict__ mirror, const u32* __restrict__ base, u64 N, u32* __restrict__ handle,
+                 WalkRec* __restrict__ recs, u32* __restrict__ used0) {
     u64 v = (u64)blockIdx.x * TB + threadIdx.x;
     if (v >= N) return;
-    const u32 d = deg[v], b = base[v], h = walk_handle(b, d), cap = walk_cap(d);
+    const u32 m = mirror[v];
+    const u32 d = deg[v], b = m < v ? base[m] + walk_cap(deg[m]) : base[v], h = walk_handle(b, d), cap = walk_cap(d);
     handle[v] = h;
     const u32 first = walk_first_slot(h);
     if (d > 4) {
@@ -267,7 +274,7 @@ void tail_build_records(mtg_ctx* ctx, const u32* breaking_pairs, u64 n_break, Ta
     total.resize(3, s);
     total.zero(s);
     exclusive_sum_u32(ctx, deg.p, row_ptr.p, N, total.p + 0);
-    MTG_LAUNCH(ctx, slot_caps, grid_for(N, TB), TB, 0, deg.p, N, cap.p);
+    MTG_LAUNCH(ctx, slot_caps, grid_for(N, TB), TB, 0, deg.p, ctx->mirror.p, N, cap.p);
     exclusive_sum_u32(ctx, cap.p, base.p, N, total.p + 1);
     MTG_LAUNCH(ctx, eulerian_check, grid_for(N, TB), TB, 0, deg.p, ctx->mirror.p, N, total.p + 2);
     u32 h_total[3];
@@ -287,7 +294,7 @@ void tail_build_records(mtg_ctx* ctx, const u32* breaking_pairs, u64 n_break, Ta
     used0.resize(used_words32, s);
     used0.zero(s);
     from_handle.resize(E0, s);
-    MTG_LAUNCH(ctx, node_handles, grid_for(N, TB), TB, 0, deg.p, base.p, N, handle.p, recs.p, used0.p);
+    MTG_LAUNCH(ctx, node_handles, grid_for(N, TB), TB, 0, deg.p, ctx->mirror.p, base.p, N, handle.p, recs.p, used0.p);
     if (E) {
         MTG_LAUNCH(ctx, place_slots, grid_for(E, TB), TB, 0, which ? key_b.p : key_a.p, which ? val_b.p : val_a.p, E, E0, ctx->edge_to.p, pair_out.p,
                    pair_in.p, ctx->mirror.p, row_ptr.p, handle.p, recs.p, slot_edge.p, slot_of_edge.p, slot_to.p);

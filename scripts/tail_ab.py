@@ -17,8 +17,9 @@ ctx.build_graph_from_text(text, k, bcalm=bench.WORKLOADS[name]["bcalm"])
 ctx.dijkstra_candidates(bench.CAP, 0, 1)
 ctx.greedy_match()
 print(ctx.graph_info())
-for label, env in (("default", {}), ("nocopy", {"MTG_TAIL_NOCOPY": "1"}), ("nohint", {"MTG_TAIL_NOHINT": "1"}),
-                   ("nocopy+nohint", {"MTG_TAIL_NOCOPY": "1", "MTG_TAIL_NOHINT": "1"}), ("default", {})):
+for label, env in (("default", {}), ("prefetchnta", {"MTG_WALK_PREFETCH": "nta"}), ("prefetcht2", {"MTG_WALK_PREFETCH": "2"}),
+                   ("ntstore", {"MTG_WALK_NTSTORE": "1"}), ("nta+ntstore", {"MTG_WALK_PREFETCH": "nta", "MTG_WALK_NTSTORE": "1"}),
+                   ("nocopy", {"MTG_TAIL_NOCOPY": "1"}), ("nohint", {"MTG_TAIL_NOHINT": "1"}), ("default", {})):
     for k_, v in env.items():
         os.environ[k_] = v
     rows = []
