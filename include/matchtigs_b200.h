@@ -220,7 +220,8 @@ int mtg_broadcast_walks(mtg_ctx* ctx, int root);
 int mtg_compute_greedytigs_from_sequences(mtg_ctx* ctx, const char* seq_ascii, const uint64_t* offsets,
                                           uint64_t unitigs, uint32_t k, uint32_t cap);
 int mtg_get_search_stats(mtg_ctx* ctx, mtg_search_stats* stats);
-/* Diagnostics of the last run (either pointer may be NULL): host-tail phases in ms (degrees, eulerise, adjacency,
+/* Diagnostics of the last run (either pointer may be NULL): host-tail phases in ms (preparation = degree counting on the
+ * host-prepared path / record kernels on the device-prepared path, eulerise, walk records = built on the host / DMA + copy,
  * Euler walk, breaking) and device time of the last graph build in ms: build_ms[0] = H2D copy + record parsing
  * (mtg_build_graph_from_text only, else 0), build_ms[1] = graph construction proper (pack .. CSR). */
 int mtg_get_diagnostics(mtg_ctx* ctx, double tail_ms[5], double build_ms[2]);

@@ -269,7 +269,9 @@ class Context:
     def diagnostics(self) -> dict:
         ms, bms = (C.c_double * 5)(), (C.c_double * 2)()
         self._check(self._l.mtg_get_diagnostics(self._h, ms, bms))
-        names = ["degrees", "eulerise", "adjacency", "euler_walk", "breaking"]
+        # prepare: degree counting (host-prepared tail) / record kernels incl. one round trip (device-prepared tail);
+        # records: building them on the host / their DMA + copy into the walk's arena
+        names = ["prepare", "eulerise", "records", "euler_walk", "breaking"]
         return {"tail_ms": {n: round(float(v), 3) for n, v in zip(names, ms)},
                 "build_ms": {"parse": float(bms[0]), "graph": float(bms[1])}}
 
