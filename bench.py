@@ -335,7 +335,7 @@ def run_ours(args):
         return total_ms / steps, dj_ms / steps, mt_ms / steps, stats, launches, out
 
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("MTG_BENCH_NOSAMPLER"):  # (experiments only: does the polling disturb the run?)
         sampler.start()
     ms_res, dj_ms, match_ms, stats, launches, _ = timed(True, args.steps, args.warmup)
     if args.profile:

@@ -7,6 +7,9 @@
 #include <new>
 
 #include <algorithm>
+#include <map>
+#include <mutex>
+#include <vector>
 #include <memory>
 
 #include "mtg_internal.cuh"
@@ -58,6 +61,68 @@ static int* option_slot(mtg_ctx* ctx, const char* name) {
         if (!strcmp(name, t.name)) return &(ctx->opt.*(t.field));
     return nullptr;
 }
+
+// ---- device block cache (declared in mtg_internal.cuh) ----
+namespace mtg {
+namespace {
+struct BlockCache {
+    std::mutex m;
+    std::map<std::pair<cudaStream_t, size_t>, std::vector<void*>> free_blocks;  // (stream, class) -> blocks
+};
+BlockCache& block_cache() {
+    static BlockCache* c = new BlockCache();  // never destroyed: contexts may outlive static destruction order
+    return *c;
+}
+}  // namespace
+
+size_t block_class_bytes(size_t bytes) {
+    if (bytes <= 512) return 512;
+    int top = 63 - __builtin_clzll((unsigned long long)bytes);  // eight classes per power of two: at most 12.5 % over
+    const size_t step = size_t(1) << (top - 3);
+    return (bytes + step - 1) / step * step;
+}
+
+void* block_alloc(size_t class_bytes, cudaStream_t s) {
+    BlockCache& c = block_cache();
+    {
+        std::lock_guard<std::mutex> g(c.m);
+        auto it = c.free_blocks.find({s, class_bytes});
+        if (it != c.free_blocks.end() && !it->second.empty()) {
+            void* p = it->second.back();
+            it->second.pop_back();
+            return p;
+        }
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaMallocAsync(&p, class_bytes, s);
+    if (e == cudaErrorMemoryAllocation) {  // hand the cached blocks of this stream back and try once more
+        cudaGetLastError();
+        block_cache_trim(s);
+        e = cudaMallocAsync(&p, class_bytes, s);
+    }
+    if (e != cudaSuccess) throw Error{MTG_ERR_CUDA, std::string("cudaMallocAsync failed: ") + cudaGetErrorString(e)};
+    return p;
+}
+
+void block_free(void* p, size_t class_bytes, cudaStream_t s) {
+    BlockCache& c = block_cache();
+    std::lock_guard<std::mutex> g(c.m);
+    c.free_blocks[{s, class_bytes}].push_back(p);
+}
+
+void block_cache_trim(cudaStream_t s) {
+    BlockCache& c = block_cache();
+    std::lock_guard<std::mutex> g(c.m);
+    for (auto it = c.free_blocks.begin(); it != c.free_blocks.end();) {
+        if (it->first.first == s) {
+            for (void* p : it->second) cudaFreeAsync(p, s);
+            it = c.free_blocks.erase(it);
+        } else {
+            ++it;
+        }
+    }
+}
+}  // namespace mtg
 
 extern "C" {
 
@@ -138,6 +203,9 @@ void mtg_ctx_destroy(mtg_ctx* ctx) {
     ctx->parse_ws.text.release(s);
     for (auto& b : ctx->text_stage) b.release();
     for (auto& b : ctx->tail_stage) b.release();
+    ctx->gathered_rec.release(s);
+    ctx->gathered_meta.release(s);
+    mtg::block_cache_trim(s);  // everything this context's stream ever cached goes back to the driver
     if (s) {
         cudaStreamSynchronize(s);
         cudaStreamDestroy(s);

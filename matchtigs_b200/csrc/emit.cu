@@ -265,6 +265,8 @@ u64 emit(mtg_ctx* ctx, int mode, const char* prefix, size_t prefix_len, char* ou
     MTG_REQUIRE(walk_lo <= walk_hi, MTG_ERR_INVALID, "bad walk range");
     if (walk_lo != 0) prefix_len = 0;  // the header line belongs to the share that starts the text
     PinnedBuf& stage = ctx->text_stage[mode];
+    const double t_begin = wall_ms();
+    double t_scan = t_begin, t_alloc = t_begin, t_launched = t_begin;
     u64 h_bounds[3] = {0, 0, 0};
     DBuf<u32> seg_len, seg_tig;
     DBuf<u64> seg_off, bounds;
@@ -278,6 +280,7 @@ u64 emit(mtg_ctx* ctx, int mode, const char* prefix, size_t prefix_len, char* ou
         MTG_LAUNCH(ctx, range_bounds, 1, 1, 0, w.limits, seg_off.p, w.W, walk_lo, walk_hi, bounds.p);
         MTG_CUDA(cudaMemcpyAsync(h_bounds, bounds.p, sizeof(h_bounds), cudaMemcpyDeviceToHost, s));
         MTG_CUDA(cudaStreamSynchronize(s));
+        t_scan = wall_ms();
     }
     const u64 b0 = h_bounds[0], b1 = h_bounds[1], part = b1 - b0;
     if (where) {
@@ -296,10 +299,15 @@ u64 emit(mtg_ctx* ctx, int mode, const char* prefix, size_t prefix_len, char* ou
             const dim3 grid = grid_for(chunks, TB);
             DBuf<u32> first;
             first.resize(grid.x + 1, s);
+            t_alloc = wall_ms();
             MTG_LAUNCH(ctx, cta_first_segments, grid_for(w.W, TB), TB, 0, seg_off.p, seg_len.p, w.W, b0, b1, first.p);
             MTG_LAUNCH(ctx, fill_text, grid, TB, 0, w, mode, seg_off.p, seg_len.p, seg_tig.p, first.p, ctx->seq_words.p, b0, b1, d_out);
             MTG_CUDA(cudaMemcpyAsync(stage.p + prefix_len, d_out, part, cudaMemcpyDeviceToHost, s));
+            t_launched = wall_ms();
             MTG_CUDA(cudaStreamSynchronize(s));
+            if (trace_slow_calls() && wall_ms() - t_begin > 50.0)
+                fprintf(stderr, "[mtg trace] emit mode %d, %llu bytes: scan %.1f ms, allocations %.1f ms, launches %.1f ms, wait %.1f ms\n", mode,
+                        (unsigned long long)part, t_scan - t_begin, t_alloc - t_scan, t_launched - t_alloc, wall_ms() - t_launched);
         }
         if (out && part + prefix_len) memcpy(out, stage.p, part + prefix_len);
         if (view) *view = stage.p;

@@ -17,6 +17,11 @@
 #include <sys/mman.h>
 
 #include <algorithm>
+#include <omp.h>
+#if defined(__x86_64__)
+#include <x86intrin.h>
+#endif
+
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
@@ -255,7 +260,7 @@ void build_walk_records(u32 n, u64 E0, u64 E, u32 k, const u32* out_deg, const u
     };
     // The lookahead levels only pay off once the records outgrow the caches; below that (every graph the library prepares
     // on the host) building them would cost more than the walk itself.
-    w.hints = n_slots * sizeof(WalkRec) > (64u << 20);
+    w.hints = n_slots * sizeof(WalkRec) > (64u << 20) || getenv("MTG_TAIL_FORCEHINT");
     for (u32 level = 2; w.hints && level <= WALK_DEPTH; level++) {
 #pragma omp parallel for schedule(static) if (par)
         for (i64 sl = 0; sl < (i64)n_slots; sl++)
@@ -355,6 +360,16 @@ void walk_and_break(const WalkInput& in, TailOutput& out, TailScratch& scratch) 
     const WalkRec* const recs = in.recs;
     u64* const used = in.used;
     double t3 = now_ms();
+    struct TraceAtExit {
+        const u64 *steps, *reset, *have, *nohint, *big, *end;
+        ~TraceAtExit() {
+            if (trace_slow_calls() && *steps > 100000)
+                fprintf(stderr, "[mtg trace] walk: %llu steps, chain known to level 1/2/3/4/5 after a step: %llu/%llu/%llu/%llu/%llu, unexpected next slot %llu, "
+                        "big-node steps %llu, run ends %llu, without hints %llu\n", (unsigned long long)*steps, (unsigned long long)have[1],
+                        (unsigned long long)have[2], (unsigned long long)have[3], (unsigned long long)have[4], (unsigned long long)have[5],
+                        (unsigned long long)*reset, (unsigned long long)*big, (unsigned long long)*end, (unsigned long long)*nohint);
+        }
+    };
     // bits of the (up to 4) slots of a small node.  Loads and marks use the same aligned 64-bit words, so a load right
     // behind a mark of the same word is served by store forwarding (a byte store under a wider load is not).
     auto slot_bits = [&](u32 base) -> u32 {
@@ -422,7 +437,9 @@ void walk_and_break(const WalkInput& in, TailOutput& out, TailScratch& scratch) 
     const bool use_hints = in.hints && !getenv("MTG_TAIL_NOHINT");
     const char* pf_env = getenv("MTG_WALK_PREFETCH");  // experiments: nta / t2 instead of t0
     const int pf_kind = pf_env ? (pf_env[0] == 'n' ? 1 : pf_env[0] == '2' ? 2 : 0) : 0;
-    const bool nt_store = getenv("MTG_WALK_NTSTORE") != nullptr;  // experiment: queue appends with non-temporal stores
+    const bool nt_store = getenv("MTG_WALK_NTSTORE") != nullptr;
+    const bool fast_path = !(getenv("MTG_WALK_FAST") && getenv("MTG_WALK_FAST")[0] == '0');  // A/B switch
+    const int n_sources = getenv("MTG_WALK_SOURCES") ? atoi(getenv("MTG_WALK_SOURCES")) : 2;  // A/B switch: records used as hint sources
     auto append = [&](HVec<u32>& v, u32 x) {
 #if defined(__x86_64__)
         if (nt_store) {
@@ -452,6 +469,42 @@ void walk_and_break(const WalkInput& in, TailOutput& out, TailScratch& scratch) 
     auto weight_of = [&](u32 q) { return (q & SLOT_BREAK) ? in.k : in.dummy_w[in.slot_edge[q & SLOT_MASK] - E0]; };  // q is a dummy
     auto breaks = [&](u32 q) { return (q & SLOT_BREAK) != 0; };
     u64 steps_total = 0;
+    u64 ct_steps = 0, ct_reset = 0, ct_have[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ct_nohint = 0, ct_big = 0, ct_end = 0;  // MTG_TRACE statistics
+    const bool stats = trace_slow_calls();
+    // MTG_WALK_PROBE=1 (x86 only): every 64th step the latencies of the record load and of the two used-bit loads are timed
+    // with rdtscp / lfence and collected in power-of-two histograms -- says where a step waits (late prefetch, bitset miss).
+    const bool probe = getenv("MTG_WALK_PROBE") != nullptr;
+    u64 probe_hist[4][16] = {};
+    auto probe_load = [&](int which, const volatile void* addr, int bytes) {
+#if defined(__x86_64__)
+        unsigned aux;
+        _mm_lfence();
+        const u64 a = __rdtscp(&aux);
+        _mm_lfence();
+        if (bytes == 8) (void)*(const volatile u64*)addr;
+        else (void)*(const volatile u32*)addr;
+        _mm_lfence();
+        const u64 b = __rdtscp(&aux);
+        int bucket = 0;
+        for (u64 d = b - a; d > 1 && bucket < 15; d >>= 1) bucket++;
+        probe_hist[which][bucket]++;
+#endif
+    };
+    struct ProbeAtExit {
+        const bool* on;
+        u64 (*h)[16];
+        ~ProbeAtExit() {
+            if (!*on) return;
+            const char* names[4] = {"record load", "used bits of the target", "used bits of the far node", "used bits of the mirror slot"};
+            for (int w = 0; w < 4; w++) {
+                fprintf(stderr, "[mtg probe] %-26s cycles 2^k..:", names[w]);
+                for (int b = 4; b < 14; b++) fprintf(stderr, " %d:%llu", b, (unsigned long long)h[w][b]);
+                fprintf(stderr, "\n");
+            }
+        }
+    } probe_at_exit{&probe, probe_hist};
+    u64 probe_tick = 0;
+    TraceAtExit trace_at_exit{&ct_steps, &ct_reset, ct_have, &ct_nohint, &ct_big, &ct_end};
     for (u64 e0 = 0; e0 < E0 && steps_total < E / 2; e0++) {
         if (is_used(in.slot_of_edge[e0])) continue;
         // one closed walk per component, started at the lowest unused edge id (every node owns an original edge, so the
@@ -473,49 +526,106 @@ void walk_and_break(const WalkInput& in, TailOutput& out, TailScratch& scratch) 
             // the far end of the chain has to be extended (normally by one level: one look at the used bits, one prefetch).
             // The chain ends at a node that will be left through its third or fourth slot (the records follow two slots
             // per node behind their own target) and grows again once that node is the next one.
-            u32 P[WALK_DEPTH + 2], Q[WALK_DEPTH + 2];
+            u32 P[WALK_DEPTH + 4] = {}, Q[WALK_DEPTH + 4] = {};
             u32 have = 1;  // deepest level known
+            // Extends the chain from the hints of record `src`, whose own slot sits `b` steps ahead (b = 0: the record in
+            // hand, b = 1: the record of the next step).  Level L' of src's hints is level b + L' from here, indexed by the
+            // slot choices Q[b + 1] (at src.to; 0 .. 3) and Q[b + 2 ..] (0 .. 1) on the way.
+            auto extend = [&](const WalkRec& src, u32 b) {
+                const u32 cc = src.to;
+                if (cc & H_BIG) return;
+                if (have < b + 1) {  // (b >= 1 only) the slot behind src straight from src.to
+                    u32 j = 0;
+                    const u32 sl = peek(cc, &j);
+                    if (sl == NONE32) return;
+                    prefetch_rec(&recs[sl]);
+                    P[b + 1] = sl, Q[b + 1] = j, have = b + 1;
+                }
+                const bool four = (cc & H_FOUR) != 0;
+                const u32 last = b + (four ? WALK_DEPTH - 1 : WALK_DEPTH);  // deepest level this record knows
+                u32 idx = Q[b + 1];
+                bool open_end = true;
+                for (u32 M = b + 2; M <= have; M++) {
+                    open_end = Q[M] < 2;
+                    idx = 2 * idx + Q[M];
+                }
+                for (u32 L = have + 1; open_end && L <= last; L++) {
+                    u32 j = 2;
+                    const u32 sl = peek(src.h[(four ? walk_level_four(L - b) : walk_level_two(L - b)) + idx], &j);
+                    if (sl == NONE32) break;
+                    prefetch_rec(&recs[sl]);
+                    if (WALK_DEPTH >= 5) __builtin_prefetch(reinterpret_cast<const char*>(&recs[sl]) + 64);
+                    P[L] = sl, Q[L] = j, have = L;
+                    open_end = j < 2;
+                    idx = 2 * idx + j;
+                }
+            };
             while (s != NONE32) {
                 const WalkRec& r = recs[s];
+                const bool probing = probe && (++probe_tick & 63) == 0;
+                if (probing) probe_load(0, &r.to, 4);
                 const u32 ms = r.mslot;
+                if (probing) probe_load(3, &used[(ms & SLOT_MASK) >> 6], 8);
                 mark(s);
                 mark(ms & SLOT_MASK);
                 append(q_slot, s | (ms & ~SLOT_MASK));
                 append(q_from, from_h);
                 const u32 c = r.to;
+                if (probing) probe_load(1, &used[(c & H_BASE) >> 6], 8);
                 const u32 nxt = first_unused(c);  // the next step is certain
-                if (more) append(cand, (u32)q_slot.size());
+                // (branch-free: whether a node still has a second unused slot is a coin flip the predictor cannot learn)
+                cand.p[cand.n] = (u32)q_slot.size();
+                cand.n += more;
                 if (use_hints && nxt != NONE32 && !(c & H_BIG)) {
-                    if (have >= 2 && nxt == P[2]) {  // as expected
-                        for (u32 M = 2; M < have; M++) P[M] = P[M + 1], Q[M] = Q[M + 1];
+                    // Slot choice at `to` (Q[1]).  When the next slot is the expected one the choice comes from the chain, not
+                    // from `nxt`: the extension (hint -> used bits of the far node -> prefetch) then does not wait for the
+                    // used bits of `to`, it runs ahead under the predicted branch.
+                    if (__builtin_expect(have >= 2 && nxt == P[2], 1)) {  // as expected: everything moves one step closer
+#pragma GCC unroll 8
+                        for (u32 M = 1; M < WALK_DEPTH + 2; M++) P[M] = P[M + 1], Q[M] = Q[M + 1];  // fixed length: no loop branch
                         have--;
                     } else {
+                        P[1] = nxt, Q[1] = nxt - (c & H_BASE);
                         prefetch_rec(&recs[nxt]);
                         have = 1;
+                        ct_reset++;
                     }
-                    // extend the chain as far as this record's layout and the path allow
-                    const bool four = (c & H_FOUR) != 0;
-                    const u32 last = four ? WALK_DEPTH - 1 : WALK_DEPTH;  // deepest level this record knows
-                    u32 idx = nxt - (c & H_BASE);                       // slot choice at `to`: 0 .. 3
-                    bool open_end = true;
-                    for (u32 M = 2; M <= have; M++) {
-                        open_end = Q[M] < 2;
-                        idx = 2 * idx + Q[M];
+                    u32 open_bits = 0;
+#pragma GCC unroll 8
+                    for (u32 M = 2; M < WALK_DEPTH; M++) open_bits |= Q[M];
+                    if (__builtin_expect(fast_path && have == WALK_DEPTH - 1 && !(c & H_FOUR) && open_bits < 2, 1)) {
+                        // The steady state, written out: the chain lacks exactly its deepest level, the record in hand has the
+                        // two-slot layout and the path stays on first/second slots.  One hint, one look at the used bits, one
+                        // prefetch -- no loops whose trip counts the branch predictor would have to guess.
+                        u32 idx = 0;
+#pragma GCC unroll 8
+                        for (u32 M = 1; M < WALK_DEPTH; M++) idx = 2 * idx + Q[M];
+                        u32 j = 0;
+                        if (probing) probe_load(2, &used[(r.h[walk_level_two(WALK_DEPTH) + idx] & H_BASE) >> 6], 8);
+                        const u32 sl = peek(r.h[walk_level_two(WALK_DEPTH) + idx], &j);
+                        if (sl != NONE32) {
+                            prefetch_rec(&recs[sl]);
+                            P[WALK_DEPTH] = sl, Q[WALK_DEPTH] = j, have = WALK_DEPTH;
+                        }
+                    } else {
+                        extend(r, 0);
+                        // The record of the next step was asked for several steps ago and has normally arrived: its hints go on
+                        // where this record's stop (behind a node with three or four slots, which the record in hand only
+                        // follows when that node is its own target; one level short when its own target has four slots).
+                        if (n_sources >= 2 && (have < WALK_DEPTH || !fast_path)) extend(recs[nxt], 1);
+                        if (n_sources >= 3 && have >= 2) extend(recs[P[2]], 2);  // experiment: may not have arrived yet
                     }
-                    for (u32 L = have + 1; open_end && L <= last; L++) {
-                        u32 j = 2;
-                        const u32 sl = peek(r.h[(four ? walk_level_four(L) : walk_level_two(L)) + idx], &j);
-                        if (sl == NONE32) break;
-                        prefetch_rec(&recs[sl]);
-                        if (WALK_DEPTH >= 5) __builtin_prefetch(reinterpret_cast<const char*>(&recs[sl]) + 64);
-                        P[L] = sl, Q[L] = j, have = L;
-                        open_end = j < 2;
-                        idx = 2 * idx + j;
-                    }
+                    if (stats) ct_have[have & 7]++;
                 } else {
                     if (nxt != NONE32) prefetch_rec(&recs[nxt]);
                     have = 1;
+                    if (stats) {
+                        if (nxt == NONE32) ct_end++;
+                        else if (c & H_BIG) ct_big++;
+                        else ct_nohint++;
+                    }
                 }
+                if (stats) ct_steps++;
                 from_h = c;
                 s = nxt;
             }
@@ -604,37 +714,81 @@ void walk_and_break(const WalkInput& in, TailOutput& out, TailScratch& scratch) 
             }
             if (done) break;
         }
-        // one streaming copy: every element except the cutting dummies goes to the output, in order
+        // Every element except the cutting dummies goes to the output, in order.  The emission order is a short list of
+        // ranges of the queue; the host cores take equal shares of it: count, prefix, write.  A cut closes a piece only if
+        // the piece is not empty, so the limits are the distinct output offsets at which cuts happen.
+        struct Range {
+            u32 b, e;
+            u64 g0;  // position of b in emission order
+        };
+        std::vector<Range> ranges;
+        {
+            u64 g = 0;
+            auto add = [&](u32 b, u32 e) {
+                if (b < e) ranges.push_back({b, e, g}), g += e - b;
+            };
+            add(order[rot_s].b + rot_o, order[rot_s].e);
+            for (size_t si = rot_s + 1; si < order.size(); si++) add(order[si].b, order[si].e);
+            for (size_t si = 0; si < rot_s; si++) add(order[si].b, order[si].e);
+            add(order[rot_s].b, order[rot_s].b + rot_o);
+            MTG_REQUIRE(g == len, MTG_ERR_INTERNAL, "emission order lost elements");
+        }
         const size_t base = walk_slots.size();
         walk_slots.resize(base + len);
-        u32* wp = walk_slots.data() + base;
-        u32* piece = wp;  // start of the piece being collected
-        auto close = [&] {
-            if (wp == piece) return;
-            MTG_REQUIRE(!is_dummy(*piece), MTG_ERR_INTERNAL, "walk starts with a dummy edge");
-            out.walk_limits.push_back((u64)(wp - walk_slots.data()));
-            piece = wp;
-        };
-        bool first = true;
-        auto emit_range = [&](u32 b, u32 e) {
-            for (u32 j = b; j < e; j++) {
-                const u32 x = qe[j];
-                if (is_dummy(x) && (first || breaks(x))) {
-                    close();
-                    out.breaking++;
-                } else {
-                    *wp++ = x;
-                }
-                first = false;
+        u32* const wbase = walk_slots.data() + base;
+        const int n_parts = len > (1u << 16) ? std::max(1, std::min(omp_get_max_threads(), 16)) : 1;
+        std::vector<u64> part_out(n_parts + 1, 0), part_cuts(n_parts + 1, 0);
+        std::vector<std::vector<u64>> part_cut_at(n_parts);
+        // calls f(x, g) for every element of emission positions [g_lo, g_hi)
+        auto for_positions = [&](u64 g_lo, u64 g_hi, auto&& f) {
+            if (g_lo >= g_hi) return;
+            size_t ri = std::upper_bound(ranges.begin(), ranges.end(), g_lo, [](u64 v, const Range& r) { return v < r.g0; }) - ranges.begin() - 1;
+            u64 g = g_lo;
+            for (; ri < ranges.size() && g < g_hi; ri++) {
+                const Range& r = ranges[ri];
+                const u32 jb = r.b + (u32)(g - r.g0), je = (u32)std::min<u64>(r.e, r.b + (g_hi - r.g0));
+                for (u32 j = jb; j < je; j++, g++) f(qe[j], g);
             }
         };
-        emit_range(order[rot_s].b + rot_o, order[rot_s].e);
-        for (size_t si = rot_s + 1; si < order.size(); si++) emit_range(order[si].b, order[si].e);
-        for (size_t si = 0; si < rot_s; si++) emit_range(order[si].b, order[si].e);
-        emit_range(order[rot_s].b, order[rot_s].b + rot_o);
-        if (wp != piece && is_dummy(wp[-1])) wp--;  // a trailing (light) dummy is dropped
-        close();
-        walk_slots.resize((size_t)(wp - walk_slots.data()));
+        const auto cuts = [&](u32 x, u64 g) { return is_dummy(x) && (g == 0 || breaks(x)); };
+#pragma omp parallel for schedule(static, 1) num_threads(n_parts) if (n_parts > 1)
+        for (int t = 0; t < n_parts; t++) {
+            u64 n_out = 0, n_cut = 0;
+            for_positions(len * t / n_parts, len * (t + 1) / n_parts, [&](u32 x, u64 g) {
+                const bool c = cuts(x, g);
+                n_cut += c;
+                n_out += !c;
+            });
+            part_out[t + 1] = n_out;
+            part_cuts[t + 1] = n_cut;
+        }
+        for (int t = 0; t < n_parts; t++) part_out[t + 1] += part_out[t];
+#pragma omp parallel for schedule(static, 1) num_threads(n_parts) if (n_parts > 1)
+        for (int t = 0; t < n_parts; t++) {
+            u32* wp = wbase + part_out[t];
+            std::vector<u64>& cut_at = part_cut_at[t];
+            cut_at.reserve(part_cuts[t + 1]);
+            for_positions(len * t / n_parts, len * (t + 1) / n_parts, [&](u32 x, u64 g) {
+                if (cuts(x, g)) cut_at.push_back((u64)(wp - walk_slots.data()));
+                else *wp++ = x;
+            });
+        }
+        u64 piece = base;  // start of the piece being collected
+        auto close = [&](u64 at) {
+            if (at == piece) return;
+            MTG_REQUIRE(!is_dummy(walk_slots[piece]), MTG_ERR_INTERNAL, "walk starts with a dummy edge");
+            out.walk_limits.push_back(at);
+            piece = at;
+        };
+        for (int t = 0; t < n_parts; t++)
+            for (const u64 at : part_cut_at[t]) {
+                close(at);
+                out.breaking++;
+            }
+        u64 end = base + part_out[n_parts];
+        if (end != piece && is_dummy(walk_slots[end - 1])) end--;  // a trailing (light) dummy is dropped
+        close(end);
+        walk_slots.resize(end);
         out.cycles++;
         ms_break += now_ms() - tb;
     }
@@ -792,10 +946,11 @@ void finish_walks(mtg_ctx* ctx) {
     (void)N;
     // The walk works on a copy inside its huge-page arena (page-locking the arena itself loses the huge pages); copied in
     // cache-sized chunks by a few threads: one big memcpy would use non-temporal stores and leave everything cold.
-    auto warm_copy = [](void* dst, const void* src, size_t bytes) {
+    const int copy_threads = std::max(1, std::min(omp_get_max_threads(), 16));
+    auto warm_copy = [copy_threads](void* dst, const void* src, size_t bytes) {
         const size_t chunk = 256 << 10;
         const i64 n_chunks = (i64)((bytes + chunk - 1) / chunk);
-#pragma omp parallel for schedule(static) num_threads(8) if (bytes > (8u << 20))
+#pragma omp parallel for schedule(static) num_threads(copy_threads) if (bytes > (8u << 20))
         for (i64 c = 0; c < n_chunks; c++) {
             const size_t o = (size_t)c * chunk;
             memcpy((char*)dst + o, (const char*)src + o, std::min(chunk, bytes - o));
@@ -812,12 +967,16 @@ void finish_walks(mtg_ctx* ctx) {
     }
     for (u64 j = ctx->n_triples; j < P; j++) out.dummy_w[2 * j] = out.dummy_w[2 * j + 1] = ctx->k;
     const WalkRec* recs = tr.recs;
+    double ms_wait = 0, ms_copy = 0;
     if (!getenv("MTG_TAIL_NOCOPY")) {
         WalkRec* arena = static_cast<WalkRec*>(scratch.recs.ensure(std::max<u64>(tr.n_slots, 1) * sizeof(WalkRec)));
         for (int c = 0; c < TAIL_DMA_CHUNKS && tr.n_slots; c++) {  // piece c is copied while piece c+1 is still on the link
             const u64 lo = std::min<u64>((u64)c * tr.chunk_slots, tr.n_slots), hi = std::min<u64>(lo + tr.chunk_slots, tr.n_slots);
+            const double ta = now_ms();
             MTG_CUDA(cudaEventSynchronize(ctx->tail_events[c]));
+            const double tb = now_ms();
             if (hi > lo) warm_copy(arena + lo, tr.recs + lo, (hi - lo) * sizeof(WalkRec));
+            ms_wait += tb - ta, ms_copy += now_ms() - tb;
         }
         recs = arena;
     }
@@ -827,6 +986,9 @@ void finish_walks(mtg_ctx* ctx) {
     if (tr.used0) memcpy(used, tr.used0, used_bytes);
     else memset(used, 0, used_bytes);  // empty graph
     double t2 = now_ms();
+    if (trace_slow_calls() && t2 - t1b > 30.0)
+        fprintf(stderr, "[mtg trace] tail records, %llu slots: waiting for the DMA %.1f ms, copying %.1f ms, rest %.1f ms\n",
+                (unsigned long long)tr.n_slots, ms_wait, ms_copy, t2 - t1b - ms_wait - ms_copy);
     WalkInput w{ctx->k, N, E0, E0 + 2 * P, tr.n_slots, recs, used, nullptr, tr.slot_edge, tr.slot_of_edge, nullptr, tr.handle,
                 out.dummy_w.data(), max_matching_w < ctx->k, true};
     walk_and_break(w, out, scratch);

@@ -4,6 +4,8 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
+#include <ctime>
 #include <string>
 #include <vector>
 
@@ -23,6 +25,17 @@ constexpr u32 NONE32 = 0xFFFFFFFFu;
 constexpr int TAIL_DMA_CHUNKS = 8;  // pieces in which the walk records travel to the host
 constexpr int NUM_SMS_B200 = 148;
 
+// MTG_TRACE=1: calls that take unexpectedly long say on stderr where the time went (allocation, launch, wait).
+inline bool trace_slow_calls() {
+    static const bool on = [] { const char* e = getenv("MTG_TRACE"); return e && *e && *e != '0'; }();
+    return on;
+}
+inline double wall_ms() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
 struct Error {
     int code;
     std::string msg;
@@ -40,8 +53,18 @@ struct Error {
         if (!(cond)) throw ::mtg::Error{(code), (text)}; \
     } while (0)
 
-// Stream-ordered device array that only ever grows; memory comes from the device's default
-// pool (cudaMallocAsync) whose release threshold the context raises, so repeated runs reuse it.
+// Device blocks are handed out in size classes (eight per power of two) and a released block goes to a free list
+// of its stream and class instead of back to the driver (prims.cu); the next request of that class on that stream takes it.
+// A repeated job therefore allocates nothing after its first pass.  Going back to the driver's stream-ordered pool on
+// every release looked equivalent but is not: a 250 MB request that fits no cached block makes the pool rebuild a
+// contiguous range out of scattered physical pieces, which was measured at 0.2 - 1.2 s per occurrence inside chr1-size
+// jobs (MTG_TRACE=1).  Reuse on the same stream is ordered by the stream itself.  block_cache_trim returns everything.
+size_t block_class_bytes(size_t bytes);
+void* block_alloc(size_t class_bytes, cudaStream_t s);
+void block_free(void* p, size_t class_bytes, cudaStream_t s);
+void block_cache_trim(cudaStream_t s);
+
+// Stream-ordered device array that only ever grows (see the block cache above).
 // Owning and move-only: a buffer that goes out of scope -- normally or because an MTG_REQUIRE / MTG_CUDA threw --
 // returns its memory on the stream it was last sized on.  borrow() wraps memory owned by somebody else.
 template <class T>
@@ -49,17 +72,18 @@ struct DBuf {
     T* p = nullptr;
     size_t cap = 0;
     size_t n = 0;
+    size_t bytes = 0;  // size class of the block
     cudaStream_t st = nullptr;
     bool owned = true;
     DBuf() = default;
     DBuf(const DBuf&) = delete;
     DBuf& operator=(const DBuf&) = delete;
-    DBuf(DBuf&& o) noexcept : p(o.p), cap(o.cap), n(o.n), st(o.st), owned(o.owned) { o.p = nullptr, o.cap = o.n = 0; }
+    DBuf(DBuf&& o) noexcept : p(o.p), cap(o.cap), n(o.n), bytes(o.bytes), st(o.st), owned(o.owned) { o.p = nullptr, o.cap = o.n = o.bytes = 0; }
     DBuf& operator=(DBuf&& o) noexcept {
         if (this != &o) {
             release(st);
-            p = o.p, cap = o.cap, n = o.n, st = o.st, owned = o.owned;
-            o.p = nullptr, o.cap = o.n = 0;
+            p = o.p, cap = o.cap, n = o.n, bytes = o.bytes, st = o.st, owned = o.owned;
+            o.p = nullptr, o.cap = o.n = o.bytes = 0;
         }
         return *this;
     }
@@ -68,9 +92,9 @@ struct DBuf {
         st = s;
         if (count > cap || !owned) {
             release(s);
-            size_t want = count + count / 16 + 64;
-            MTG_CUDA(cudaMallocAsync((void**)&p, want * sizeof(T), s));
-            cap = want;
+            bytes = block_class_bytes((count + 16) * sizeof(T));
+            p = static_cast<T*>(block_alloc(bytes, s));
+            cap = bytes / sizeof(T);
         }
         n = count;
     }
@@ -85,9 +109,9 @@ struct DBuf {
         if (n) MTG_CUDA(cudaMemsetAsync(p, 0xFF, n * sizeof(T), s));
     }
     void release(cudaStream_t s) {
-        if (p && owned) cudaFreeAsync(p, s);
+        if (p && owned) block_free(p, bytes, s);
         p = nullptr;
-        cap = n = 0;
+        cap = n = bytes = 0;
         owned = true;
     }
     void upload(const T* h, size_t count, cudaStream_t s) {

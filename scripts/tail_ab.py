@@ -17,9 +17,12 @@ ctx.build_graph_from_text(text, k, bcalm=bench.WORKLOADS[name]["bcalm"])
 ctx.dijkstra_candidates(bench.CAP, 0, 1)
 ctx.greedy_match()
 print(ctx.graph_info())
-for label, env in (("default", {}), ("prefetchnta", {"MTG_WALK_PREFETCH": "nta"}), ("prefetcht2", {"MTG_WALK_PREFETCH": "2"}),
-                   ("ntstore", {"MTG_WALK_NTSTORE": "1"}), ("nta+ntstore", {"MTG_WALK_PREFETCH": "nta", "MTG_WALK_NTSTORE": "1"}),
-                   ("nocopy", {"MTG_TAIL_NOCOPY": "1"}), ("nohint", {"MTG_TAIL_NOHINT": "1"}), ("default", {})):
+ctx.finish_walks()
+print('THP:', open('/sys/kernel/mm/transparent_hugepage/enabled').read().strip(), '| defrag:', open('/sys/kernel/mm/transparent_hugepage/defrag').read().strip(), '|', [l.strip() for l in open('/proc/self/smaps_rollup') if 'AnonHuge' in l or l.startswith('Rss')])
+for label, env in (("default", {}), ("fast0", {"MTG_WALK_FAST": "0"}), ("sources1", {"MTG_WALK_SOURCES": "1"}),
+                   ("t0+store", {"MTG_WALK_PREFETCH": "t0", "MTG_WALK_NTSTORE": "0"}), ("t0", {"MTG_WALK_PREFETCH": "t0"}),
+                   ("store", {"MTG_WALK_NTSTORE": "0"}), ("default", {}), ("probe", {"MTG_WALK_PROBE": "1"}),
+                   ("probe+store+t0", {"MTG_WALK_PROBE": "1", "MTG_WALK_NTSTORE": "0", "MTG_WALK_PREFETCH": "t0"})):
     for k_, v in env.items():
         os.environ[k_] = v
     rows = []
