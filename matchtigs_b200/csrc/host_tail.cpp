@@ -354,64 +354,245 @@ void run_tail(const TailInput& in, TailOutput& out, TailScratch& scratch) {
     walk_and_break(w, out, scratch);
 }
 
+// ---- F: one run of the walk ----
+// Bit helpers over the used-slot bitset.  Loads and marks use the same aligned 64-bit words, so a load right behind a
+// mark of the same word is served by store forwarding (a byte store under a wider load is not).
+static inline u32 slot_bits_of(const u64* used, u32 base) {
+    const u32 sh = base & 63;
+    u64 x = used[base >> 6] >> sh;
+    if (__builtin_expect(sh > 60, 0)) x |= used[(base >> 6) + 1] << (64 - sh);  // four slots starting at bit 62
+    return (u32)x;
+}
+static inline u32 small_mask(u32 h) { return 3u + 12u * (h & H_FOUR); }  // two or four slots (H_FOUR == 1)
+static_assert(H_FOUR == 1u, "small_mask relies on the flag being bit 0");
+
+// What a run reads and appends to.  Kept apart from walk_and_break so that the hot loop is a small function whose state
+// the compiler keeps in registers (inside the big function most of it lived on the stack).
+struct RunIO {
+    const WalkRec* recs;
+    u64* used;
+    u32 *q_slot, *q_from;  // the cycle under construction (same length)
+    size_t q_n;
+    u32* cand;             // positions whose from-node had slots left when the walk passed
+    size_t cand_n;
+    int n_sources;         // records used as hint sources (A/B switch)
+    bool fast_path;        // A/B switch
+    // diagnostics (DIAG instantiation only)
+    u64 dg_steps, dg_reset, dg_have[8], dg_nohint, dg_big, dg_end;
+    u64 probe_hist[4][16];
+    u64 probe_tick;
+    bool probe;
+};
+
+// first unused slot of the node with handle h (NONE32: exhausted); *more = the node owns further unused slots behind it
+static inline u32 first_unused_of(const WalkRec* recs, const u64* used, u32 h, bool* more) {
+    const u32 base = h & H_BASE;
+    if (__builtin_expect(!(h & H_BIG), 1)) {
+        const u32 free_bits = ~slot_bits_of(used, base) & small_mask(h);
+        *more = (free_bits & (free_bits - 1)) != 0;
+        return free_bits ? base + (u32)__builtin_ctz(free_bits) : NONE32;
+    }
+    const u32 d = recs[base].to;
+    u32 first = NONE32;
+    *more = false;
+    for (u32 s = base + 2; s < base + 2 + d; s++)
+        if (!((used[s >> 6] >> (s & 63)) & 1u)) {
+            if (first == NONE32) first = s;
+            else {
+                *more = true;
+                break;
+            }
+        }
+    return first;
+}
+
+// Follows first-unused out-edges from slot `s` (leaving the node with handle from_h) until the walk is stuck.
+// HINTS: the records carry their lookahead levels.  PF: prefetch hint (0 = t0, 1 = nta, 2 = t2).  NTS: the queues are
+// appended with non-temporal stores.  DIAG: statistics and latency probes.
+template <bool HINTS, int PF, bool NTS, bool DIAG>
+__attribute__((noinline)) static void walk_run(RunIO& io, u32 s, u32 from_h) {
+    const WalkRec* const recs = io.recs;
+    u64* const used = io.used;
+    u32* const q_slot = io.q_slot;
+    u32* const q_from = io.q_from;
+    u32* const cand = io.cand;
+    size_t q_n = io.q_n, cand_n = io.cand_n;
+    const int n_sources = io.n_sources;
+    const bool fast_path = io.fast_path;
+    auto mark = [&](u32 x) { used[x >> 6] |= 1ull << (x & 63); };
+    auto prefetch_rec = [&](const void* p) {
+        if (PF == 1) __builtin_prefetch(p, 0, 0);
+        else if (PF == 2) __builtin_prefetch(p, 0, 1);
+        else __builtin_prefetch(p, 0, 3);
+    };
+    auto append = [&](u32* v, size_t at, u32 x) {
+#if defined(__x86_64__)
+        if (NTS) {
+            __builtin_ia32_movnti(reinterpret_cast<int*>(v + at), (int)x);
+            return;
+        }
+#endif
+        v[at] = x;
+    };
+    // the slot the node with handle h would hand out next, if the walk can tell without its records (small nodes)
+    auto peek = [&](u32 h, u32* j) -> u32 {
+        if (__builtin_expect((h & H_BIG) != 0, 0)) return NONE32;
+        const u32 base = h & H_BASE;
+        const u32 free_bits = ~slot_bits_of(used, base) & small_mask(h);
+        if (__builtin_expect(!free_bits, 0)) return NONE32;
+        *j = (u32)__builtin_ctz(free_bits);
+        return base + *j;
+    };
+    auto probe_load = [&](int which, const volatile void* addr, int bytes) {
+#if defined(__x86_64__)
+        unsigned aux;
+        _mm_lfence();
+        const u64 a = __rdtscp(&aux);
+        _mm_lfence();
+        if (bytes == 8) (void)*(const volatile u64*)addr;
+        else (void)*(const volatile u32*)addr;
+        _mm_lfence();
+        const u64 b = __rdtscp(&aux);
+        int bucket = 0;
+        for (u64 d = b - a; d > 1 && bucket < 15; d >>= 1) bucket++;
+        io.probe_hist[which][bucket]++;
+#endif
+    };
+    // What the walk expects 1 .. `have` steps from now -- P[L] = slot, Q[L] = its index inside its node -- carried from
+    // step to step: as long as the next slot is the one expected, everything moves one step closer and only the far end
+    // of the chain has to be extended (normally by one level: one look at the used bits, one prefetch).  The chain ends
+    // at a node that will be left through its third or fourth slot (the records follow two slots per node behind their
+    // own target) and grows again from the record of the next step, or once that node is the next one.
+    u32 P[WALK_DEPTH + 4] = {}, Q[WALK_DEPTH + 4] = {};
+    u32 have = 1;  // deepest level known
+    // Extends the chain from the hints of record `src`, whose own slot sits `b` steps ahead (b = 0: the record in hand,
+    // b = 1: the record of the next step).  Level L' of src's hints is level b + L' from here, indexed by the slot choices
+    // Q[b + 1] (at src.to; 0 .. 3) and Q[b + 2 ..] (0 .. 1) on the way.
+    auto extend = [&](const WalkRec& src, u32 b) {
+        const u32 cc = src.to;
+        if (cc & H_BIG) return;
+        if (have < b + 1) {  // (b >= 1 only) the slot behind src straight from src.to
+            u32 j = 0;
+            const u32 sl = peek(cc, &j);
+            if (sl == NONE32) return;
+            prefetch_rec(&recs[sl]);
+            P[b + 1] = sl, Q[b + 1] = j, have = b + 1;
+        }
+        const bool four = (cc & H_FOUR) != 0;
+        const u32 last = b + (four ? WALK_DEPTH - 1 : WALK_DEPTH);  // deepest level this record knows
+        u32 idx = Q[b + 1];
+        bool open_end = true;
+        for (u32 M = b + 2; M <= have; M++) {
+            open_end = Q[M] < 2;
+            idx = 2 * idx + Q[M];
+        }
+        for (u32 L = have + 1; open_end && L <= last; L++) {
+            u32 j = 2;
+            const u32 sl = peek(src.h[(four ? walk_level_four(L - b) : walk_level_two(L - b)) + idx], &j);
+            if (sl == NONE32) break;
+            prefetch_rec(&recs[sl]);
+            if (WALK_DEPTH >= 5) __builtin_prefetch(reinterpret_cast<const char*>(&recs[sl]) + 64);
+            P[L] = sl, Q[L] = j, have = L;
+            open_end = j < 2;
+            idx = 2 * idx + j;
+        }
+    };
+    while (s != NONE32) {
+        const WalkRec& r = recs[s];
+        const bool probing = DIAG && io.probe && (++io.probe_tick & 63) == 0;
+        if (probing) probe_load(0, &r.to, 4);
+        const u32 ms = r.mslot;
+        if (probing) probe_load(3, &used[(ms & SLOT_MASK) >> 6], 8);
+        mark(s);
+        mark(ms & SLOT_MASK);
+        append(q_slot, q_n, s | (ms & ~SLOT_MASK));
+        append(q_from, q_n, from_h);
+        q_n++;
+        const u32 c = r.to;
+        if (probing) probe_load(1, &used[(c & H_BASE) >> 6], 8);
+        bool more;
+        const u32 nxt = first_unused_of(recs, used, c, &more);  // the next step is certain
+        // (branch-free: whether a node still has a second unused slot is a coin flip the predictor cannot learn)
+        cand[cand_n] = (u32)q_n;
+        cand_n += more;
+        if (HINTS && nxt != NONE32 && !(c & H_BIG)) {
+            // Slot choice at `to` (Q[1]).  When the next slot is the expected one the choice comes from the chain, not from
+            // `nxt`: the extension (hint -> used bits of the far node -> prefetch) then does not wait for the used bits
+            // of `to`, it runs ahead under the predicted branch.
+            if (__builtin_expect(have >= 2 && nxt == P[2], 1)) {  // as expected: everything moves one step closer
+#pragma GCC unroll 8
+                for (u32 M = 1; M < WALK_DEPTH + 2; M++) P[M] = P[M + 1], Q[M] = Q[M + 1];  // fixed length: no loop branch
+                have--;
+            } else {
+                P[1] = nxt, Q[1] = nxt - (c & H_BASE);
+                prefetch_rec(&recs[nxt]);
+                have = 1;
+                if (DIAG) io.dg_reset++;
+            }
+            u32 open_bits = 0;
+#pragma GCC unroll 8
+            for (u32 M = 2; M < WALK_DEPTH; M++) open_bits |= Q[M];
+            if (__builtin_expect(fast_path && have == WALK_DEPTH - 1 && !(c & H_FOUR) && open_bits < 2, 1)) {
+                // The steady state, written out: the chain lacks exactly its deepest level, the record in hand has the
+                // two-slot layout and the path stays on first/second slots.  One hint, one look at the used bits, one
+                // prefetch -- no loops whose trip counts the branch predictor would have to guess.
+                u32 idx = 0;
+#pragma GCC unroll 8
+                for (u32 M = 1; M < WALK_DEPTH; M++) idx = 2 * idx + Q[M];
+                u32 j = 0;
+                const u32 hh = r.h[walk_level_two(WALK_DEPTH) + idx];
+                if (probing) probe_load(2, &used[(hh & H_BASE) >> 6], 8);
+                const u32 sl = peek(hh, &j);
+                if (sl != NONE32) {
+                    prefetch_rec(&recs[sl]);
+                    P[WALK_DEPTH] = sl, Q[WALK_DEPTH] = j, have = WALK_DEPTH;
+                }
+            } else {
+                extend(r, 0);
+                // The record of the next step was asked for several steps ago and has normally arrived: its hints go on where
+                // this record's stop (behind a node with three or four slots, which the record in hand only follows when
+                // that node is its own target; one level short when its own target has four slots).
+                if (n_sources >= 2 && (have < WALK_DEPTH || !fast_path)) extend(recs[nxt], 1);
+                if (n_sources >= 3 && have >= 2) extend(recs[P[2]], 2);  // experiment: may not have arrived yet
+            }
+            if (DIAG) io.dg_have[have & 7]++;
+        } else {
+            if (nxt != NONE32) prefetch_rec(&recs[nxt]);
+            have = 1;
+            if (DIAG) {
+                if (nxt == NONE32) io.dg_end++;
+                else if (c & H_BIG) io.dg_big++;
+                else io.dg_nohint++;
+            }
+        }
+        if (DIAG) io.dg_steps++;
+        from_h = c;
+        s = nxt;
+    }
+    io.q_n = q_n;
+    io.cand_n = cand_n;
+}
+
+using WalkRunFn = void (*)(RunIO&, u32, u32);
+template <bool HINTS, int PF>
+static WalkRunFn pick_walk_run(bool nts, bool diag) {
+    if (diag) return nts ? walk_run<HINTS, PF, true, true> : walk_run<HINTS, PF, false, true>;
+    return nts ? walk_run<HINTS, PF, true, false> : walk_run<HINTS, PF, false, false>;
+}
+static WalkRunFn pick_walk_run(bool hints, int pf, bool nts, bool diag) {
+    if (!hints) return pick_walk_run<false, 0>(nts, diag);
+    if (pf == 1) return pick_walk_run<true, 1>(nts, diag);
+    if (pf == 2) return pick_walk_run<true, 2>(nts, diag);
+    return pick_walk_run<true, 0>(nts, diag);
+}
+
 // ---- F + G ----
 void walk_and_break(const WalkInput& in, TailOutput& out, TailScratch& scratch) {
     const u64 E0 = in.E0, E = in.E;
     const WalkRec* const recs = in.recs;
     u64* const used = in.used;
     double t3 = now_ms();
-    struct TraceAtExit {
-        const u64 *steps, *reset, *have, *nohint, *big, *end;
-        ~TraceAtExit() {
-            if (trace_slow_calls() && *steps > 100000)
-                fprintf(stderr, "[mtg trace] walk: %llu steps, chain known to level 1/2/3/4/5 after a step: %llu/%llu/%llu/%llu/%llu, unexpected next slot %llu, "
-                        "big-node steps %llu, run ends %llu, without hints %llu\n", (unsigned long long)*steps, (unsigned long long)have[1],
-                        (unsigned long long)have[2], (unsigned long long)have[3], (unsigned long long)have[4], (unsigned long long)have[5],
-                        (unsigned long long)*reset, (unsigned long long)*big, (unsigned long long)*end, (unsigned long long)*nohint);
-        }
-    };
-    // bits of the (up to 4) slots of a small node.  Loads and marks use the same aligned 64-bit words, so a load right
-    // behind a mark of the same word is served by store forwarding (a byte store under a wider load is not).
-    auto slot_bits = [&](u32 base) -> u32 {
-        const u32 sh = base & 63;
-        u64 x = used[base >> 6] >> sh;
-        if (sh > 60) x |= used[(base >> 6) + 1] << (64 - sh);  // four slots starting at bit 62
-        return (u32)x;
-    };
-    auto mark = [&](u32 s) { used[s >> 6] |= 1ull << (s & 63); };
-    auto is_used = [&](u32 s) { return (u32)(used[s >> 6] >> (s & 63)) & 1u; };
-    bool more = false;  // set by first_unused: does the node own further unused slots behind the returned one?
-    // first unused slot of the node with handle h (NONE32: exhausted)
-    auto first_unused = [&](u32 h) -> u32 {
-        const u32 base = h & H_BASE;
-        if (!(h & H_BIG)) {
-            const u32 mask = (h & H_FOUR) ? 15u : 3u;
-            const u32 free_bits = ~slot_bits(base) & mask;
-            more = (free_bits & (free_bits - 1)) != 0;
-            return free_bits ? base + (u32)__builtin_ctz(free_bits) : NONE32;
-        }
-        const u32 d = recs[base].to;
-        u32 first = NONE32;
-        more = false;
-        for (u32 s = base + 2; s < base + 2 + d; s++)
-            if (!is_used(s)) {
-                if (first == NONE32) first = s;
-                else {
-                    more = true;
-                    break;
-                }
-            }
-        return first;
-    };
-    // the slot the node with handle h would hand out next, if the walk can tell without its records (small nodes)
-    auto peek = [&](u32 h, u32* j) -> u32 {
-        if (h & H_BIG) return NONE32;
-        const u32 base = h & H_BASE, mask = (h & H_FOUR) ? 15u : 3u;
-        const u32 free_bits = ~slot_bits(base) & mask;
-        if (!free_bits) return NONE32;
-        *j = (u32)__builtin_ctz(free_bits);
-        return base + *j;
-    };
+    auto is_used = [&](u32 x) { return (u32)(used[x >> 6] >> (x & 63)) & 1u; };
     // The cycle under construction: element i = (q_slot[i] = slot | flags, q_from[i] = handle of the node it leaves).
     // Every extension appends a contiguous run (creation order == the order in which positions are scanned for leftover
     // out-edges).  A run created while position i was the head sits, in cycle order, immediately before element i
@@ -434,27 +615,42 @@ void walk_and_break(const WalkInput& in, TailOutput& out, TailScratch& scratch) 
         size_t ci, ce;   // children of this block: children[ci, ce)
     };
     std::vector<Frame> stack;
+    // Queue appends use non-temporal stores: the queues are not read again during the walk, and kept out of L2 they leave
+    // it to the used-slot bitset (bench box, chr1: 44 -> 42 ns per step).  MTG_WALK_NTSTORE=0, MTG_WALK_PREFETCH=nta|2,
+    // MTG_WALK_FAST=0, MTG_WALK_SOURCES=n and MTG_TAIL_NOHINT=1 are A/B switches; MTG_TRACE / MTG_WALK_PROBE select the
+    // instantiation with statistics and latency probes.
     const bool use_hints = in.hints && !getenv("MTG_TAIL_NOHINT");
-    const char* pf_env = getenv("MTG_WALK_PREFETCH");  // experiments: nta / t2 instead of t0
+    const char* pf_env = getenv("MTG_WALK_PREFETCH");
     const int pf_kind = pf_env ? (pf_env[0] == 'n' ? 1 : pf_env[0] == '2' ? 2 : 0) : 0;
-    const bool nt_store = getenv("MTG_WALK_NTSTORE") != nullptr;
-    const bool fast_path = !(getenv("MTG_WALK_FAST") && getenv("MTG_WALK_FAST")[0] == '0');  // A/B switch
-    const int n_sources = getenv("MTG_WALK_SOURCES") ? atoi(getenv("MTG_WALK_SOURCES")) : 2;  // A/B switch: records used as hint sources
-    auto append = [&](HVec<u32>& v, u32 x) {
-#if defined(__x86_64__)
-        if (nt_store) {
-            __builtin_ia32_movnti(reinterpret_cast<int*>(v.p + v.n), (int)x);
-            v.n++;
-            return;
+    const char* nts_env = getenv("MTG_WALK_NTSTORE");
+    const bool nt_store = !(nts_env && nts_env[0] == '0');
+    const bool diag = trace_slow_calls() || getenv("MTG_WALK_PROBE") != nullptr;
+    const WalkRunFn run = pick_walk_run(use_hints, pf_kind, nt_store, diag);
+    RunIO io{};
+    io.recs = recs;
+    io.used = used;
+    io.n_sources = getenv("MTG_WALK_SOURCES") ? atoi(getenv("MTG_WALK_SOURCES")) : 2;
+    io.fast_path = !(getenv("MTG_WALK_FAST") && getenv("MTG_WALK_FAST")[0] == '0');
+    io.probe = getenv("MTG_WALK_PROBE") != nullptr;
+    struct DiagAtExit {
+        const RunIO* io;
+        bool on;
+        ~DiagAtExit() {
+            if (!on || io->dg_steps < 100000) return;
+            const u64* h = io->dg_have;
+            fprintf(stderr, "[mtg trace] walk: %llu steps, chain known to level 1/2/3/4/5 after a step: %llu/%llu/%llu/%llu/%llu, unexpected "
+                    "next slot %llu, big-node steps %llu, run ends %llu, without hints %llu\n", (unsigned long long)io->dg_steps,
+                    (unsigned long long)h[1], (unsigned long long)h[2], (unsigned long long)h[3], (unsigned long long)h[4], (unsigned long long)h[5],
+                    (unsigned long long)io->dg_reset, (unsigned long long)io->dg_big, (unsigned long long)io->dg_end, (unsigned long long)io->dg_nohint);
+            if (!io->probe) return;
+            const char* names[4] = {"record load", "used bits of the target", "used bits of the far node", "used bits of the mirror slot"};
+            for (int w = 0; w < 4; w++) {
+                fprintf(stderr, "[mtg probe] %-28s cycles 2^k..:", names[w]);
+                for (int b = 4; b < 14; b++) fprintf(stderr, " %d:%llu", b, (unsigned long long)io->probe_hist[w][b]);
+                fprintf(stderr, "\n");
+            }
         }
-#endif
-        v.p[v.n++] = x;
-    };
-    auto prefetch_rec = [&](const void* p) {
-        if (pf_kind == 1) __builtin_prefetch(p, 0, 0);
-        else if (pf_kind == 2) __builtin_prefetch(p, 0, 1);
-        else __builtin_prefetch(p, 0, 3);
-    };
+    } diag_at_exit{&io, diag};
     // Positions whose from-node may still own an unused out-edge, in cycle order from the head.  A position is only
     // recorded if its node had slots left when the walk passed (exhaustion is permanent), which skips about half of
     // the re-root probes.
@@ -469,42 +665,6 @@ void walk_and_break(const WalkInput& in, TailOutput& out, TailScratch& scratch) 
     auto weight_of = [&](u32 q) { return (q & SLOT_BREAK) ? in.k : in.dummy_w[in.slot_edge[q & SLOT_MASK] - E0]; };  // q is a dummy
     auto breaks = [&](u32 q) { return (q & SLOT_BREAK) != 0; };
     u64 steps_total = 0;
-    u64 ct_steps = 0, ct_reset = 0, ct_have[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ct_nohint = 0, ct_big = 0, ct_end = 0;  // MTG_TRACE statistics
-    const bool stats = trace_slow_calls();
-    // MTG_WALK_PROBE=1 (x86 only): every 64th step the latencies of the record load and of the two used-bit loads are timed
-    // with rdtscp / lfence and collected in power-of-two histograms -- says where a step waits (late prefetch, bitset miss).
-    const bool probe = getenv("MTG_WALK_PROBE") != nullptr;
-    u64 probe_hist[4][16] = {};
-    auto probe_load = [&](int which, const volatile void* addr, int bytes) {
-#if defined(__x86_64__)
-        unsigned aux;
-        _mm_lfence();
-        const u64 a = __rdtscp(&aux);
-        _mm_lfence();
-        if (bytes == 8) (void)*(const volatile u64*)addr;
-        else (void)*(const volatile u32*)addr;
-        _mm_lfence();
-        const u64 b = __rdtscp(&aux);
-        int bucket = 0;
-        for (u64 d = b - a; d > 1 && bucket < 15; d >>= 1) bucket++;
-        probe_hist[which][bucket]++;
-#endif
-    };
-    struct ProbeAtExit {
-        const bool* on;
-        u64 (*h)[16];
-        ~ProbeAtExit() {
-            if (!*on) return;
-            const char* names[4] = {"record load", "used bits of the target", "used bits of the far node", "used bits of the mirror slot"};
-            for (int w = 0; w < 4; w++) {
-                fprintf(stderr, "[mtg probe] %-26s cycles 2^k..:", names[w]);
-                for (int b = 4; b < 14; b++) fprintf(stderr, " %d:%llu", b, (unsigned long long)h[w][b]);
-                fprintf(stderr, "\n");
-            }
-        }
-    } probe_at_exit{&probe, probe_hist};
-    u64 probe_tick = 0;
-    TraceAtExit trace_at_exit{&ct_steps, &ct_reset, ct_have, &ct_nohint, &ct_big, &ct_end};
     for (u64 e0 = 0; e0 < E0 && steps_total < E / 2; e0++) {
         if (is_used(in.slot_of_edge[e0])) continue;
         // one closed walk per component, started at the lowest unused edge id (every node owns an original edge, so the
@@ -520,122 +680,19 @@ void walk_and_break(const WalkInput& in, TailOutput& out, TailScratch& scratch) 
         bool rooted = false;
         for (;;) {
             cand.push_back((u32)q_slot.size());  // a walk start is always probed again
-            u32 s = start_slot, from_h = start_from;
-            // What the walk expects 2 .. `have` steps from now -- P[L] = slot, Q[L] = its index inside its node -- carried
-            // from step to step: as long as the next slot is the one expected, everything moves one step closer and only
-            // the far end of the chain has to be extended (normally by one level: one look at the used bits, one prefetch).
-            // The chain ends at a node that will be left through its third or fourth slot (the records follow two slots
-            // per node behind their own target) and grows again once that node is the next one.
-            u32 P[WALK_DEPTH + 4] = {}, Q[WALK_DEPTH + 4] = {};
-            u32 have = 1;  // deepest level known
-            // Extends the chain from the hints of record `src`, whose own slot sits `b` steps ahead (b = 0: the record in
-            // hand, b = 1: the record of the next step).  Level L' of src's hints is level b + L' from here, indexed by the
-            // slot choices Q[b + 1] (at src.to; 0 .. 3) and Q[b + 2 ..] (0 .. 1) on the way.
-            auto extend = [&](const WalkRec& src, u32 b) {
-                const u32 cc = src.to;
-                if (cc & H_BIG) return;
-                if (have < b + 1) {  // (b >= 1 only) the slot behind src straight from src.to
-                    u32 j = 0;
-                    const u32 sl = peek(cc, &j);
-                    if (sl == NONE32) return;
-                    prefetch_rec(&recs[sl]);
-                    P[b + 1] = sl, Q[b + 1] = j, have = b + 1;
-                }
-                const bool four = (cc & H_FOUR) != 0;
-                const u32 last = b + (four ? WALK_DEPTH - 1 : WALK_DEPTH);  // deepest level this record knows
-                u32 idx = Q[b + 1];
-                bool open_end = true;
-                for (u32 M = b + 2; M <= have; M++) {
-                    open_end = Q[M] < 2;
-                    idx = 2 * idx + Q[M];
-                }
-                for (u32 L = have + 1; open_end && L <= last; L++) {
-                    u32 j = 2;
-                    const u32 sl = peek(src.h[(four ? walk_level_four(L - b) : walk_level_two(L - b)) + idx], &j);
-                    if (sl == NONE32) break;
-                    prefetch_rec(&recs[sl]);
-                    if (WALK_DEPTH >= 5) __builtin_prefetch(reinterpret_cast<const char*>(&recs[sl]) + 64);
-                    P[L] = sl, Q[L] = j, have = L;
-                    open_end = j < 2;
-                    idx = 2 * idx + j;
-                }
-            };
-            while (s != NONE32) {
-                const WalkRec& r = recs[s];
-                const bool probing = probe && (++probe_tick & 63) == 0;
-                if (probing) probe_load(0, &r.to, 4);
-                const u32 ms = r.mslot;
-                if (probing) probe_load(3, &used[(ms & SLOT_MASK) >> 6], 8);
-                mark(s);
-                mark(ms & SLOT_MASK);
-                append(q_slot, s | (ms & ~SLOT_MASK));
-                append(q_from, from_h);
-                const u32 c = r.to;
-                if (probing) probe_load(1, &used[(c & H_BASE) >> 6], 8);
-                const u32 nxt = first_unused(c);  // the next step is certain
-                // (branch-free: whether a node still has a second unused slot is a coin flip the predictor cannot learn)
-                cand.p[cand.n] = (u32)q_slot.size();
-                cand.n += more;
-                if (use_hints && nxt != NONE32 && !(c & H_BIG)) {
-                    // Slot choice at `to` (Q[1]).  When the next slot is the expected one the choice comes from the chain, not
-                    // from `nxt`: the extension (hint -> used bits of the far node -> prefetch) then does not wait for the
-                    // used bits of `to`, it runs ahead under the predicted branch.
-                    if (__builtin_expect(have >= 2 && nxt == P[2], 1)) {  // as expected: everything moves one step closer
-#pragma GCC unroll 8
-                        for (u32 M = 1; M < WALK_DEPTH + 2; M++) P[M] = P[M + 1], Q[M] = Q[M + 1];  // fixed length: no loop branch
-                        have--;
-                    } else {
-                        P[1] = nxt, Q[1] = nxt - (c & H_BASE);
-                        prefetch_rec(&recs[nxt]);
-                        have = 1;
-                        ct_reset++;
-                    }
-                    u32 open_bits = 0;
-#pragma GCC unroll 8
-                    for (u32 M = 2; M < WALK_DEPTH; M++) open_bits |= Q[M];
-                    if (__builtin_expect(fast_path && have == WALK_DEPTH - 1 && !(c & H_FOUR) && open_bits < 2, 1)) {
-                        // The steady state, written out: the chain lacks exactly its deepest level, the record in hand has the
-                        // two-slot layout and the path stays on first/second slots.  One hint, one look at the used bits, one
-                        // prefetch -- no loops whose trip counts the branch predictor would have to guess.
-                        u32 idx = 0;
-#pragma GCC unroll 8
-                        for (u32 M = 1; M < WALK_DEPTH; M++) idx = 2 * idx + Q[M];
-                        u32 j = 0;
-                        if (probing) probe_load(2, &used[(r.h[walk_level_two(WALK_DEPTH) + idx] & H_BASE) >> 6], 8);
-                        const u32 sl = peek(r.h[walk_level_two(WALK_DEPTH) + idx], &j);
-                        if (sl != NONE32) {
-                            prefetch_rec(&recs[sl]);
-                            P[WALK_DEPTH] = sl, Q[WALK_DEPTH] = j, have = WALK_DEPTH;
-                        }
-                    } else {
-                        extend(r, 0);
-                        // The record of the next step was asked for several steps ago and has normally arrived: its hints go on
-                        // where this record's stop (behind a node with three or four slots, which the record in hand only
-                        // follows when that node is its own target; one level short when its own target has four slots).
-                        if (n_sources >= 2 && (have < WALK_DEPTH || !fast_path)) extend(recs[nxt], 1);
-                        if (n_sources >= 3 && have >= 2) extend(recs[P[2]], 2);  // experiment: may not have arrived yet
-                    }
-                    if (stats) ct_have[have & 7]++;
-                } else {
-                    if (nxt != NONE32) prefetch_rec(&recs[nxt]);
-                    have = 1;
-                    if (stats) {
-                        if (nxt == NONE32) ct_end++;
-                        else if (c & H_BIG) ct_big++;
-                        else ct_nohint++;
-                    }
-                }
-                if (stats) ct_steps++;
-                from_h = c;
-                s = nxt;
-            }
+            io.q_slot = q_slot.p, io.q_from = q_from.p, io.q_n = q_slot.n;
+            io.cand = cand.p, io.cand_n = cand.n;
+            run(io, start_slot, start_from);
+            q_slot.n = q_from.n = io.q_n;
+            cand.n = io.cand_n;
             if (rooted) children.back().end = (u32)q_slot.size();  // the run just appended belongs to the head's block
             else n0 = (u32)q_slot.size();
             // re-root at the first cycle position (from the head) whose from-node still has an unused out-edge
             bool found = false;
             while (cf < cand.size()) {
                 const u32 qf = cand[cf];
-                const u32 a = first_unused(q_from[qf]);
+                bool more_unused;
+                const u32 a = first_unused_of(recs, used, q_from[qf], &more_unused);
                 if (a != NONE32) {
                     head_idx = qf;  // rotate_left(position)
                     rooted = true;

@@ -19,10 +19,8 @@ ctx.greedy_match()
 print(ctx.graph_info())
 ctx.finish_walks()
 print('THP:', open('/sys/kernel/mm/transparent_hugepage/enabled').read().strip(), '| defrag:', open('/sys/kernel/mm/transparent_hugepage/defrag').read().strip(), '|', [l.strip() for l in open('/proc/self/smaps_rollup') if 'AnonHuge' in l or l.startswith('Rss')])
-for label, env in (("default", {}), ("fast0", {"MTG_WALK_FAST": "0"}), ("sources1", {"MTG_WALK_SOURCES": "1"}),
-                   ("t0+store", {"MTG_WALK_PREFETCH": "t0", "MTG_WALK_NTSTORE": "0"}), ("t0", {"MTG_WALK_PREFETCH": "t0"}),
-                   ("store", {"MTG_WALK_NTSTORE": "0"}), ("default", {}), ("probe", {"MTG_WALK_PROBE": "1"}),
-                   ("probe+store+t0", {"MTG_WALK_PROBE": "1", "MTG_WALK_NTSTORE": "0", "MTG_WALK_PREFETCH": "t0"})):
+for label, env in (("default", {}), ("fast0", {"MTG_WALK_FAST": "0"}), ("store", {"MTG_WALK_NTSTORE": "0"}),
+                   ("nta", {"MTG_WALK_PREFETCH": "nta"}), ("default", {}), ("probe", {"MTG_WALK_PROBE": "1"})):
     for k_, v in env.items():
         os.environ[k_] = v
     rows = []
