@@ -34,6 +34,11 @@ ROOT = Path(__file__).resolve().parent
 if str(ROOT) not in sys.path:
     sys.path.insert(0, str(ROOT))
 
+# torchrun exports OMP_NUM_THREADS=1 for every rank; the host-side helpers of this bench (the synthetic unitig builder on rank 0)
+# are OpenMP code that should use the box's cores.  (The library itself sizes its host threads from the CPU affinity mask.)
+if os.environ.get("OMP_NUM_THREADS") == "1":
+    del os.environ["OMP_NUM_THREADS"]
+
 import numpy as np  # noqa: E402
 
 WORKLOADS = {

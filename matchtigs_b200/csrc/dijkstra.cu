@@ -120,10 +120,15 @@ constexpr int T0_THREADS = 128;
 #define MTG_T0_ENTRIES 48
 #endif
 constexpr int T0_ENTRIES = MTG_T0_ENTRIES;
+constexpr int T0_HASH = 64;           // hash slots per thread (power of two, > T0_ENTRIES)
+static_assert(T0_ENTRIES < T0_HASH && T0_ENTRIES < 255, "label indices are bytes and the table must keep free slots");
+__device__ __forceinline__ u32 t0_hash(u32 v) { return (v * 0x9E3779B1u) >> 26; }
 
 __global__ void __launch_bounds__(T0_THREADS) dijkstra_thread_kernel(SearchArgs a) {
-    __shared__ u32 s_key[T0_ENTRIES][T0_THREADS];
-    __shared__ u8 s_dist[T0_ENTRIES][T0_THREADS];
+    __shared__ u32 s_key[T0_ENTRIES][T0_THREADS];   // labelled node ids, in insertion order (labels never move)
+    __shared__ u8 s_dist[T0_ENTRIES][T0_THREADS];   // tentative distance of an open label, 0 once settled
+    __shared__ u8 s_open[T0_ENTRIES][T0_THREADS];   // indices of the open labels (unordered)
+    __shared__ u8 s_hash[T0_HASH][T0_THREADS];      // node id -> label index + 1 (open addressing, 0 = empty)
     const unsigned tid = threadIdx.x, lane = tid & 31;
     const u32 flip = a.tie_flip;
     unsigned long long st_settled = 0, st_relaxed = 0, st_cand = 0, st_searched = 0, st_trunc = 0, st_ovf = 0, st_labels = 0;
@@ -133,8 +138,7 @@ __global__ void __launch_bounds__(T0_THREADS) dijkstra_thread_kernel(SearchArgs 
     // is done (a nested search loop would reconverge only after all 32 searches).
     bool active = false;
     u64 t = 0;
-    u64 sig = 0;  // signature of the labelled node ids
-    u32 src = 0, n = 0, ns = 0, emitted = 0, relaxed = 0, max_open = 0;
+    u32 src = 0, n = 0, n_open = 0, n_settled = 0, emitted = 0, relaxed = 0, max_open = 0;
     for (;;) {
         if (!active) {
             u64 q;
@@ -154,72 +158,84 @@ __global__ void __launch_bounds__(T0_THREADS) dijkstra_thread_kernel(SearchArgs 
             } else {
                 st_searched++;
                 n = 1;
-                ns = 0;
+                n_open = 1;
+                n_settled = 0;
                 emitted = relaxed = 0;
                 max_open = 1;
+#pragma unroll
+                for (int h = 0; h < T0_HASH; h++) s_hash[h][tid] = 0;
                 s_key[0][tid] = src;
                 s_dist[0][tid] = 0;
-                sig = 1ull << ((src * 0x9E3779B1u) >> 26);
+                s_open[0][tid] = 0;
+                s_hash[t0_hash(src)][tid] = 1;
                 active = true;
             }
         }
         if (active) {
             // extract-min over the open labels: total order (dist, node id)
             unsigned long long best = ~0ull;
-            u32 bi = ns;
-            for (u32 i = ns; i < n; i++) {
-                const unsigned long long val = ((unsigned long long)s_dist[i][tid] << 32) | (s_key[i][tid] ^ flip);
+            u32 bi = 0;
+            for (u32 i = 0; i < n_open; i++) {
+                const u32 l = s_open[i][tid];
+                const unsigned long long val = ((unsigned long long)s_dist[l][tid] << 32) | (s_key[l][tid] ^ flip);
                 if (val < best) {
                     best = val;
                     bi = i;
                 }
             }
             const u32 d = (u32)(best >> 32), v = (u32)best ^ flip;
-            if (bi != ns) {  // the winner joins the settled prefix
-                s_key[bi][tid] = s_key[ns][tid];
-                s_dist[bi][tid] = s_dist[ns][tid];
-                s_key[ns][tid] = v;
-                s_dist[ns][tid] = (u8)d;
+            {  // the winner leaves the open list and is marked settled
+                const u32 l = s_open[bi][tid];
+                s_open[bi][tid] = s_open[--n_open][tid];
+                s_dist[l][tid] = 0;  // settled: no relaxation (nw >= 1) compares smaller any more
             }
-            ns++;
+            n_settled++;
             if (v != src && ((a.bitmap[v >> 5] >> (v & 31)) & 1u)) a.records[t * a.cap + emitted++] = (u64)v | ((u64)d << 32);
             bool overflow = false;
             const u32 e0 = a.row_s[v], e1 = a.row_s[v + 1];
-            for (u32 e = e0; e < e1; e++) {
-                const u32 nw = d + a.w_s[e];
+            auto relax = [&](u32 u, u32 w) {
+                const u32 nw = d + w;
                 relaxed++;
-                if (nw > a.max_weight) continue;
-                const u32 u = a.col_s[e];
-                const u64 bit = 1ull << ((u * 0x9E3779B1u) >> 26);
-                u32 j = n;
-                if (sig & bit) {
-                    j = 0;
-                    while (j < n && s_key[j][tid] != u) j++;
-                }
-                if (j < n) {
-                    if (j >= ns && nw < s_dist[j][tid]) s_dist[j][tid] = (u8)nw;  // open label: decrease-key in place
+                if (nw > a.max_weight || overflow) return;
+                // label of u: a few probes of the per-thread hash table instead of a scan over all labels
+                u32 h = t0_hash(u), j;
+                while ((j = s_hash[h][tid]) != 0 && s_key[j - 1][tid] != u) h = (h + 1) & (T0_HASH - 1);
+                if (j) {
+                    if (nw < s_dist[j - 1][tid]) s_dist[j - 1][tid] = (u8)nw;  // open label: decrease-key in place (settled ones hold 0)
                 } else if (n < T0_ENTRIES) {
                     s_key[n][tid] = u;
                     s_dist[n][tid] = (u8)nw;
-                    n++;
-                    sig |= bit;
+                    s_open[n_open++][tid] = (u8)n;
+                    s_hash[h][tid] = (u8)(++n);
                 } else {
                     overflow = true;
-                    break;
                 }
+            };
+            // A node of a de Bruijn graph has at most four out-edges: their targets and weights are requested together,
+            // so the row costs one round trip to L2 instead of two per edge (weight, then target behind the bound check).
+            u32 eu[4], ew[4];
+#pragma unroll
+            for (u32 q = 0; q < 4; q++) {
+                const bool in_row = e0 + q < e1;
+                eu[q] = in_row ? a.col_s[e0 + q] : 0u;
+                ew[q] = in_row ? (u32)a.w_s[e0 + q] : 0u;
             }
-            max_open = max(max_open, n - ns);
+#pragma unroll
+            for (u32 q = 0; q < 4; q++)
+                if (e0 + q < e1) relax(eu[q], ew[q]);
+            for (u32 e = e0 + 4; e < e1 && !overflow; e++) relax(a.col_s[e], (u32)a.w_s[e]);
+            max_open = max(max_open, n_open);
             if (overflow) {
                 a.meta[t] = META_OVERFLOW;
                 a.overflow_list[atomicAdd(a.overflow_count, 1u)] = (u32)t;
                 st_ovf++;
                 active = false;
-            } else if (ns == n || emitted == a.cap) {
+            } else if (n_open == 0 || emitted == a.cap) {
                 // a full list is complete only if nothing is left to settle (checked after v's own relaxation, because
                 // the last target may be the only way to further ones)
-                const bool truncated = ns != n;
+                const bool truncated = n_open != 0;
                 a.meta[t] = emitted | (truncated ? META_TRUNC : 0u);
-                st_settled += ns;
+                st_settled += n_settled;
                 st_relaxed += relaxed;
                 st_cand += emitted;
                 st_trunc += truncated;

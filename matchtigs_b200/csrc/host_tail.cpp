@@ -18,6 +18,7 @@
 
 #include <algorithm>
 #include <omp.h>
+#include <sched.h>
 #if defined(__x86_64__)
 #include <x86intrin.h>
 #endif
@@ -70,6 +71,20 @@ namespace mtg {
 namespace {
 
 double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+// Threads for the data-parallel parts of the tail: the cores this process may run on (at most 16), NOT OpenMP's default --
+// launchers such as torchrun export OMP_NUM_THREADS=1 for every rank, which would serialise the record copy and the piece
+// emission of the one rank that runs the tail.  MTG_HOST_THREADS overrides.
+int host_threads() {
+    static const int n = [] {
+        if (const char* e = getenv("MTG_HOST_THREADS")) return std::max(1, atoi(e));
+        cpu_set_t set;
+        int cpus = 1;
+        if (sched_getaffinity(0, sizeof(set), &set) == 0) cpus = CPU_COUNT(&set);
+        return std::max(1, std::min(cpus, 16));
+    }();
+    return n;
+}
 
 struct TailInput {
     u32 k;
@@ -242,7 +257,7 @@ void build_walk_records(u32 n, u64 E0, u64 E, u32 k, const u32* out_deg, const u
         recs[sl].to = handle[t];
     }
     const bool par = n_slots > (1u << 18);
-#pragma omp parallel for schedule(static) if (par)
+#pragma omp parallel for schedule(static) num_threads(host_threads()) if (par)
     for (i64 sl = 0; sl < (i64)n_slots; sl++) {
         const u32 e = slot_edge[sl];
         if (e == NONE32) continue;
@@ -262,7 +277,7 @@ void build_walk_records(u32 n, u64 E0, u64 E, u32 k, const u32* out_deg, const u
     // on the host) building them would cost more than the walk itself.
     w.hints = n_slots * sizeof(WalkRec) > (64u << 20) || getenv("MTG_TAIL_FORCEHINT");
     for (u32 level = 2; w.hints && level <= WALK_DEPTH; level++) {
-#pragma omp parallel for schedule(static) if (par)
+#pragma omp parallel for schedule(static) num_threads(host_threads()) if (par)
         for (i64 sl = 0; sl < (i64)n_slots; sl++)
             if (slot_edge[sl] != NONE32) walk_fill_hints(recs, (u32)sl, deg_of_handle(recs[sl].to), level);
     }
@@ -294,14 +309,14 @@ void run_tail(const TailInput& in, TailOutput& out, TailScratch& scratch) {
     };
     u32* od = out_deg.data();
     u32* id = in_deg.data();
-#pragma omp parallel for schedule(static) if (par)
+#pragma omp parallel for schedule(static) num_threads(host_threads()) if (par)
     for (i64 e = 0; e < (i64)E0; e++) {
         bump(od[in.from[e]]);
         bump(id[in.to[e]]);
     }
     std::vector<Pair> pairs(in.n_triples);
     pairs.reserve(in.n_triples + 1024);
-#pragma omp parallel for schedule(static) if (par)
+#pragma omp parallel for schedule(static) num_threads(host_threads()) if (par)
     for (i64 j = 0; j < (i64)in.n_triples; j++) {
         const u32 o = in.triples[3 * j], i = in.triples[3 * j + 1];
         pairs[j] = {o, i, in.triples[3 * j + 2]};
@@ -793,7 +808,7 @@ void walk_and_break(const WalkInput& in, TailOutput& out, TailScratch& scratch) 
         const size_t base = walk_slots.size();
         walk_slots.resize(base + len);
         u32* const wbase = walk_slots.data() + base;
-        const int n_parts = len > (1u << 16) ? std::max(1, std::min(omp_get_max_threads(), 16)) : 1;
+        const int n_parts = len > (1u << 16) ? host_threads() : 1;
         std::vector<u64> part_out(n_parts + 1, 0), part_cuts(n_parts + 1, 0);
         std::vector<std::vector<u64>> part_cut_at(n_parts);
         // calls f(x, g) for every element of emission positions [g_lo, g_hi)
@@ -859,7 +874,7 @@ void walk_and_break(const WalkInput& in, TailOutput& out, TailScratch& scratch) 
         u32* we = out.walk_edges.data();
         const u32* se = in.slot_edge;
         const i64 n = (i64)walk_slots.size();
-#pragma omp parallel for schedule(static) if (n > (1 << 16))
+#pragma omp parallel for schedule(static) num_threads(host_threads()) if (n > (1 << 16))
         for (i64 i = 0; i < n; i++) we[i] = se[ws[i] & SLOT_MASK];
     }
     double t4 = now_ms();
@@ -1003,7 +1018,7 @@ void finish_walks(mtg_ctx* ctx) {
     (void)N;
     // The walk works on a copy inside its huge-page arena (page-locking the arena itself loses the huge pages); copied in
     // cache-sized chunks by a few threads: one big memcpy would use non-temporal stores and leave everything cold.
-    const int copy_threads = std::max(1, std::min(omp_get_max_threads(), 16));
+    const int copy_threads = host_threads();
     auto warm_copy = [copy_threads](void* dst, const void* src, size_t bytes) {
         const size_t chunk = 256 << 10;
         const i64 n_chunks = (i64)((bytes + chunk - 1) / chunk);

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -144,6 +145,26 @@ struct PinnedBuf {
         if (p) cudaFreeHost(p);
         p = nullptr;
         cap = 0;
+    }
+};
+
+// Vector-like view over page-locked memory (contents are NOT preserved when it grows): results that come back from the
+// device land here at full link speed instead of being staged through the driver's bounce buffer.
+template <class T>
+struct PinnedVec {
+    PinnedBuf buf;
+    size_t n = 0;
+    T* data() { return reinterpret_cast<T*>(buf.p); }
+    const T* data() const { return reinterpret_cast<const T*>(buf.p); }
+    size_t size() const { return n; }
+    void resize(size_t count) {
+        buf.ensure(std::max<size_t>(count, 1) * sizeof(T));
+        n = count;
+    }
+    void clear() { n = 0; }
+    void release() {
+        buf.release();
+        n = 0;
     }
 };
 
@@ -312,7 +333,7 @@ struct mtg_ctx {
     mtg::DBuf<mtg::i32> final_mult;   // [N] node multiplicities after the matching == leftover imbalance
     mtg::DBuf<mtg::u32> triples;      // [3 * n_triples] device
     uint64_t n_triples = 0;
-    std::vector<uint32_t> h_triples;
+    mtg::PinnedVec<uint32_t> h_triples;  // page-locked: 12 B per matched pair come back after every matching
     bool have_triples = false;
 
     // ---- host tail ----
