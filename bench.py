@@ -460,9 +460,9 @@ def run_ours(args):
 
 SEARCH_KERNEL = "dijkstra_thread_kernel"
 # (workload, scale) -> DRAM bytes (read + write) of one main launch of dijkstra_thread_kernel, from ncu --set full
-NCU_DRAM_BYTES = {("ecoli", 1.0): 208896 + 0, ("chr1", 0.3): 27804160 + 17134592}
+NCU_DRAM_BYTES = {("chr1", 1.0): 100583680 + 120263168}  # profiles/round2_ncu_full_dijkstra_thread_kernel_chr1.txt
 # same captures: L2 sectors the kernel read (lts__t_sectors_srcunit_tex_op_read.sum), i.e. the sector-granular traffic
-NCU_L2_READ_SECTORS = {("ecoli", 1.0): 144437, ("chr1", 0.3): 33546649}
+NCU_L2_READ_SECTORS = {("chr1", 1.0): 110160889}
 # random 32-byte-sector gather ceilings measured on a B200 of this pool with scripts/micro/gather_ceiling.cu
 # (profiles/round1_gather_ceiling.jsonl): footprint 8 GiB (HBM) and 32 MiB (L2-resident), independent gathers
 GATHER_CEILING_GBPS = {"hbm_random": 1174.8, "l2_resident": 6663.9}

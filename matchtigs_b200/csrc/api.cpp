@@ -204,6 +204,7 @@ void mtg_ctx_destroy(mtg_ctx* ctx) {
     for (auto& b : ctx->text_stage) b.release();
     for (auto& b : ctx->tail_stage) b.release();
     ctx->h_triples.release();
+    ctx->walk_edges.release();
     ctx->gathered_rec.release(s);
     ctx->gathered_meta.release(s);
     mtg::block_cache_trim(s);  // everything this context's stream ever cached goes back to the driver

@@ -128,9 +128,12 @@ __global__ void __launch_bounds__(T0_THREADS) dijkstra_thread_kernel(SearchArgs 
     __shared__ u32 s_key[T0_ENTRIES][T0_THREADS];   // labelled node ids, in insertion order (labels never move)
     __shared__ u8 s_dist[T0_ENTRIES][T0_THREADS];   // tentative distance of an open label, 0 once settled
     __shared__ u8 s_open[T0_ENTRIES][T0_THREADS];   // indices of the open labels (unordered)
-    __shared__ u8 s_hash[T0_HASH][T0_THREADS];      // node id -> label index + 1 (open addressing, 0 = empty)
+    __shared__ u32 s_hash32[T0_HASH / 4][T0_THREADS];  // node id -> label index + 1 (open addressing, 0 = empty): one byte per
+                                                       // slot, four slots of a thread per word so that a table is cleared
+                                                       // with 16 stores; every access of a lane stays in its own bank
     const unsigned tid = threadIdx.x, lane = tid & 31;
     const u32 flip = a.tie_flip;
+    auto hash_slot_of = [&](u32 h) -> u8& { return reinterpret_cast<u8*>(&s_hash32[h >> 2][tid])[h & 3]; };
     unsigned long long st_settled = 0, st_relaxed = 0, st_cand = 0, st_searched = 0, st_trunc = 0, st_ovf = 0, st_labels = 0;
     u32 st_max_labels = 0, st_max_open = 0;
     // One flat loop: every iteration a lane either fetches its next source or settles ONE node of its current search.
@@ -163,11 +166,11 @@ __global__ void __launch_bounds__(T0_THREADS) dijkstra_thread_kernel(SearchArgs 
                 emitted = relaxed = 0;
                 max_open = 1;
 #pragma unroll
-                for (int h = 0; h < T0_HASH; h++) s_hash[h][tid] = 0;
+                for (int h = 0; h < T0_HASH / 4; h++) s_hash32[h][tid] = 0;
                 s_key[0][tid] = src;
                 s_dist[0][tid] = 0;
                 s_open[0][tid] = 0;
-                s_hash[t0_hash(src)][tid] = 1;
+                hash_slot_of(t0_hash(src)) = 1;
                 active = true;
             }
         }
@@ -199,14 +202,14 @@ __global__ void __launch_bounds__(T0_THREADS) dijkstra_thread_kernel(SearchArgs 
                 if (nw > a.max_weight || overflow) return;
                 // label of u: a few probes of the per-thread hash table instead of a scan over all labels
                 u32 h = t0_hash(u), j;
-                while ((j = s_hash[h][tid]) != 0 && s_key[j - 1][tid] != u) h = (h + 1) & (T0_HASH - 1);
+                while ((j = hash_slot_of(h)) != 0 && s_key[j - 1][tid] != u) h = (h + 1) & (T0_HASH - 1);
                 if (j) {
                     if (nw < s_dist[j - 1][tid]) s_dist[j - 1][tid] = (u8)nw;  // open label: decrease-key in place (settled ones hold 0)
                 } else if (n < T0_ENTRIES) {
                     s_key[n][tid] = u;
                     s_dist[n][tid] = (u8)nw;
                     s_open[n_open++][tid] = (u8)n;
-                    s_hash[h][tid] = (u8)(++n);
+                    hash_slot_of(h) = (u8)(++n);
                 } else {
                     overflow = true;
                 }

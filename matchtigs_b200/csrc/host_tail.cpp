@@ -97,6 +97,7 @@ struct TailInput {
 
 struct TailOutput {
     std::vector<u32> walk_edges;
+    PinnedVec<u32>* edges_pinned = nullptr;  // if set, the walk edges are written there instead (page-locked: uploaded right after)
     std::vector<u64> walk_limits;
     std::vector<u32> dummy_w;  // weight of dummy edge e at [(e - n_orig)]
     u64 cycles = 0, breaking = 0;
@@ -868,10 +869,11 @@ void walk_and_break(const WalkInput& in, TailOutput& out, TailScratch& scratch) 
     MTG_REQUIRE(steps_total == E / 2, MTG_ERR_INTERNAL, "Failed to make the graph Eulerian (the closed walks do not cover every edge).");
     double tt = now_ms();
     // slots -> edge ids: independent gathers, spread over the host cores
-    out.walk_edges.resize(walk_slots.size());
+    if (out.edges_pinned) out.edges_pinned->resize(walk_slots.size());
+    else out.walk_edges.resize(walk_slots.size());
     {
         const u32* ws = walk_slots.data();
-        u32* we = out.walk_edges.data();
+        u32* we = out.edges_pinned ? out.edges_pinned->data() : out.walk_edges.data();
         const u32* se = in.slot_edge;
         const i64 n = (i64)walk_slots.size();
 #pragma omp parallel for schedule(static) num_threads(host_threads()) if (n > (1 << 16))
@@ -974,8 +976,8 @@ static void finish_walks_host_prep(mtg_ctx* ctx) {
     }
     TailInput in{ctx->k, N, E, from, to, uw, mirror, ctx->h_triples.data(), ctx->n_triples, ctx->opt.p3_oldest_first != 0};
     TailOutput out;
+    out.edges_pinned = &ctx->walk_edges;
     run_tail(in, out, ctx->tail_scratch);
-    ctx->walk_edges.swap(out.walk_edges);
     ctx->walk_limits.swap(out.walk_limits);
     ctx->h_dummy_w.swap(out.dummy_w);
     ctx->tail_ms[0] = out.ms_degrees;
@@ -1019,8 +1021,8 @@ void finish_walks(mtg_ctx* ctx) {
     // The walk works on a copy inside its huge-page arena (page-locking the arena itself loses the huge pages); copied in
     // cache-sized chunks by a few threads: one big memcpy would use non-temporal stores and leave everything cold.
     const int copy_threads = host_threads();
-    auto warm_copy = [copy_threads](void* dst, const void* src, size_t bytes) {
-        const size_t chunk = 256 << 10;
+    auto warm_copy = [copy_threads](void* dst, const void* src, size_t bytes) {  // NOLINT
+        static const size_t chunk = (getenv("MTG_TAIL_COPY_CHUNK_KB") ? (size_t)atol(getenv("MTG_TAIL_COPY_CHUNK_KB")) : 256) << 10;  // A/B switch
         const i64 n_chunks = (i64)((bytes + chunk - 1) / chunk);
 #pragma omp parallel for schedule(static) num_threads(copy_threads) if (bytes > (8u << 20))
         for (i64 c = 0; c < n_chunks; c++) {
@@ -1030,6 +1032,7 @@ void finish_walks(mtg_ctx* ctx) {
     };
     // while the records are in flight: dummy weights (matching dummies carry their distance, breaking dummies weigh k)
     TailOutput out;
+    out.edges_pinned = &ctx->walk_edges;
     out.dummy_w.resize(2 * P);
     const u32* trp = ctx->h_triples.data();
     u32 max_matching_w = 0;
@@ -1064,7 +1067,6 @@ void finish_walks(mtg_ctx* ctx) {
     WalkInput w{ctx->k, N, E0, E0 + 2 * P, tr.n_slots, recs, used, nullptr, tr.slot_edge, tr.slot_of_edge, nullptr, tr.handle,
                 out.dummy_w.data(), max_matching_w < ctx->k, true};
     walk_and_break(w, out, scratch);
-    ctx->walk_edges.swap(out.walk_edges);
     ctx->walk_limits.swap(out.walk_limits);
     ctx->h_dummy_w.swap(out.dummy_w);
     ctx->tail_ms[0] = t1b - t1;  // device-prepared path: record kernels up to the point where the DMA is queued

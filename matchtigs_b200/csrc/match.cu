@@ -43,6 +43,9 @@ void run_searches(mtg_ctx* ctx, const u32* bitmap, const u32* work_list, u64 n_w
 namespace {
 
 constexpr int TB = 256;
+#ifndef MTG_MATCH_SLEEP_NS
+#define MTG_MATCH_SLEEP_NS 100  // pause between two attempts of a blocked source (A/B: -DMTG_MATCH_SLEEP_NS=0|20|50)
+#endif
 constexpr u32 META_TRUNC = 0x80000000u;
 constexpr u32 META_COUNT = 0x00FFFFFFu;
 constexpr u32 NO_INDEX = 0xFFFFFFFFu;
@@ -201,7 +204,7 @@ __global__ void __launch_bounds__(TB) match_dataflow_kernel(MatchArgs a) {
                 break;
             }
             retries++;
-            __nanosleep(100);
+            if (MTG_MATCH_SLEEP_NS) __nanosleep(MTG_MATCH_SLEEP_NS);
         }
     }
     for (int o = 16; o > 0; o >>= 1) retries += __shfl_down_sync(0xffffffffu, retries, o);

@@ -157,6 +157,9 @@ struct PinnedVec {
     T* data() { return reinterpret_cast<T*>(buf.p); }
     const T* data() const { return reinterpret_cast<const T*>(buf.p); }
     size_t size() const { return n; }
+    bool empty() const { return n == 0; }
+    T& operator[](size_t i) { return data()[i]; }
+    const T& operator[](size_t i) const { return data()[i]; }
     void resize(size_t count) {
         buf.ensure(std::max<size_t>(count, 1) * sizeof(T));
         n = count;
@@ -339,7 +342,7 @@ struct mtg_ctx {
     // ---- host tail ----
     std::vector<uint32_t> h_dummy_w;  // weight of dummy edge e at [e - 2U]
     double tail_ms[5] = {0, 0, 0, 0, 0};  // degrees, eulerise, csr, walk, break
-    std::vector<uint32_t> walk_edges;
+    mtg::PinnedVec<uint32_t> walk_edges;  // page-locked: written by the tail, uploaded for the output kernels
     std::vector<uint64_t> walk_limits;
     bool have_walks = false;
     mtg::DBuf<mtg::u32> d_walk_edges;
