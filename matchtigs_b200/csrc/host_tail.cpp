@@ -1021,8 +1021,8 @@ void finish_walks(mtg_ctx* ctx) {
     // The walk works on a copy inside its huge-page arena (page-locking the arena itself loses the huge pages); copied in
     // cache-sized chunks by a few threads: one big memcpy would use non-temporal stores and leave everything cold.
     const int copy_threads = host_threads();
-    auto warm_copy = [copy_threads](void* dst, const void* src, size_t bytes) {  // NOLINT
-        static const size_t chunk = (getenv("MTG_TAIL_COPY_CHUNK_KB") ? (size_t)atol(getenv("MTG_TAIL_COPY_CHUNK_KB")) : 256) << 10;  // A/B switch
+    auto warm_copy = [copy_threads](void* dst, const void* src, size_t bytes) {
+        const size_t chunk = 256 << 10;  // (64 KB .. 8 MB measured alike: the phase waits for the link, not for the copy)
         const i64 n_chunks = (i64)((bytes + chunk - 1) / chunk);
 #pragma omp parallel for schedule(static) num_threads(copy_threads) if (bytes > (8u << 20))
         for (i64 c = 0; c < n_chunks; c++) {

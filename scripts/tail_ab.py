@@ -19,8 +19,12 @@ ctx.greedy_match()
 print(ctx.graph_info())
 ctx.finish_walks()
 print('THP:', open('/sys/kernel/mm/transparent_hugepage/enabled').read().strip(), '| defrag:', open('/sys/kernel/mm/transparent_hugepage/defrag').read().strip(), '|', [l.strip() for l in open('/proc/self/smaps_rollup') if 'AnonHuge' in l or l.startswith('Rss')])
-for label, env in (("default", {}), ("copy8M", {"MTG_TAIL_COPY_CHUNK_KB": "8192"}), ("copy64K", {"MTG_TAIL_COPY_CHUNK_KB": "64"}),
-                   ("copy8M+8thr", {"MTG_TAIL_COPY_CHUNK_KB": "8192", "MTG_HOST_THREADS": "8"}), ("default", {})):
+VARIANTS = (("default", {}), ("sources1", {"MTG_WALK_SOURCES": "1"}), ("fast0", {"MTG_WALK_FAST": "0"}), ("store", {"MTG_WALK_NTSTORE": "0"}),
+            ("nta", {"MTG_WALK_PREFETCH": "nta"}), ("nohint", {"MTG_TAIL_NOHINT": "1"}), ("default", {}), ("probe", {"MTG_WALK_PROBE": "1"}))
+only = os.environ.get("TAIL_AB_ONLY")  # comma-separated labels
+for label, env in VARIANTS:
+    if only and label not in only.split(","):
+        continue
     for k_, v in env.items():
         os.environ[k_] = v
     rows = []
