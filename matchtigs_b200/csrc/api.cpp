@@ -68,6 +68,8 @@ namespace {
 struct BlockCache {
     std::mutex m;
     std::map<std::pair<cudaStream_t, size_t>, std::vector<void*>> free_blocks;  // (stream, class) -> blocks
+    size_t free_bytes = 0;  // bytes sitting in the free lists
+    size_t limit = 0;       // beyond this, released blocks go straight back to the driver (0 = not initialised yet)
 };
 BlockCache& block_cache() {
     static BlockCache* c = new BlockCache();  // never destroyed: contexts may outlive static destruction order
@@ -90,6 +92,7 @@ void* block_alloc(size_t class_bytes, cudaStream_t s) {
         if (it != c.free_blocks.end() && !it->second.empty()) {
             void* p = it->second.back();
             it->second.pop_back();
+            c.free_bytes -= class_bytes;
             return p;
         }
     }
@@ -107,7 +110,21 @@ void* block_alloc(size_t class_bytes, cudaStream_t s) {
 void block_free(void* p, size_t class_bytes, cudaStream_t s) {
     BlockCache& c = block_cache();
     std::lock_guard<std::mutex> g(c.m);
+    if (c.limit == 0) {
+        // idle blocks may hold up to a quarter of the device (MTG_BLOCK_CACHE_MAX_MB overrides): enough for the scratch
+        // of any job that fits the device next to its resident graph, bounded for a process that runs many different jobs
+        size_t free_b = 0, total_b = 0;
+        if (const char* e = getenv("MTG_BLOCK_CACHE_MAX_MB")) c.limit = (size_t)std::max(1L, atol(e)) << 20;
+        else if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) c.limit = std::max<size_t>(total_b / 4, size_t(1) << 30);
+        else c.limit = size_t(16) << 30;
+        cudaGetLastError();
+    }
+    if (c.free_bytes + class_bytes > c.limit) {
+        cudaFreeAsync(p, s);
+        return;
+    }
     c.free_blocks[{s, class_bytes}].push_back(p);
+    c.free_bytes += class_bytes;
 }
 
 void block_cache_trim(cudaStream_t s) {
@@ -116,6 +133,7 @@ void block_cache_trim(cudaStream_t s) {
     for (auto it = c.free_blocks.begin(); it != c.free_blocks.end();) {
         if (it->first.first == s) {
             for (void* p : it->second) cudaFreeAsync(p, s);
+            c.free_bytes -= it->first.second * it->second.size();
             it = c.free_blocks.erase(it);
         } else {
             ++it;

@@ -1061,7 +1061,7 @@ void finish_walks(mtg_ctx* ctx) {
     if (tr.used0) memcpy(used, tr.used0, used_bytes);
     else memset(used, 0, used_bytes);  // empty graph
     double t2 = now_ms();
-    if (trace_slow_calls() && t2 - t1b > 30.0)
+    if (trace_slow_calls() && (t2 - t1b > 30.0 || getenv("MTG_TRACE_ALL")))
         fprintf(stderr, "[mtg trace] tail records, %llu slots: waiting for the DMA %.1f ms, copying %.1f ms, rest %.1f ms\n",
                 (unsigned long long)tr.n_slots, ms_wait, ms_copy, t2 - t1b - ms_wait - ms_copy);
     WalkInput w{ctx->k, N, E0, E0 + 2 * P, tr.n_slots, recs, used, nullptr, tr.slot_edge, tr.slot_of_edge, nullptr, tr.handle,

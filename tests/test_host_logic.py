@@ -103,6 +103,31 @@ def test_host_tail_threaded_preparation_with_hints(mt):
     check_tail(mt, text, k, "fasta", euler_fast=True)
 
 
+WALK_SWITCHES = [{}, {"MTG_WALK_FAST": "0"}, {"MTG_WALK_SOURCES": "1"}, {"MTG_WALK_SOURCES": "3"}, {"MTG_WALK_NTSTORE": "0"},
+                 {"MTG_WALK_PREFETCH": "nta"}, {"MTG_WALK_PROBE": "1"}, {"MTG_HOST_THREADS": "3"}]
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_host_tail_with_lookahead_hints_on_small_graphs(mt, seed, monkeypatch):
+    """The walk's lookahead machinery (hint levels, the written-out steady state, the second hint source, chain resets at
+    nodes with three or four out-edges and at big nodes) normally only runs on graphs whose records outgrow the caches.
+    MTG_TAIL_FORCEHINT=1 builds the hint levels for any graph, so that every variant of the run loop (the A/B switches
+    select template instantiations and code paths) is compared with the oracle on small, repeat-rich, branching inputs."""
+    rng = random.Random(7700 + seed)
+    k = rng.choice([4, 5, 6, 8])  # small k: many nodes with three and four out-edges, palindromes, self-mirrors
+    text = random_fasta(rng, rng.randint(30, 400), k, max_extra=10, pool=rng.choice([None, 3, 8, 25]))
+    o, args = oracle_inputs(text, k, "fasta")
+    ow = o.walks()
+    monkeypatch.setenv("MTG_TAIL_FORCEHINT", "1")
+    for env in WALK_SWITCHES:
+        with monkeypatch.context() as m:
+            for name, value in env.items():
+                m.setenv(name, value)
+            walks, _, _ = mt.api.host_tail(k, *args)
+        assert len(walks) == len(ow), env
+        assert all(np.array_equal(a, b) for a, b in zip(walks, ow)), env
+
+
 @pytest.mark.parametrize("seed", range(6))
 def test_host_tail_heavy_matching_dummies_take_the_generic_breaking_path(mt, seed):
     """Behind the GPU matching a matching dummy always weighs less than k, and the tail recognises breaking dummies by edge
