@@ -395,7 +395,7 @@ struct RunIO {
     bool fast_path;        // A/B switch
     // diagnostics (DIAG instantiation only)
     u64 dg_steps, dg_reset, dg_have[8], dg_nohint, dg_big, dg_end;
-    u64 probe_hist[4][16];
+    u64 probe_hist[5][40];  // 16-tick buckets; [4] = the probe itself on a line that is certainly in L1
     u64 probe_tick;
     bool probe;
 };
@@ -469,9 +469,7 @@ __attribute__((noinline)) static void walk_run(RunIO& io, u32 s, u32 from_h) {
         else (void)*(const volatile u32*)addr;
         _mm_lfence();
         const u64 b = __rdtscp(&aux);
-        int bucket = 0;
-        for (u64 d = b - a; d > 1 && bucket < 15; d >>= 1) bucket++;
-        io.probe_hist[which][bucket]++;
+        io.probe_hist[which][std::min<u64>((b - a) >> 4, 39)]++;
 #endif
     };
     // What the walk expects 1 .. `have` steps from now -- P[L] = slot, Q[L] = its index inside its node -- carried from
@@ -516,7 +514,10 @@ __attribute__((noinline)) static void walk_run(RunIO& io, u32 s, u32 from_h) {
     while (s != NONE32) {
         const WalkRec& r = recs[s];
         const bool probing = DIAG && io.probe && (++io.probe_tick & 63) == 0;
-        if (probing) probe_load(0, &r.to, 4);
+        if (probing) {
+            probe_load(4, &io.probe_tick, 8);
+            probe_load(0, &r.to, 4);
+        }
         const u32 ms = r.mslot;
         if (probing) probe_load(3, &used[(ms & SLOT_MASK) >> 6], 8);
         mark(s);
@@ -659,10 +660,12 @@ void walk_and_break(const WalkInput& in, TailOutput& out, TailScratch& scratch) 
                     (unsigned long long)h[1], (unsigned long long)h[2], (unsigned long long)h[3], (unsigned long long)h[4], (unsigned long long)h[5],
                     (unsigned long long)io->dg_reset, (unsigned long long)io->dg_big, (unsigned long long)io->dg_end, (unsigned long long)io->dg_nohint);
             if (!io->probe) return;
-            const char* names[4] = {"record load", "used bits of the target", "used bits of the far node", "used bits of the mirror slot"};
-            for (int w = 0; w < 4; w++) {
-                fprintf(stderr, "[mtg probe] %-28s cycles 2^k..:", names[w]);
-                for (int b = 4; b < 14; b++) fprintf(stderr, " %d:%llu", b, (unsigned long long)io->probe_hist[w][b]);
+            const char* names[5] = {"record load", "used bits of the target", "used bits of the far node", "used bits of the mirror slot",
+                                    "(probe alone, L1 hit)"};
+            for (int w = 0; w < 5; w++) {
+                fprintf(stderr, "[mtg probe] %-28s TSC ticks, 16 per bucket:", names[w]);
+                for (int b = 0; b < 40; b++)
+                    if (io->probe_hist[w][b]) fprintf(stderr, " %d:%llu", 16 * b, (unsigned long long)io->probe_hist[w][b]);
                 fprintf(stderr, "\n");
             }
         }

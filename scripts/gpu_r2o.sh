@@ -1,6 +1,5 @@
 #!/bin/bash
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-T=${1:-r2o}
-MTG_TRACE=1 MTG_TRACE_ALL=1 TAIL_AB_ONLY=default timeout 600 python scripts/tail_ab.py chr1 1.0 4 2>&1 | grep "tail records\|default" | tail -12
-OMP_WAIT_POLICY=active MTG_TRACE=1 MTG_TRACE_ALL=1 TAIL_AB_ONLY=default timeout 600 python scripts/tail_ab.py chr1 1.0 4 2>&1 | grep "tail records\|default" | tail -12
+TAIL_AB_ONLY=probe timeout 600 python scripts/tail_ab.py chr1 1.0 2 2>&1 | grep "probe" | tail -6 | tee gpurun_out/r2o_probe_chr1.txt
+TAIL_AB_ONLY=probe timeout 600 python scripts/tail_ab.py pangenome 1.0 2 2>&1 | grep "probe" | tail -6 | tee gpurun_out/r2o_probe_pan.txt
