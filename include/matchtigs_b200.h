@@ -113,7 +113,7 @@ int mtg_build_graph_from_links(mtg_ctx* ctx, uint64_t unitigs, const uint64_t* w
 
 /* Same two builders fed by the device-side record parser: `text` is the raw FASTA (bcalm == 0, --fa-in semantics) or
  * bcalm2 FASTA (bcalm != 0, --bcalm-in semantics: ids must equal positions, `L:` fields become links) file content,
- * < 4 GiB, on the host or (text_on_device != 0) already in HBM.  Line splitting, header/sequence separation,
+ * < 32 GiB and < 2^32 bases, on the host or (text_on_device != 0) already in HBM.  Line splitting, header/sequence separation,
  * multi-line records, id validation and link extraction all run as scans on the GPU
  * (replaces the record parsing of genome-graph's readers, call sites src/bin.rs:896-899, :907-910). */
 int mtg_build_graph_from_text(mtg_ctx* ctx, const char* text, uint64_t len, int bcalm, uint32_t k, int text_on_device);

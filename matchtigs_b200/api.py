@@ -327,13 +327,13 @@ class Graph:
         return self.ctx.graph_info()["edges"]
 
 
-_DEVICE_PARSE_LIMIT = 0xFFFFFFF0  # the device-side record parser indexes bytes with 32 bits
+_DEVICE_PARSE_LIMIT = (1 << 35) - 64  # the device-side record parser tags 32-byte chunks with 30-bit indices
 
 
 def read_bigraph_from_fasta_as_edge_centric(text: bytes, k: int, ctx: Context | None = None, device_parse: bool = True) -> Graph:
     """``--fa-in``: nodes are the distinct (k-1)-mers at unitig ends, numbered in first-seen order.
 
-    Records are split on the device (``mtg_build_graph_from_text``); ``device_parse=False`` (or a file of 4 GiB and
+    Records are split on the device (``mtg_build_graph_from_text``); ``device_parse=False`` (or a file of 32 GiB and
     more) uses the host reader + ``mtg_build_graph_from_sequences`` instead -- same graph either way."""
     ctx = ctx or Context()
     if device_parse and len(text) < _DEVICE_PARSE_LIMIT:

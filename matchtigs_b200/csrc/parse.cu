@@ -262,11 +262,34 @@ __global__ void __launch_bounds__(TB) weights_from_offsets(const u64* __restrict
     }
 }
 
+// 64-bit totals of two per-chunk count arrays: the offsets below are 32-bit sums, this is their overflow guard
+__global__ void __launch_bounds__(TB) sum_counts_u64(const u32* __restrict__ a, const u32* __restrict__ b, const u32* __restrict__ c, u64 n,
+                                                      unsigned long long* __restrict__ out) {
+    unsigned long long sa = 0, sb = 0, sc = 0;
+    for (u64 i = (u64)blockIdx.x * TB + threadIdx.x; i < n; i += (u64)gridDim.x * TB) {
+        sa += a[i];
+        sb += b[i];
+        if (c) sc += c[i];
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        sa += __shfl_down_sync(0xffffffffu, sa, o);
+        sb += __shfl_down_sync(0xffffffffu, sb, o);
+        sc += __shfl_down_sync(0xffffffffu, sc, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (sa) atomicAdd(out, sa);
+        if (sb) atomicAdd(out + 1, sb);
+        if (sc) atomicAdd(out + 2, sc);
+    }
+}
+
 }  // namespace
 
 void build_graph_from_text(mtg_ctx* ctx, const char* text, u64 L, bool bcalm, u32 k, bool text_on_device) {
     MTG_REQUIRE(L == 0 || text, MTG_ERR_INVALID, "null text");
-    MTG_REQUIRE(L < 0xFFFFFFF0ull, MTG_ERR_UNSUPPORTED, "text of 4 GiB or more: parse it in pieces with the host reader");
+    // Text positions are 64-bit throughout; what is 32-bit are the chunk tags of the line-state scan (chunk index << 2) and
+    // the per-chunk offsets (records, bases, links) -- the latter guarded by 64-bit totals below.
+    MTG_REQUIRE(L < (u64(1) << 35) - 64, MTG_ERR_UNSUPPORTED, "text of 32 GiB or more: parse it in pieces with the host reader");
     cudaStream_t s = ctx->stream;
     if (!ctx->text_event_recorded) MTG_CUDA(cudaEventRecord(ctx->ev_build[0], s));
     ctx->text_event_recorded = false;
@@ -298,7 +321,20 @@ void build_graph_from_text(mtg_ctx* ctx, const char* text, u64 L, bool bcalm, u3
         exclusive_sum_u32(ctx, ws.n_seq.p, ws.sbase.p, n_chunks, totals.p + 1);
         if (bcalm) exclusive_sum_u32(ctx, ws.n_link.p, ws.lbase.p, n_chunks, totals.p + 2);
         MTG_CUDA(cudaMemcpyAsync(h_tot, totals.p, sizeof(h_tot), cudaMemcpyDeviceToHost, s));
+        unsigned long long h_tot64[3] = {0, 0, 0};
+        const bool may_overflow = L >= 0xFFFFFFF0ull;  // below 4 GiB of text no count can reach 2^32
+        DBuf<unsigned long long> tot64;
+        if (may_overflow) {
+            tot64.resize(3, s);
+            tot64.zero(s);
+            MTG_LAUNCH(ctx, sum_counts_u64, (unsigned)std::min<u64>(grid_for(n_chunks, TB).x, 148u * 16u), TB, 0, ws.n_rec.p, ws.n_seq.p,
+                       bcalm ? ws.n_link.p : (const u32*)nullptr, n_chunks, tot64.p);
+            MTG_CUDA(cudaMemcpyAsync(h_tot64, tot64.p, sizeof(h_tot64), cudaMemcpyDeviceToHost, s));
+        }
         MTG_CUDA(cudaStreamSynchronize(s));
+        if (may_overflow)
+            MTG_REQUIRE(h_tot64[0] == h_tot[0] && h_tot64[1] == h_tot[1] && (!bcalm || h_tot64[2] == h_tot[2]), MTG_ERR_UNSUPPORTED,
+                        "more than 2^32 - 1 records, bases or links in one file");
     }
     const u64 U = h_tot[0], B = h_tot[1], NL = bcalm ? h_tot[2] : 0;
     // the bases go straight into the context's 2-bit store (zeroed: the chunks OR their pieces in)

@@ -254,6 +254,34 @@ def test_device_parser_equals_host_reader(mt, ctx, bcalm):
         assert ctx.assemble_tigs("gfa") == o.text("gfa") and ctx.dup_bitvector() == o.text("bitvector")
 
 
+@pytest.mark.parametrize("bcalm", [False, True])
+def test_device_parser_text_beyond_4_gib(mt, ctx, bcalm):
+    """Text positions are 64-bit in the device parser (the 32-bit quantities are chunk tags and guarded sums): a file of
+    4.3 GiB -- a small workload whose header lines carry megabytes of comment -- must give the graph and the outputs of
+    the same records without the padding (bcalm2 files of human-scale inputs are of this size, src/bin.rs:905-911)."""
+    text, k, info = tools.config_unitigs("ecoli", 0.02)
+    mode = "bcalm" if bcalm else "fasta"
+    o = run_oracle(text, k, mode)
+    build(mt, ctx, text, k, mode, device_parse=True)
+    gi_ref, ex_ref = graph_state(ctx)
+    lines = text.split(b"\n")
+    n_hdr = sum(ln.startswith(b">") for ln in lines)
+    pad = b" " + b"x" * (int(4.3 * 2**30) // n_hdr)
+    big = b"\n".join(ln + pad if ln.startswith(b">") else ln for ln in lines)
+    del lines
+    assert len(big) > 2**32 + 2**20
+    ctx.build_graph_from_text(big, k, bcalm)
+    del big
+    gi, ex = graph_state(ctx)
+    assert gi == gi_ref
+    for name in ex_ref:
+        assert np.array_equal(ex[name], ex_ref[name]), name
+    ctx.dijkstra_candidates(8)
+    ctx.greedy_match()
+    ctx.finish_walks()
+    assert ctx.assemble_tigs("gfa") == o.text("gfa") and ctx.dup_bitvector() == o.text("bitvector")
+
+
 def test_device_parser_errors_and_edge_cases(mt, ctx):
     for bad, bcalm in ((b"ACGT\n>0\nACGTA\n", False), (b">1 LN:i:5\nACGTA\n", True), (b">0 L:+:x:+\nACGTA\n", True),
                        (b">0 L:*:1:+\nACGTA\n", True), (b">0 L:+:7:+\nACGTA\n", True), (b">0\nACGNA\n", False), (b">0\nAC\n", True)):
