@@ -156,6 +156,21 @@ __global__ void __launch_bounds__(TB)
               const u32* __restrict__ first, const u64* __restrict__ words, u64 q_base, u64 total, char* __restrict__ out) {
     // produces bytes [q_base, total) of the text into out[0 ..): a rank's share of the output, or all of it
     __shared__ SegMeta s_meta[SEG_CACHE];
+    // four bases (one byte of the 2-bit store) -> four characters: forward, and reverse complement (characters reversed)
+    __shared__ u32 s_fwd[256], s_rc[256];
+    static_assert(TB == 256, "one table entry per thread");
+    {
+        const u32 b = threadIdx.x;
+        u32 f = 0, r = 0;
+#pragma unroll
+        for (u32 i = 0; i < 4; i++) {
+            const u32 c = (b >> (2 * i)) & 3u;
+            f |= (u32)(u8)base_char(c) << (8 * i);
+            r |= (u32)(u8)base_char(c ^ 2u) << (8 * (3 - i));
+        }
+        s_fwd[b] = f;
+        s_rc[b] = r;
+    }
     const u64 cta_q0 = q_base + (u64)blockIdx.x * TB * CHUNK;
     const u64 j0 = first[blockIdx.x];
     const u64 j1 = blockIdx.x + 1 < gridDim.x ? (u64)first[blockIdx.x + 1] : w.W - 1;
@@ -192,6 +207,22 @@ __global__ void __launch_bounds__(TB)
         const bool dummy = (m.flags & 256u) != 0, backward = (m.flags & 512u) != 0, last = (m.flags & 1024u) != 0;
         const u64 stop = min(qend, s0 + len);             // this thread's bytes of the segment: [q, stop)
         const u32 body_end = len - (last ? 1u : 0u);      // segment-relative index of the trailing '\n', if any
+        if (CHUNK == 16 && q == q0 && qend - q0 == CHUNK && (u32)(q - s0) >= hdr && q0 + CHUNK <= s0 + body_end) {
+            // the common case: all 16 bytes are body characters of one segment -- four table look-ups, one 16-byte store
+            uint4 v;
+            if (mode == 0) {
+                const u32 c = dummy ? 0x30303030u : 0x31313131u;
+                v = make_uint4(c, c, c, c);
+            } else if (!backward) {
+                const u64 bits = read_bases64(words, m.first + ((u32)(q - s0) - hdr));
+                v = make_uint4(s_fwd[bits & 255u], s_fwd[(bits >> 8) & 255u], s_fwd[(bits >> 16) & 255u], s_fwd[(bits >> 24) & 255u]);
+            } else {
+                const u64 bits = read_bases64(words, m.first - ((u32)(q - s0) - hdr) - CHUNK);
+                v = make_uint4(s_rc[(bits >> 24) & 255u], s_rc[(bits >> 16) & 255u], s_rc[(bits >> 8) & 255u], s_rc[bits & 255u]);
+            }
+            *reinterpret_cast<uint4*>(out + (q0 - q_base)) = v;
+            return;
+        }
         // header characters: "S\t<i>\t" (GFA) / "><i>\n" (FASTA)
         for (; q < stop && (u32)(q - s0) < hdr; q++) {
             const u32 c = (u32)(q - s0);
