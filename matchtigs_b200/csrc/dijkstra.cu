@@ -115,7 +115,10 @@ __device__ __forceinline__ u64 warp_or64(u64 v) {
 //   a relaxed edge first asks a 64-bit signature of the labelled node ids (one bit per hash class): most relaxed
 //   edges lead to a node not seen before and skip the linear search of the labels altogether.
 // Searches that outgrow T0_ENTRIES labels go to the warp tier.
-constexpr int T0_THREADS = 128;
+#ifndef MTG_T0_THREADS
+#define MTG_T0_THREADS 128
+#endif
+constexpr int T0_THREADS = MTG_T0_THREADS;
 #ifndef MTG_T0_ENTRIES
 #define MTG_T0_ENTRIES 48
 #endif
@@ -124,15 +127,20 @@ constexpr int T0_HASH = 64;           // hash slots per thread (power of two, > 
 static_assert(T0_ENTRIES < T0_HASH && T0_ENTRIES < 255, "label indices are bytes and the table must keep free slots");
 __device__ __forceinline__ u32 t0_hash(u32 v) { return (v * 0x9E3779B1u) >> 26; }
 
+// PACKED (graphs with at most 2^26 nodes; distances are < 64): a label is ONE word, distance << 26 | node id, so the
+// extract-min compares 32-bit words from one array and the distance array (and its shared memory: one more CTA per SM)
+// goes away.  The unpacked variant serves bigger graphs.
+constexpr u32 T0_ID_BITS = 26, T0_ID_MASK = (1u << T0_ID_BITS) - 1u;
+template <bool PACKED>
 __global__ void __launch_bounds__(T0_THREADS) dijkstra_thread_kernel(SearchArgs a) {
     __shared__ u32 s_key[T0_ENTRIES][T0_THREADS];   // labelled node ids, in insertion order (labels never move)
-    __shared__ u8 s_dist[T0_ENTRIES][T0_THREADS];   // tentative distance of an open label, 0 once settled
+    __shared__ u8 s_dist[PACKED ? 1 : T0_ENTRIES][T0_THREADS];   // tentative distance of an open label, 0 once settled
     __shared__ u8 s_open[T0_ENTRIES][T0_THREADS];   // indices of the open labels (unordered)
     __shared__ u32 s_hash32[T0_HASH / 4][T0_THREADS];  // node id -> label index + 1 (open addressing, 0 = empty): one byte per
                                                        // slot, four slots of a thread per word so that a table is cleared
                                                        // with 16 stores; every access of a lane stays in its own bank
     const unsigned tid = threadIdx.x, lane = tid & 31;
-    const u32 flip = a.tie_flip;
+    const u32 flip = PACKED ? (a.tie_flip & T0_ID_MASK) : a.tie_flip;
     auto hash_slot_of = [&](u32 h) -> u8& { return reinterpret_cast<u8*>(&s_hash32[h >> 2][tid])[h & 3]; };
     unsigned long long st_settled = 0, st_relaxed = 0, st_cand = 0, st_searched = 0, st_trunc = 0, st_ovf = 0, st_labels = 0;
     u32 st_max_labels = 0, st_max_open = 0;
@@ -168,7 +176,7 @@ __global__ void __launch_bounds__(T0_THREADS) dijkstra_thread_kernel(SearchArgs 
 #pragma unroll
                 for (int h = 0; h < T0_HASH / 4; h++) s_hash32[h][tid] = 0;
                 s_key[0][tid] = src;
-                s_dist[0][tid] = 0;
+                if (!PACKED) s_dist[0][tid] = 0;
                 s_open[0][tid] = 0;
                 hash_slot_of(t0_hash(src)) = 1;
                 active = true;
@@ -180,17 +188,20 @@ __global__ void __launch_bounds__(T0_THREADS) dijkstra_thread_kernel(SearchArgs 
             u32 bi = 0;
             for (u32 i = 0; i < n_open; i++) {
                 const u32 l = s_open[i][tid];
-                const unsigned long long val = ((unsigned long long)s_dist[l][tid] << 32) | (s_key[l][tid] ^ flip);
+                const unsigned long long val = PACKED ? (unsigned long long)(s_key[l][tid] ^ flip)
+                                                      : ((unsigned long long)s_dist[l][tid] << 32) | (s_key[l][tid] ^ flip);
                 if (val < best) {
                     best = val;
                     bi = i;
                 }
             }
-            const u32 d = (u32)(best >> 32), v = (u32)best ^ flip;
-            {  // the winner leaves the open list and is marked settled
+            const u32 d = PACKED ? (u32)best >> T0_ID_BITS : (u32)(best >> 32);
+            const u32 v = PACKED ? ((u32)best ^ flip) & T0_ID_MASK : (u32)best ^ flip;
+            {  // the winner leaves the open list and is marked settled (distance 0: no relaxation, nw >= 1, compares smaller)
                 const u32 l = s_open[bi][tid];
                 s_open[bi][tid] = s_open[--n_open][tid];
-                s_dist[l][tid] = 0;  // settled: no relaxation (nw >= 1) compares smaller any more
+                if (PACKED) s_key[l][tid] = v;
+                else s_dist[l][tid] = 0;
             }
             n_settled++;
             if (v != src && ((a.bitmap[v >> 5] >> (v & 31)) & 1u)) a.records[t * a.cap + emitted++] = (u64)v | ((u64)d << 32);
@@ -202,12 +213,16 @@ __global__ void __launch_bounds__(T0_THREADS) dijkstra_thread_kernel(SearchArgs 
                 if (nw > a.max_weight || overflow) return;
                 // label of u: a few probes of the per-thread hash table instead of a scan over all labels
                 u32 h = t0_hash(u), j;
-                while ((j = hash_slot_of(h)) != 0 && s_key[j - 1][tid] != u) h = (h + 1) & (T0_HASH - 1);
-                if (j) {
-                    if (nw < s_dist[j - 1][tid]) s_dist[j - 1][tid] = (u8)nw;  // open label: decrease-key in place (settled ones hold 0)
+                while ((j = hash_slot_of(h)) != 0 && (PACKED ? s_key[j - 1][tid] & T0_ID_MASK : s_key[j - 1][tid]) != u) h = (h + 1) & (T0_HASH - 1);
+                if (j) {  // open label: decrease-key in place (settled ones hold distance 0)
+                    if (PACKED) {
+                        if (nw < (s_key[j - 1][tid] >> T0_ID_BITS)) s_key[j - 1][tid] = (nw << T0_ID_BITS) | u;
+                    } else if (nw < s_dist[j - 1][tid]) {
+                        s_dist[j - 1][tid] = (u8)nw;
+                    }
                 } else if (n < T0_ENTRIES) {
-                    s_key[n][tid] = u;
-                    s_dist[n][tid] = (u8)nw;
+                    s_key[n][tid] = PACKED ? (nw << T0_ID_BITS) | u : u;
+                    if (!PACKED) s_dist[n][tid] = (u8)nw;
                     s_open[n_open++][tid] = (u8)n;
                     hash_slot_of(h) = (u8)(++n);
                 } else {
@@ -581,11 +596,15 @@ void run_searches(mtg_ctx* ctx, const u32* bitmap, const u32* work_list, u64 n_w
     a.overflow_list = list0;
     a.overflow_count = counts;
     int occ = 0;
-    MTG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dijkstra_thread_kernel, T0_THREADS, 0));
+    // one-word labels whenever node ids fit 26 bits (MTG_T0_UNPACKED=1 forces the general kernel: tests)
+    const bool packed = ctx->N <= (u64(1) << T0_ID_BITS) && a.max_weight < 64 && !getenv("MTG_T0_UNPACKED");
+    if (packed) MTG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dijkstra_thread_kernel<true>, T0_THREADS, 0));
+    else MTG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dijkstra_thread_kernel<false>, T0_THREADS, 0));
     if (occ < 1) occ = 1;
     u32 grid = (u32)std::min<u64>((n_work + T0_THREADS - 1) / T0_THREADS, (u64)ctx->num_sms * occ);  // persistent CTAs
     MTG_CUDA(cudaEventRecord(ctx->ev2, s));
-    MTG_LAUNCH(ctx, dijkstra_thread_kernel, grid, T0_THREADS, 0, a);
+    if (packed) MTG_LAUNCH(ctx, dijkstra_thread_kernel<true>, grid, T0_THREADS, 0, a);
+    else MTG_LAUNCH(ctx, dijkstra_thread_kernel<false>, grid, T0_THREADS, 0, a);
     MTG_CUDA(cudaEventRecord(ctx->ev3, s));
     u32 h_counts[2] = {0, 0};
     MTG_CUDA(cudaMemcpyAsync(h_counts, counts, sizeof(u32), cudaMemcpyDeviceToHost, s));

@@ -195,6 +195,22 @@ def test_overflow_tier(mt, ctx):
     assert st["overflow_sources"] > 0, "tier 2 not exercised"
 
 
+@pytest.mark.parametrize("tie_desc", [0, 1])
+def test_tier0_unpacked_labels(mt, ctx, monkeypatch, tie_desc):
+    """Graphs with at most 2^26 nodes run the tier-0 search with one-word labels (distance << 26 | node id); bigger ones
+    with separate id / distance arrays.  MTG_T0_UNPACKED=1 forces the general kernel on a small input: same candidate
+    lists, same everything, under both tie orders of assumption P1."""
+    anc = tools.genome(30_000, 17, families=4, copies=4, min_len=40, max_len=400, divergence=0.03)
+    text, _, _ = tools.unitigs(tools.pangenome(anc, 12, 5, snp_site_rate=0.05, indel_site_rate=0.004), 19)
+    monkeypatch.setenv("MTG_T0_UNPACKED", "1")
+    ctx.set_option("p1_tie_desc", tie_desc)
+    try:
+        compare_all(mt, ctx, text, 19, "fasta", cap=8, opt={"p1_tie_desc": tie_desc} if tie_desc else None)
+        compare_all(mt, ctx, text, 19, "bcalm", cap=3, opt={"p1_tie_desc": tie_desc} if tie_desc else None)
+    finally:
+        ctx.set_option("p1_tie_desc", 0)
+
+
 def test_empty_and_degenerate_inputs(mt, ctx):
     compare_all(mt, ctx, b"", 5, "fasta")
     compare_all(mt, ctx, b">0\nACGTA\n", 5, "fasta")                # a single k-mer
