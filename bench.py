@@ -460,9 +460,9 @@ def run_ours(args):
 
 SEARCH_KERNEL = "dijkstra_thread_kernel"
 # (workload, scale) -> DRAM bytes (read + write) of one main launch of dijkstra_thread_kernel, from ncu --set full
-NCU_DRAM_BYTES = {("chr1", 1.0): 100583680 + 120263168}  # profiles/round2_ncu_full_dijkstra_thread_kernel_chr1.txt
+NCU_DRAM_BYTES = {("chr1", 1.0): 99224576 + 119722496}  # profiles/round2_ncu_full_dijkstra_thread_kernel_chr1.txt
 # same captures: L2 sectors the kernel read (lts__t_sectors_srcunit_tex_op_read.sum), i.e. the sector-granular traffic
-NCU_L2_READ_SECTORS = {("chr1", 1.0): 110160889}
+NCU_L2_READ_SECTORS = {("chr1", 1.0): 109156110}
 # random 32-byte-sector gather ceilings measured on a B200 of this pool with scripts/micro/gather_ceiling.cu
 # (profiles/round1_gather_ceiling.jsonl): footprint 8 GiB (HBM) and 32 MiB (L2-resident), independent gathers
 GATHER_CEILING_GBPS = {"hbm_random": 1174.8, "l2_resident": 6663.9}
