@@ -238,10 +238,15 @@ __global__ void __launch_bounds__(TB) compact_indices(const u32* __restrict__ fl
     u64 i = (u64)blockIdx.x * TB + threadIdx.x;
     if (i < n && flag[i]) out[pos[i]] = (u32)i;
 }
-// wait-list entries of a pending source: mirror(src) + every entry that is open at the start of the phase
+// Wait lists by counting: a pending source waits on mirror(src) and on every entry of its list that is open at the start
+// of the phase.  Pass 1 counts per source (the 64-bit guard of the total) and per node (the list lengths); after the scan
+// of the lengths pass 2 drops every source into its nodes' lists through per-node cursors -- in arbitrary order -- and pass
+// 3 sorts every list in place (lists hold a handful of sources; the few long ones get a CTA each).  This replaces a
+// three-pass radix sort of all (node, source) pairs.
 __global__ void __launch_bounds__(TB)
     count_waits(const u32* __restrict__ pend, const u32* __restrict__ n_pend_dev, u64 S, const u64* __restrict__ list_addr,
-                const u32* __restrict__ list_meta, const i32* __restrict__ mult, u32* __restrict__ cnt) {
+                const u32* __restrict__ list_meta, const i32* __restrict__ mult, const u32* __restrict__ sources,
+                const u32* __restrict__ mirror, u32* __restrict__ cnt, u32* __restrict__ deg) {
     u32 r = blockIdx.x * TB + threadIdx.x;
     if (r >= S) return;
     if (r >= *n_pend_dev) {  // launched over all S slots: the host learns n_pend together with the wait-list total
@@ -252,32 +257,74 @@ __global__ void __launch_bounds__(TB)
     const u64* list = reinterpret_cast<const u64*>(list_addr[i]);
     const u32 count = list_meta[i] & META_COUNT;
     u32 c = 1;
-    for (u32 p = 0; p < count; p++) c += mult[(u32)list[p]] > 0;
+    atomicAdd(&deg[mirror[sources[i]]], 1u);
+    for (u32 p = 0; p < count; p++) {
+        const u32 x = (u32)list[p];
+        if (mult[x] > 0) {
+            atomicAdd(&deg[x], 1u);
+            c++;
+        }
+    }
     cnt[r] = c;
 }
 __global__ void __launch_bounds__(TB)
-    write_waits(const u32* __restrict__ pend, u32 n_pend, const u64* __restrict__ list_addr, const u32* __restrict__ list_meta,
-                const i32* __restrict__ mult, const u32* __restrict__ sources, const u32* __restrict__ mirror,
-                const u32* __restrict__ off, u32* __restrict__ key, u32* __restrict__ val, u32* __restrict__ deg) {
+    fill_waits(const u32* __restrict__ pend, u32 n_pend, const u64* __restrict__ list_addr, const u32* __restrict__ list_meta,
+               const i32* __restrict__ mult, const u32* __restrict__ sources, const u32* __restrict__ mirror, u32* __restrict__ cursor,
+               u32* __restrict__ rev) {
     u32 r = blockIdx.x * TB + threadIdx.x;
     if (r >= n_pend) return;
     const u32 i = pend[r];
     const u64* list = reinterpret_cast<const u64*>(list_addr[i]);
     const u32 count = list_meta[i] & META_COUNT;
-    u32 o = off[r];
-    const u32 M = mirror[sources[i]];
-    key[o] = M;
-    val[o] = i;
-    atomicAdd(&deg[M], 1u);
-    o++;
+    rev[atomicAdd(&cursor[mirror[sources[i]]], 1u)] = i;
     for (u32 p = 0; p < count; p++) {
         const u32 x = (u32)list[p];
-        if (mult[x] > 0) {
-            key[o] = x;
-            val[o] = i;
-            atomicAdd(&deg[x], 1u);
-            o++;
+        if (mult[x] > 0) rev[atomicAdd(&cursor[x], 1u)] = i;
+    }
+}
+constexpr u32 WAIT_LONG = 48;  // lists longer than this are sorted by a CTA
+// ascending source index inside every list (equal entries -- mirror(src) that is also an entry of its own list -- stay
+// next to each other, which is all the order the matching needs)
+__global__ void __launch_bounds__(TB)
+    sort_wait_lists(const u32* __restrict__ rev_ptr, u64 N, u32* __restrict__ rev, u32* __restrict__ long_nodes, u32* __restrict__ n_long) {
+    const u64 x = (u64)blockIdx.x * TB + threadIdx.x;
+    if (x >= N) return;
+    const u32 b = rev_ptr[x], e = rev_ptr[x + 1];
+    const u32 len = e - b;
+    if (len < 2) return;
+    if (len > WAIT_LONG) {
+        long_nodes[atomicAdd(n_long, 1u)] = (u32)x;
+        return;
+    }
+    for (u32 p = b + 1; p < e; p++) {  // insertion sort, in place
+        const u32 v = rev[p];
+        u32 q = p;
+        while (q > b && rev[q - 1] > v) {
+            rev[q] = rev[q - 1];
+            q--;
         }
+        rev[q] = v;
+    }
+}
+// one CTA per long list: rank by counting (ties by position), through a scratch copy
+__global__ void __launch_bounds__(TB)
+    sort_long_wait_lists(const u32* __restrict__ rev_ptr, const u32* __restrict__ long_nodes, const u32* __restrict__ n_long,
+                         u32* __restrict__ rev, u32* __restrict__ scratch) {
+    for (u32 w = blockIdx.x; w < *n_long; w += gridDim.x) {
+        const u32 x = long_nodes[w];
+        const u32 b = rev_ptr[x], e = rev_ptr[x + 1];
+        for (u32 p = b + threadIdx.x; p < e; p += TB) scratch[p] = rev[p];
+        __syncthreads();
+        for (u32 p = b + threadIdx.x; p < e; p += TB) {
+            const u32 v = scratch[p];
+            u32 rank = 0;
+            for (u32 q = b; q < e; q++) {
+                const u32 o = scratch[q];
+                rank += (o < v) || (o == v && q < p);
+            }
+            rev[b + rank] = v;
+        }
+        __syncthreads();
     }
 }
 __global__ void __launch_bounds__(TB) final_counts(const u32* __restrict__ trip_cnt, u64 S, u64 lo, u64 hi, u32* __restrict__ out) {
@@ -344,12 +391,6 @@ __global__ void __launch_bounds__(1024) sum_u32_to_u64(const u32* __restrict__ i
     }
 }
 
-int bits_for(u64 n) {
-    int b = 1;
-    while (b < 32 && (1ull << b) < n) b++;
-    return b;
-}
-
 }  // namespace
 
 void greedy_match(mtg_ctx* ctx, const u64* d_records_all, const u32* d_meta_all, u32 shard_count) {
@@ -383,7 +424,7 @@ void greedy_match(mtg_ctx* ctx, const u64* d_records_all, const u32* d_meta_all,
     DBuf<i32>& mult = ctx->final_mult;  // ends up as the leftover imbalance the tail starts from
     DBuf<u64> list_addr;
     DBuf<u32> list_meta, max_trip, trip_off, trip_cnt, trip_slots, flag, pos, pend, small, work_list, open_bits, pool_meta;
-    DBuf<u32> wait_cnt, wait_off, key_a, key_b, val_a, val_b, rev_ptr, cur, done;
+    DBuf<u32> wait_cnt, rev, rev_scratch, long_nodes, rev_ptr, cur, done;
     DBuf<unsigned long long> big;  // [0] hand-out counter, [1] retries
     std::vector<DBuf<u64>> pools;
     list_addr.resize(S, s);
@@ -396,7 +437,6 @@ void greedy_match(mtg_ctx* ctx, const u64* d_records_all, const u32* d_meta_all,
     pend.resize(S, s);
     done.resize(S, s);
     wait_cnt.resize(S, s);
-    wait_off.resize(S, s);
     rev_ptr.resize(N + 1, s);
     cur.resize(N + 1, s);
     small.resize(16, s);  // [0] pending count, [3] min_insufficient, [5..7] scan totals, [8] error
@@ -448,9 +488,11 @@ void greedy_match(mtg_ctx* ctx, const u64* d_records_all, const u32* d_meta_all,
         MTG_LAUNCH(ctx, flag_pending, grid_for(S, TB), TB, 0, list_meta.p, S, lo, flag.p);
         exclusive_sum_u32(ctx, flag.p, pos.p, S, small.p + 0);
         MTG_LAUNCH(ctx, compact_indices, grid_for(S, TB), TB, 0, flag.p, pos.p, S, pend.p);
-        // wait lists: (node, source) pairs written in source order, stable sort by node => ascending sources per node
-        MTG_LAUNCH(ctx, count_waits, grid_for(S, TB), TB, 0, pend.p, small.p + 0, S, list_addr.p, list_meta.p, mult.p, wait_cnt.p);
-        exclusive_sum_u32(ctx, wait_cnt.p, wait_off.p, S, small.p + 6);
+        // wait lists: lengths per node counted here, filled and sorted below (ascending sources per node)
+        MTG_CUDA(cudaMemsetAsync(cur.p, 0, (N + 1) * sizeof(u32), s));  // used as the length histogram first
+        MTG_LAUNCH(ctx, count_waits, grid_for(S, TB), TB, 0, pend.p, small.p + 0, S, list_addr.p, list_meta.p, mult.p, ctx->sources.p,
+                   ctx->mirror.p, wait_cnt.p, cur.p);
+        exclusive_sum_u32(ctx, cur.p, rev_ptr.p, N + 1, small.p + 6);  // total = rev_ptr[N]
         // the 32-bit offsets are safe if even the worst case fits; otherwise the same total is taken in 64 bits
         const bool need_guard = (u64)S * ((u64)cap + 1) >= 0xFFFFFFF0ull;
         if (need_guard) MTG_LAUNCH(ctx, sum_u32_to_u64, 1, 1024, 0, wait_cnt.p, S, big.p + 2);
@@ -465,16 +507,17 @@ void greedy_match(mtg_ctx* ctx, const u64* d_records_all, const u32* d_meta_all,
         trip_cnt.zero(s);
         u32 min_insuff = NO_INDEX;
         if (n_pend) {
-            key_a.resize(P, s);
-            key_b.resize(P, s);
-            val_a.resize(P, s);
-            val_b.resize(P, s);
-            MTG_CUDA(cudaMemsetAsync(cur.p, 0, (N + 1) * sizeof(u32), s));  // used as the degree histogram first
-            MTG_LAUNCH(ctx, write_waits, grid_for(n_pend, TB), TB, 0, pend.p, n_pend, list_addr.p, list_meta.p, mult.p, ctx->sources.p,
-                       ctx->mirror.p, wait_off.p, key_a.p, val_a.p, cur.p);
-            exclusive_sum_u32(ctx, cur.p, rev_ptr.p, N + 1, nullptr);
-            MTG_CUDA(cudaMemcpyAsync(cur.p, rev_ptr.p, (N + 1) * sizeof(u32), cudaMemcpyDeviceToDevice, s));
-            const int which = radix_sort_pairs_u32(ctx, key_a.p, key_b.p, val_a.p, val_b.p, P, bits_for(N));
+            rev.resize(P, s);
+            MTG_CUDA(cudaMemcpyAsync(cur.p, rev_ptr.p, (N + 1) * sizeof(u32), cudaMemcpyDeviceToDevice, s));  // fill cursors
+            MTG_LAUNCH(ctx, fill_waits, grid_for(n_pend, TB), TB, 0, pend.p, n_pend, list_addr.p, list_meta.p, mult.p, ctx->sources.p,
+                       ctx->mirror.p, cur.p, rev.p);
+            long_nodes.resize(P / WAIT_LONG + 2, s);  // at most P / WAIT_LONG lists are longer than WAIT_LONG
+            MTG_CUDA(cudaMemsetAsync(small.p + 9, 0, sizeof(u32), s));
+            MTG_LAUNCH(ctx, sort_wait_lists, grid_for(N, TB), TB, 0, rev_ptr.p, N, rev.p, long_nodes.p, small.p + 9);
+            rev_scratch.resize(P, s);
+            MTG_LAUNCH(ctx, sort_long_wait_lists, (u32)std::min<u64>(P / WAIT_LONG + 1, (u64)ctx->num_sms * 4), TB, 0, rev_ptr.p, long_nodes.p,
+                       small.p + 9, rev.p, rev_scratch.p);
+            MTG_CUDA(cudaMemcpyAsync(cur.p, rev_ptr.p, (N + 1) * sizeof(u32), cudaMemcpyDeviceToDevice, s));  // first unfinished position per list
             done.zero(s);
             u32 init_small[2] = {NO_INDEX, 0};
             MTG_CUDA(cudaMemcpyAsync(small.p + 3, init_small, sizeof(u32), cudaMemcpyHostToDevice, s));
@@ -488,7 +531,7 @@ void greedy_match(mtg_ctx* ctx, const u64* d_records_all, const u32* d_meta_all,
             a.pend = pend.p;
             a.n_pend = n_pend;
             a.rev_ptr = rev_ptr.p;
-            a.rev = which ? val_b.p : val_a.p;
+            a.rev = rev.p;
             a.cur = cur.p;
             a.done = done.p;
             a.trip_off = trip_off.p;
@@ -580,7 +623,7 @@ void greedy_match(mtg_ctx* ctx, const u64* d_records_all, const u32* d_meta_all,
     list_addr.release(s);
     big.release(s);
     for (DBuf<u32>* b : {&list_meta, &max_trip, &trip_off, &trip_cnt, &trip_slots, &flag, &pos, &pend, &small, &work_list, &open_bits,
-                         &pool_meta, &wait_cnt, &wait_off, &key_a, &key_b, &val_a, &val_b, &rev_ptr, &cur, &done})
+                         &pool_meta, &wait_cnt, &rev, &rev_scratch, &long_nodes, &rev_ptr, &cur, &done})
         b->release(s);
     ctx->have_triples = true;
     ctx->have_walks = false;

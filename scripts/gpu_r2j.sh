@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 T=${1:-r2j}
 timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/${T}_tests.log 2>&1; echo "tests rc=$?"; tail -3 gpurun_out/${T}_tests.log
 python -c "import bench; bench.make_workload('chr1', None)" > /dev/null 2>&1
-for v in main t64 e44; do
+for v in main; do
   if [ $v = main ]; then unset MTG_LIB_PATH; else export MTG_LIB_PATH=$GRAFT_REPO_ROOT/build_variants/$v.so; fi
   timeout 600 python bench.py --steps 6 --warmup 3 2>/dev/null | python -c "
 import json,sys
