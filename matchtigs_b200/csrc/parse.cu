@@ -17,6 +17,28 @@
 
 namespace mtg {
 
+// 64-bit totals of per-chunk count arrays: the parser's offsets are 32-bit sums, this is their overflow guard.  (Kept outside
+// the anonymous namespace below, whose kernels tests/test_parse_emulation.py compiles as host code.)
+static __global__ void __launch_bounds__(256) sum_counts_u64(const u32* __restrict__ a, const u32* __restrict__ b, const u32* __restrict__ c, u64 n,
+                                                      unsigned long long* __restrict__ out) {
+    unsigned long long sa = 0, sb = 0, sc = 0;
+    for (u64 i = (u64)blockIdx.x * 256 + threadIdx.x; i < n; i += (u64)gridDim.x * 256) {
+        sa += a[i];
+        sb += b[i];
+        if (c) sc += c[i];
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        sa += __shfl_down_sync(0xffffffffu, sa, o);
+        sb += __shfl_down_sync(0xffffffffu, sb, o);
+        sc += __shfl_down_sync(0xffffffffu, sc, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (sa) atomicAdd(out, sa);
+        if (sb) atomicAdd(out + 1, sb);
+        if (sc) atomicAdd(out + 2, sc);
+    }
+}
+
 namespace {
 
 constexpr int TB = 256;
@@ -259,27 +281,6 @@ __global__ void __launch_bounds__(TB) weights_from_offsets(const u64* __restrict
         w[u] = 1;
     } else {
         w[u] = len + 1 - k;
-    }
-}
-
-// 64-bit totals of two per-chunk count arrays: the offsets below are 32-bit sums, this is their overflow guard
-__global__ void __launch_bounds__(TB) sum_counts_u64(const u32* __restrict__ a, const u32* __restrict__ b, const u32* __restrict__ c, u64 n,
-                                                      unsigned long long* __restrict__ out) {
-    unsigned long long sa = 0, sb = 0, sc = 0;
-    for (u64 i = (u64)blockIdx.x * TB + threadIdx.x; i < n; i += (u64)gridDim.x * TB) {
-        sa += a[i];
-        sb += b[i];
-        if (c) sc += c[i];
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-        sa += __shfl_down_sync(0xffffffffu, sa, o);
-        sb += __shfl_down_sync(0xffffffffu, sb, o);
-        sc += __shfl_down_sync(0xffffffffu, sc, o);
-    }
-    if ((threadIdx.x & 31) == 0) {
-        if (sa) atomicAdd(out, sa);
-        if (sb) atomicAdd(out + 1, sb);
-        if (sc) atomicAdd(out + 2, sc);
     }
 }
 
