@@ -269,24 +269,66 @@ __global__ void __launch_bounds__(RS_THREADS)
         __syncwarp();
     }
     __syncthreads();
-    {  // exclusive prefix over warps for digit == threadIdx.x, seeded with the global base of (digit, tile)
-        u32 run = my_base;
+    if constexpr (NW == 1) {
+        // One-word keys: the tile is put in output order in shared memory first (tile-local position = first position of the
+        // digit inside the tile + the warp's offset inside the digit + rank), then written out by consecutive threads:
+        // elements of one digit go to consecutive global addresses, so a warp's store covers whole sectors instead of up to
+        // 32 different ones.
+        __shared__ KW s_key[RS_TILE];
+        __shared__ u32 s_val[RS_TILE];
+        __shared__ u32 lbase[256], gbase[256];
+        {
+            u32 run = 0;
 #pragma unroll
-        for (int w = 0; w < RS_WARPS; w++) {
-            u32 c = cnt[w][threadIdx.x];
-            cnt[w][threadIdx.x] = run;
-            run += c;
+            for (int w = 0; w < RS_WARPS; w++) {
+                u32 c = cnt[w][threadIdx.x];
+                cnt[w][threadIdx.x] = run;  // offset of warp w inside the digit, tile-local
+                run += c;
+            }
+            u32 total;
+            lbase[threadIdx.x] = block_exclusive<u32>(run, OpAdd(), &total);
+            gbase[threadIdx.x] = my_base;
         }
-    }
-    __syncthreads();
+        __syncthreads();
 #pragma unroll
-    for (int r = 0; r < RS_ROWS; r++) {
-        size_t i = chunk + (size_t)r * 32 + lane;
-        if (i < n) {
-            size_t pos = (size_t)cnt[warp][dig[r]] + rank[r];
-            k0_out[pos] = k0[r];
-            if (NW == 2) k1_out[pos] = k1[r];
-            v_out[pos] = val[r];
+        for (int r = 0; r < RS_ROWS; r++) {
+            size_t i = chunk + (size_t)r * 32 + lane;
+            if (i < n) {
+                const u32 p = lbase[dig[r]] + cnt[warp][dig[r]] + rank[r];
+                s_key[p] = k0[r];
+                s_val[p] = val[r];
+            }
+        }
+        __syncthreads();
+        const size_t tile_base = (size_t)blockIdx.x * RS_TILE;
+        const u32 n_tile = (u32)min((size_t)RS_TILE, n - tile_base);
+        for (u32 p = threadIdx.x; p < n_tile; p += RS_THREADS) {
+            const KW kw = s_key[p];
+            const u32 d = (u32)(kw >> shift) & 255u;
+            const size_t pos = (size_t)gbase[d] + (p - lbase[d]);
+            k0_out[pos] = kw;
+            v_out[pos] = s_val[p];
+        }
+    } else {
+        {  // exclusive prefix over warps for digit == threadIdx.x, seeded with the global base of (digit, tile)
+            u32 run = my_base;
+#pragma unroll
+            for (int w = 0; w < RS_WARPS; w++) {
+                u32 c = cnt[w][threadIdx.x];
+                cnt[w][threadIdx.x] = run;
+                run += c;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < RS_ROWS; r++) {
+            size_t i = chunk + (size_t)r * 32 + lane;
+            if (i < n) {
+                size_t pos = (size_t)cnt[warp][dig[r]] + rank[r];
+                k0_out[pos] = k0[r];
+                if (NW == 2) k1_out[pos] = k1[r];
+                v_out[pos] = val[r];
+            }
         }
     }
 }

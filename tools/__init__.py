@@ -35,7 +35,7 @@ def _take(p, n) -> bytes:
     if not p:
         raise RuntimeError("synth tool failed (bad k or non-ACGT input)")
     try:
-        return C.string_at(p, n.value)
+        return bytes((C.c_char * n.value).from_address(p))  # (string_at takes a C int: texts of 2 GiB and more overflow it)
     finally:
         lib().mts_free(p)
 
