@@ -1024,13 +1024,32 @@ void finish_walks(mtg_ctx* ctx) {
     // The walk works on a copy inside its huge-page arena (page-locking the arena itself loses the huge pages); copied in
     // cache-sized chunks by a few threads: one big memcpy would use non-temporal stores and leave everything cold.
     const int copy_threads = host_threads();
-    auto warm_copy = [copy_threads](void* dst, const void* src, size_t bytes) {
-        const size_t chunk = 256 << 10;  // (64 KB .. 8 MB measured alike: the phase waits for the link, not for the copy)
+    const bool stream_copy = !(getenv("MTG_TAIL_COPY") && getenv("MTG_TAIL_COPY")[0] == 'm');  // A/B: MTG_TAIL_COPY=memcpy
+    auto warm_copy = [copy_threads, stream_copy](void* dst, const void* src, size_t bytes) {
+        const size_t chunk = 256 << 10;  // (64 KB .. 8 MB measured alike)
         const i64 n_chunks = (i64)((bytes + chunk - 1) / chunk);
 #pragma omp parallel for schedule(static) num_threads(copy_threads) if (bytes > (8u << 20))
         for (i64 c = 0; c < n_chunks; c++) {
-            const size_t o = (size_t)c * chunk;
-            memcpy((char*)dst + o, (const char*)src + o, std::min(chunk, bytes - o));
+            const size_t o = (size_t)c * chunk, len = std::min(chunk, bytes - o);
+#if defined(__x86_64__)
+            // Streaming stores: the arena lines are written without being read first (a third less memory traffic than a
+            // plain copy of half a gigabyte, which cannot stay in the caches anyway).  Records are 64-byte aligned.
+            if (stream_copy && len % 64 == 0 && (reinterpret_cast<uintptr_t>((char*)dst + o) & 15u) == 0) {
+                const __m128i* a = reinterpret_cast<const __m128i*>((const char*)src + o);
+                __m128i* b = reinterpret_cast<__m128i*>((char*)dst + o);
+                for (size_t q = 0; q < len / 16; q += 4) {
+                    const __m128i x0 = _mm_loadu_si128(a + q), x1 = _mm_loadu_si128(a + q + 1), x2 = _mm_loadu_si128(a + q + 2),
+                                  x3 = _mm_loadu_si128(a + q + 3);
+                    _mm_stream_si128(b + q, x0);
+                    _mm_stream_si128(b + q + 1, x1);
+                    _mm_stream_si128(b + q + 2, x2);
+                    _mm_stream_si128(b + q + 3, x3);
+                }
+                _mm_sfence();
+                continue;
+            }
+#endif
+            memcpy((char*)dst + o, (const char*)src + o, len);
         }
     };
     // while the records are in flight: dummy weights (matching dummies carry their distance, breaking dummies weigh k)
