@@ -280,11 +280,11 @@ def run_ours(args):
         phase_s["(parse, device)"] = phase_s.get("(parse, device)", 0.0) + dg["build_ms"]["parse"] * 1e-3
         if world == 1:
             call("dijkstra", ctx.dijkstra_candidates, CAP, 0, 1)
-            call("match", ctx.greedy_match)
+            call("match", ctx.greedy_match, export=False)
         else:
             call("dijkstra", ctx.dijkstra_candidates, CAP, rank, world)
             rec_all, meta_all = call("all_gather", ctx.allgather_candidates)  # ncclAllGather inside the library, over NVLink
-            call("match", ctx.greedy_match, rec_all, meta_all, world)
+            call("match", ctx.greedy_match, rec_all, meta_all, world, export=False)
         if rank == 0:
             call("tail", ctx.finish_walks)
         if world == 1:

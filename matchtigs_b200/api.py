@@ -167,11 +167,16 @@ class Context:
         return nodes, dists, meta
 
     # ---- step 3 ----
-    def greedy_match(self, records_ptr: int | None = None, meta_ptr: int | None = None, shard_count: int = 1) -> np.ndarray:
+    def greedy_match(self, records_ptr: int | None = None, meta_ptr: int | None = None, shard_count: int = 1,
+                     export: bool = True) -> np.ndarray | int:
+        """Runs the matching.  Returns the (out node, in node, distance) triples, or with ``export=False`` only their number
+        (the triples stay inside the context for ``finish_walks``; copying 12 bytes per pair out is the caller's choice)."""
         n = C.c_uint64()
         self._check(self._l.mtg_greedy_match(self._h, C.c_void_p(records_ptr or 0), C.c_void_p(meta_ptr or 0), shard_count,
                                              C.byref(n)))
-        tr = np.zeros(3 * n.value, np.uint32)
+        if not export:
+            return n.value
+        tr = np.empty(3 * n.value, np.uint32)
         self._check(self._l.mtg_triples_export(self._h, _ptr(tr)))
         return tr.reshape(-1, 3)
 
@@ -384,7 +389,7 @@ class GreedytigAlgorithm:
     def compute_tigs(graph: Graph, configuration: GreedytigAlgorithmConfiguration) -> list[np.ndarray]:
         ctx = graph.ctx
         ctx.dijkstra_candidates(configuration.candidate_cap, 0, 1)
-        ctx.greedy_match()
+        ctx.greedy_match(export=False)
         ctx.finish_walks()
         return ctx.walks()
 
