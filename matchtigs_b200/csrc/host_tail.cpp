@@ -883,6 +883,8 @@ void walk_and_break(const WalkInput& in, TailOutput& out, TailScratch& scratch) 
         for (i64 i = 0; i < n; i++) we[i] = se[ws[i] & SLOT_MASK];
     }
     double t4 = now_ms();
+    if (trace_slow_calls() && getenv("MTG_TRACE_ALL"))
+        fprintf(stderr, "[mtg trace] breaking: cycle order + cuts + piece emission %.2f ms, slot -> edge gather %.2f ms\n", ms_break, t4 - tt);
     out.ms_break = ms_break + (t4 - tt);
     out.ms_walk = t4 - t3 - out.ms_break;
 }
