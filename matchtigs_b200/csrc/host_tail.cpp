@@ -398,6 +398,8 @@ struct RunIO {
     u64 probe_hist[5][40];  // 16-tick buckets; [4] = the probe itself on a line that is certainly in L1
     u64 probe_tick;
     bool probe;
+    u32 spin;
+    u64 spin_sink;
 };
 
 // first unused slot of the node with handle h (NONE32: exhausted); *more = the node owns further unused slots behind it
@@ -425,8 +427,11 @@ static inline u32 first_unused_of(const WalkRec* recs, const u64* used, u32 h, b
 // Follows first-unused out-edges from slot `s` (leaving the node with handle from_h) until the walk is stuck.
 // HINTS: the records carry their lookahead levels.  PF: prefetch hint (0 = t0, 1 = nta, 2 = t2).  NTS: the queues are
 // appended with non-temporal stores.  DIAG: statistics and latency probes.
+// (No SLP vectorisation here: the compiler would fuse the fixed-length shift of the chain arrays into 16-byte loads that
+// overlap the 4-byte stores of the step before -- a store-forwarding failure on the loop-carried path of every step,
+// each one waiting for the store buffer to drain.)
 template <bool HINTS, int PF, bool NTS, bool DIAG>
-__attribute__((noinline)) static void walk_run(RunIO& io, u32 s, u32 from_h) {
+__attribute__((noinline, optimize("no-tree-slp-vectorize", "no-tree-vectorize"))) static void walk_run(RunIO& io, u32 s, u32 from_h) {
     const WalkRec* const recs = io.recs;
     u64* const used = io.used;
     u32* const q_slot = io.q_slot;
@@ -505,7 +510,7 @@ __attribute__((noinline)) static void walk_run(RunIO& io, u32 s, u32 from_h) {
             const u32 sl = peek(src.h[(four ? walk_level_four(L - b) : walk_level_two(L - b)) + idx], &j);
             if (sl == NONE32) break;
             prefetch_rec(&recs[sl]);
-            if (WALK_DEPTH >= 5) __builtin_prefetch(reinterpret_cast<const char*>(&recs[sl]) + 64);
+            if (WALK_DEPTH >= 5) prefetch_rec(reinterpret_cast<const char*>(&recs[sl]) + 64);
             P[L] = sl, Q[L] = j, have = L;
             open_end = j < 2;
             idx = 2 * idx + j;
@@ -562,6 +567,7 @@ __attribute__((noinline)) static void walk_run(RunIO& io, u32 s, u32 from_h) {
                 const u32 sl = peek(hh, &j);
                 if (sl != NONE32) {
                     prefetch_rec(&recs[sl]);
+                    if (WALK_DEPTH >= 5) prefetch_rec(reinterpret_cast<const char*>(&recs[sl]) + 64);  // 128-byte records: both lines
                     P[WALK_DEPTH] = sl, Q[WALK_DEPTH] = j, have = WALK_DEPTH;
                 }
             } else {
@@ -582,7 +588,14 @@ __attribute__((noinline)) static void walk_run(RunIO& io, u32 s, u32 from_h) {
                 else io.dg_nohint++;
             }
         }
-        if (DIAG) io.dg_steps++;
+        if (DIAG) {
+            io.dg_steps++;
+            // experiment (MTG_WALK_SPIN=n): n dependent multiplies per step, off the walk's own dependency chain -- does extra
+            // core work lengthen a step (core-bound) or disappear in the wait for memory?
+            u64 x = io.probe_tick | 1;
+            for (u32 i = 0; i < io.spin; i++) x = x * 0x9E3779B97F4A7C15ull + i;
+            io.spin_sink += x;
+        }
         from_h = c;
         s = nxt;
     }
@@ -641,7 +654,7 @@ void walk_and_break(const WalkInput& in, TailOutput& out, TailScratch& scratch) 
     const int pf_kind = pf_env ? (pf_env[0] == 'n' ? 1 : pf_env[0] == '2' ? 2 : 0) : 0;
     const char* nts_env = getenv("MTG_WALK_NTSTORE");
     const bool nt_store = !(nts_env && nts_env[0] == '0');
-    const bool diag = trace_slow_calls() || getenv("MTG_WALK_PROBE") != nullptr;
+    const bool diag = trace_slow_calls() || getenv("MTG_WALK_PROBE") != nullptr || getenv("MTG_WALK_SPIN") != nullptr;
     const WalkRunFn run = pick_walk_run(use_hints, pf_kind, nt_store, diag);
     RunIO io{};
     io.recs = recs;
@@ -649,6 +662,7 @@ void walk_and_break(const WalkInput& in, TailOutput& out, TailScratch& scratch) 
     io.n_sources = getenv("MTG_WALK_SOURCES") ? atoi(getenv("MTG_WALK_SOURCES")) : 2;
     io.fast_path = !(getenv("MTG_WALK_FAST") && getenv("MTG_WALK_FAST")[0] == '0');
     io.probe = getenv("MTG_WALK_PROBE") != nullptr;
+    io.spin = getenv("MTG_WALK_SPIN") ? (u32)atoi(getenv("MTG_WALK_SPIN")) : 0;
     struct DiagAtExit {
         const RunIO* io;
         bool on;
