@@ -645,13 +645,15 @@ void walk_and_break(const WalkInput& in, TailOutput& out, TailScratch& scratch) 
         size_t ci, ce;   // children of this block: children[ci, ce)
     };
     std::vector<Frame> stack;
-    // Queue appends use non-temporal stores: the queues are not read again during the walk, and kept out of L2 they leave
-    // it to the used-slot bitset (bench box, chr1: 44 -> 42 ns per step).  MTG_WALK_NTSTORE=0, MTG_WALK_PREFETCH=nta|2,
-    // MTG_WALK_FAST=0, MTG_WALK_SOURCES=n and MTG_TAIL_NOHINT=1 are A/B switches; MTG_TRACE / MTG_WALK_PROBE select the
-    // instantiation with statistics and latency probes.
+    // Records are fetched with the non-temporal hint and the queues appended with non-temporal stores: neither is touched
+    // again during the walk, and kept out of L2 they leave it to the used-slot bitset, whose words sit on the path from
+    // "record in hand" to "next prefetch issued" (bench boxes, chr1: prefetchnta 37.3 against 40.6 ns per step with
+    // prefetcht0; the pangenome, whose bitset is a third of the size, does not care).  MTG_WALK_PREFETCH=t0|2,
+    // MTG_WALK_NTSTORE=0, MTG_WALK_FAST=0, MTG_WALK_SOURCES=n and MTG_TAIL_NOHINT=1 are A/B switches; MTG_TRACE /
+    // MTG_WALK_PROBE / MTG_WALK_SPIN select the instantiation with statistics, latency probes and the spin experiment.
     const bool use_hints = in.hints && !getenv("MTG_TAIL_NOHINT");
     const char* pf_env = getenv("MTG_WALK_PREFETCH");
-    const int pf_kind = pf_env ? (pf_env[0] == 'n' ? 1 : pf_env[0] == '2' ? 2 : 0) : 0;
+    const int pf_kind = pf_env ? (pf_env[0] == 'n' ? 1 : pf_env[0] == '2' ? 2 : 0) : 1;
     const char* nts_env = getenv("MTG_WALK_NTSTORE");
     const bool nt_store = !(nts_env && nts_env[0] == '0');
     const bool diag = trace_slow_calls() || getenv("MTG_WALK_PROBE") != nullptr || getenv("MTG_WALK_SPIN") != nullptr;
