@@ -653,7 +653,8 @@ void walk_and_break(const WalkInput& in, TailOutput& out, TailScratch& scratch) 
     // MTG_WALK_PROBE / MTG_WALK_SPIN select the instantiation with statistics, latency probes and the spin experiment.
     const bool use_hints = in.hints && !getenv("MTG_TAIL_NOHINT");
     const char* pf_env = getenv("MTG_WALK_PREFETCH");
-    const int pf_kind = pf_env ? (pf_env[0] == 'n' ? 1 : pf_env[0] == '2' ? 2 : 0) : 1;
+    const bool beyond_caches = in.n_slots * sizeof(WalkRec) > (size_t(64) << 20);  // (small record arrays stay cached: keep them there)
+    const int pf_kind = pf_env ? (pf_env[0] == 'n' ? 1 : pf_env[0] == '2' ? 2 : 0) : (beyond_caches ? 1 : 0);
     const char* nts_env = getenv("MTG_WALK_NTSTORE");
     const bool nt_store = !(nts_env && nts_env[0] == '0');
     const bool diag = trace_slow_calls() || getenv("MTG_WALK_PROBE") != nullptr || getenv("MTG_WALK_SPIN") != nullptr;
@@ -1042,7 +1043,10 @@ void finish_walks(mtg_ctx* ctx) {
     // The walk works on a copy inside its huge-page arena (page-locking the arena itself loses the huge pages); copied in
     // cache-sized chunks by a few threads: one big memcpy would use non-temporal stores and leave everything cold.
     const int copy_threads = host_threads();
-    const bool stream_copy = !(getenv("MTG_TAIL_COPY") && getenv("MTG_TAIL_COPY")[0] == 'm');  // A/B: MTG_TAIL_COPY=memcpy
+    // streaming stores only for record arrays that cannot stay in the caches anyway: a small graph's records are copied
+    // with plain stores and are warm when the walk starts (E. coli-size: 0.20 instead of 0.55 ms of walk)
+    const bool stream_copy = tr.n_slots * sizeof(WalkRec) > (size_t(64) << 20) &&
+                             !(getenv("MTG_TAIL_COPY") && getenv("MTG_TAIL_COPY")[0] == 'm');  // A/B: MTG_TAIL_COPY=memcpy
     auto warm_copy = [copy_threads, stream_copy](void* dst, const void* src, size_t bytes) {
         const size_t chunk = 256 << 10;  // (64 KB .. 8 MB measured alike)
         const i64 n_chunks = (i64)((bytes + chunk - 1) / chunk);

@@ -1,5 +1,9 @@
 #!/bin/bash
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-TAIL_AB_ONLY=default,store,nta timeout 900 python scripts/tail_ab.py chr1 1.0 5 2>&1 | grep "default\|store\|nta" | tee gpurun_out/r2y3_chr1.txt
-TAIL_AB_ONLY=default,store,nta timeout 900 python scripts/tail_ab.py pangenome 1.0 5 2>&1 | grep "default\|store\|nta" | tee gpurun_out/r2y3_pan.txt
+timeout 900 python bench.py --workload ecoli --steps 25 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('ecoli', round(d['ms_per_step'],3), round(d['e2e']['ms_per_step'],3), d['byte_identical_to_oracle'], d['tail_ms_rank0'])"
+timeout 900 python bench.py --workload pangenome --scale 0.25 --steps 10 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('pan0.25', round(d['ms_per_step'],3), round(d['e2e']['ms_per_step'],3), d['byte_identical_to_oracle'], d['tail_ms_rank0'], d['workload_sizes']['unitigs'])"
