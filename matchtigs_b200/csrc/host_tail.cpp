@@ -603,6 +603,233 @@ __attribute__((noinline, optimize("no-tree-slp-vectorize", "no-tree-vectorize"))
     io.cand_n = cand_n;
 }
 
+// The run loop used by default (MTG_WALK_CHAIN=carried selects walk_run above): the same carried
+// chain, kept in a handful of scalars so that the steady state lives in registers -- the slots expected 2 .. WALK_DEPTH
+// steps from now (p[]), the slot choices on the way as the low bits of one word (they ARE the index of the deepest
+// hint), and one flag saying that the chain is complete and regular (two-slot layout, first/second slots all the way).
+// A step of the steady state reads one hint, looks at the used bits of one far node and issues one prefetch.  Whenever
+// the chain does not hold (a run start, a target with three or four slots, a third or fourth slot on the way, a big
+// node, a slot used up in between) the step re-derives all levels from the record in hand, one look at the used bits
+// per level, and prefetches what it finds; the steady state resumes as soon as that yields a full regular chain.
+// (walk_run shifts two arrays through the stack every step: about 110 instructions per step against about 60 here; the
+// perfect-lookahead replay shows what they cost: every instruction of a step is paid once per step, T = L / d + w.)
+template <int PF, bool NTS, bool DIAG>
+__attribute__((noinline, optimize("no-tree-slp-vectorize", "no-tree-vectorize"))) static void walk_run_lean(RunIO& io, u32 s, u32 from_h) {
+    const WalkRec* const recs = io.recs;
+    u64* const used = io.used;
+    u32* const q_slot = io.q_slot;
+    u32* const q_from = io.q_from;
+    u32* const cand = io.cand;
+    size_t q_n = io.q_n, cand_n = io.cand_n;
+    auto mark = [&](u32 x) { used[x >> 6] |= 1ull << (x & 63); };
+    // (DIAG) how many steps before its use a record was asked for: the last 32 prefetches, looked up at every step
+    const WalkRec* pf_rec[32] = {};
+    u64 pf_step[32] = {};
+    u32 pf_n = 0;
+    auto prefetch_rec = [&](const void* p) {
+        if (PF == 1) __builtin_prefetch(p, 0, 0);
+        else if (PF == 2) __builtin_prefetch(p, 0, 1);
+        else __builtin_prefetch(p, 0, 3);
+        if (WALK_DEPTH >= 5) {
+            if (PF == 1) __builtin_prefetch(static_cast<const char*>(p) + 64, 0, 0);
+            else __builtin_prefetch(static_cast<const char*>(p) + 64, 0, 3);
+        }
+        if (DIAG) {
+            bool known = false;
+            for (u32 x = 0; x < 32; x++) known |= pf_rec[x] == p;
+            if (!known) pf_rec[pf_n & 31] = static_cast<const WalkRec*>(p), pf_step[pf_n & 31] = io.dg_steps, pf_n++;
+        }
+    };
+    auto append = [&](u32* v, size_t at, u32 x) {
+#if defined(__x86_64__)
+        if (NTS) {
+            __builtin_ia32_movnti(reinterpret_cast<int*>(v + at), (int)x);
+            return;
+        }
+#endif
+        v[at] = x;
+    };
+    auto peek = [&](u32 h, u32* j) -> u32 {
+        if (__builtin_expect((h & H_BIG) != 0, 0)) return NONE32;
+        const u32 base = h & H_BASE;
+        const u32 free_bits = ~slot_bits_of(used, base) & small_mask(h);
+        if (__builtin_expect(!free_bits, 0)) return NONE32;
+        *j = (u32)__builtin_ctz(free_bits);
+        return base + *j;
+    };
+    constexpr u32 IDX_MASK = (1u << (WALK_DEPTH - 1)) - 1u;
+    // p[0 .. deep): the slots expected for the next `deep` steps; the low `deep` bits of `path`: the slot choices that lead
+    // to them (0 / 1 each while the chain is regular) == the index of the hint one level further
+    u32 p[WALK_DEPTH + 1] = {};
+    u32 path = 0, deep = 0;
+    bool regular = false;
+    while (s != NONE32) {
+        const WalkRec& r = recs[s];
+        if (DIAG) {
+            u64 lead = 0;
+            for (u32 x = 0; x < 32; x++)
+                if (pf_rec[x] == &r) lead = io.dg_steps - pf_step[x];
+            io.probe_hist[0][std::min<u64>(lead, 39)]++;
+        }
+        const u32 ms = r.mslot;
+        mark(s);
+        mark(ms & SLOT_MASK);
+        append(q_slot, q_n, s | (ms & ~SLOT_MASK));
+        append(q_from, q_n, from_h);
+        q_n++;
+        const u32 c = r.to;
+        bool more;
+        const u32 nxt = first_unused_of(recs, used, c, &more);  // the next step is certain
+        cand[cand_n] = (u32)q_n;
+        cand_n += more;
+        if (__builtin_expect(regular && nxt == p[0] && !(c & H_BIG), 1)) {
+            if (__builtin_expect(deep == WALK_DEPTH - 1 && !(c & H_FOUR), 1)) {
+                // steady state: the far end grows by one level, everything moves one step closer
+                u32 j = 0;
+                const u32 sl = peek(r.h[walk_level_two(WALK_DEPTH) + (path & IDX_MASK)], &j);
+#pragma GCC unroll 8
+                for (u32 M = 0; M + 2 < WALK_DEPTH; M++) p[M] = p[M + 1];
+                if (__builtin_expect(sl != NONE32, 1)) {
+                    prefetch_rec(&recs[sl]);
+                    p[WALK_DEPTH - 2] = sl;
+                    path = 2 * path + j;
+                    regular = j < 2;  // a third or fourth slot ends what the records behind it follow
+                } else {
+                    regular = false;
+                }
+            } else {
+                // behind a target with three or four slots (whose layout ends one level earlier) the chain is one level short
+                // and catches up from the next record: as many levels as this record knows beyond the chain
+                // (`p` itself is only ever indexed by constants, so that it lives in registers: the variable part works on a copy)
+                u32 pa[WALK_DEPTH + 2];
+#pragma GCC unroll 8
+                for (u32 M = 0; M <= WALK_DEPTH; M++) pa[M] = p[M];
+                const bool four = (c & H_FOUR) != 0;
+                const u32 last = four ? WALK_DEPTH - 1 : WALK_DEPTH;
+                while (regular && deep < last) {
+                    u32 j = 0;
+                    const u32 L = deep + 1;
+                    const u32 sl = peek(r.h[(four ? walk_level_four(L) : walk_level_two(L)) + (path & ((1u << deep) - 1u))], &j);
+                    if (sl == NONE32) {
+                        regular = false;
+                        break;
+                    }
+                    prefetch_rec(&recs[sl]);
+                    pa[deep++] = sl;
+                    path = 2 * path + j;
+                    regular = j < 2;
+                }
+#pragma GCC unroll 8
+                for (u32 M = 0; M < WALK_DEPTH; M++) p[M] = pa[M + 1];
+                deep--;
+                if (deep == 0) regular = false;
+            }
+        } else if (nxt != NONE32) {
+            // all levels again from the record in hand
+            if (DIAG) io.dg_reset++, io.dg_big += (c & H_FOUR) != 0;
+            regular = false;
+            prefetch_rec(&recs[nxt]);
+            if (!(c & H_BIG)) {
+                const bool four = (c & H_FOUR) != 0;
+                const u32 last = four ? WALK_DEPTH - 1 : WALK_DEPTH;
+                u32 idx = nxt - (c & H_BASE);  // slot choice at `to`
+                bool open = true;  // (idx may be 2 or 3 here: the four-slot layout is indexed by it, and the steps behind no longer need it)
+                u32 found = 0;  // levels 2 .. found + 1: the slots of the `found` steps behind the next one
+                u32 pa[WALK_DEPTH + 1] = {};
+                for (u32 L = 2; open && L <= last; L++) {
+                    u32 j = 0;
+                    const u32 sl = peek(r.h[(four ? walk_level_four(L) : walk_level_two(L)) + idx], &j);
+                    if (sl == NONE32) {
+                        open = false;
+                        break;
+                    }
+                    prefetch_rec(&recs[sl]);
+                    pa[found++] = sl;
+                    open = j < 2;
+                    idx = 2 * idx + j;
+                }
+#pragma GCC unroll 8
+                for (u32 M = 0; M < WALK_DEPTH; M++) p[M] = pa[M];
+                deep = found;
+                path = idx;
+                regular = open && found > 0;
+            }
+        }
+        if (DIAG) io.dg_steps++, io.dg_have[regular ? WALK_DEPTH : 1]++;
+        from_h = c;
+        s = nxt;
+    }
+    io.q_n = q_n;
+    io.cand_n = cand_n;
+}
+
+// Diagnostic (MTG_WALK_REPLAY="mode:depth,..."): the finished walk is run again from its own slot sequence, with the
+// record `depth` steps ahead prefetched from that sequence -- the walk loop with a perfect lookahead of any depth, which
+// separates what the loop itself costs from what the hint chain costs.  mode bits: 1 = the prefetch address depends on
+// the record in hand (as a hint does), 2 = and on the used-bit word of the far slot, 4 = no used-bit work at all,
+// 8 = no queue appends, 16 = the slot of a step depends on the result of the step before (the walk's own dependence),
+// 32 = the prefetch is the first thing a step does.  Returns the number of steps whose first-unused slot differed from the sequence (must be 0).
+template <int PF>
+__attribute__((noinline, optimize("no-tree-slp-vectorize", "no-tree-vectorize"))) static u64 walk_replay(
+    const WalkRec* recs, u64* used, const u32* seq, size_t b, size_t e, u32 from_h, u32 depth, int mode, u32 zero, u32* q_slot, u32* q_from,
+    u32* cand) {
+    size_t q_n = b, cand_n = b;
+    u64 wrong = 0;
+    auto mark = [&](u32 x) { used[x >> 6] |= 1ull << (x & 63); };
+    u32 carried = 0;  // mode 16: the slot of a step depends on what the step before found, as in the walk itself
+    for (size_t i = b; i < e; i++) {
+        const u32 s = seq[i] ^ carried;
+        const WalkRec& r = recs[s];
+        const u32 ms = r.mslot;
+        const u32 c = r.to;
+        if (mode & 32) {  // the prefetch before everything else
+            u32 x = seq[i + depth];
+            if (mode & 1) x ^= c & zero;
+            if (mode & 2) x ^= (u32)used[x >> 6] & zero;
+            if (PF == 1) __builtin_prefetch(&recs[x], 0, 0);
+            else __builtin_prefetch(&recs[x], 0, 3);
+        }
+        if (!(mode & 4)) {
+            mark(s);
+            mark(ms & SLOT_MASK);
+        }
+        if (!(mode & 8)) {
+#if defined(__x86_64__)
+            __builtin_ia32_movnti(reinterpret_cast<int*>(q_slot + q_n), (int)(s | (ms & ~SLOT_MASK)));
+            __builtin_ia32_movnti(reinterpret_cast<int*>(q_from + q_n), (int)from_h);
+#else
+            q_slot[q_n] = s | (ms & ~SLOT_MASK), q_from[q_n] = from_h;
+#endif
+            q_n++;
+        }
+        if (!(mode & 4)) {
+            bool more;
+            const u32 nxt = first_unused_of(recs, used, c, &more);
+            cand[cand_n] = (u32)q_n;
+            cand_n += more;
+            wrong += (i + 1 < e) & (nxt != seq[i + 1]);
+            if (mode & 16) carried = nxt & zero;
+        } else if (mode & 16) {
+            carried = c & zero;
+        }
+        if (mode & 32) {
+            from_h = c;
+            continue;
+        }
+        u32 x = seq[i + depth];
+        if (mode & 1) x ^= c & zero;
+        if (mode & 2) x ^= (u32)used[x >> 6] & zero;
+        if (PF == 1) __builtin_prefetch(&recs[x], 0, 0);
+        else __builtin_prefetch(&recs[x], 0, 3);
+        if (sizeof(WalkRec) > 64) {  // 128-byte records: both lines, and the loop reads the second one as the walk does
+            __builtin_prefetch(reinterpret_cast<const char*>(&recs[x]) + 64, 0, PF == 1 ? 0 : 3);
+            wrong += r.h[WALK_HINTS - 1] == 0xFFFFFFF0u;
+        }
+        from_h = c;
+    }
+    return wrong;
+}
+
 using WalkRunFn = void (*)(RunIO&, u32, u32);
 template <bool HINTS, int PF>
 static WalkRunFn pick_walk_run(bool nts, bool diag) {
@@ -658,7 +885,26 @@ void walk_and_break(const WalkInput& in, TailOutput& out, TailScratch& scratch) 
     const char* nts_env = getenv("MTG_WALK_NTSTORE");
     const bool nt_store = !(nts_env && nts_env[0] == '0');
     const bool diag = trace_slow_calls() || getenv("MTG_WALK_PROBE") != nullptr || getenv("MTG_WALK_SPIN") != nullptr;
-    const WalkRunFn run = pick_walk_run(use_hints, pf_kind, nt_store, diag);
+    WalkRunFn run = pick_walk_run(use_hints, pf_kind, nt_store, diag);
+    const char* chain_env = getenv("MTG_WALK_CHAIN");  // A/B: carried = walk_run (also used for the probes), default = walk_run_lean
+    const bool probes = getenv("MTG_WALK_PROBE") != nullptr || getenv("MTG_WALK_SPIN") != nullptr;  // only walk_run has them
+    if (use_hints && !probes && !(chain_env && chain_env[0] == 'c')) {
+        if (diag) run = pf_kind == 1 ? walk_run_lean<1, true, true> : walk_run_lean<0, true, true>;
+        else if (pf_kind == 1) run = nt_store ? walk_run_lean<1, true, false> : walk_run_lean<1, false, false>;
+        else if (pf_kind == 2) run = nt_store ? walk_run_lean<2, true, false> : walk_run_lean<2, false, false>;
+        else run = nt_store ? walk_run_lean<0, true, false> : walk_run_lean<0, false, false>;
+    }
+
+    // MTG_WALK_REPLAY: keep the initial used bits and every run's slot sequence for the replay diagnostic below
+    const char* replay_env = getenv("MTG_WALK_REPLAY");
+    std::vector<u64> replay_used0;
+    std::vector<u32> replay_seq;
+    struct ReplayRun {
+        size_t b, e;
+        u32 from_h;
+    };
+    std::vector<ReplayRun> replay_runs;
+    if (replay_env) replay_used0.assign(used, used + in.n_slots / 64 + 2);
     RunIO io{};
     io.recs = recs;
     io.used = used;
@@ -676,7 +922,12 @@ void walk_and_break(const WalkInput& in, TailOutput& out, TailScratch& scratch) 
                     "next slot %llu, big-node steps %llu, run ends %llu, without hints %llu\n", (unsigned long long)io->dg_steps,
                     (unsigned long long)h[1], (unsigned long long)h[2], (unsigned long long)h[3], (unsigned long long)h[4], (unsigned long long)h[5],
                     (unsigned long long)io->dg_reset, (unsigned long long)io->dg_big, (unsigned long long)io->dg_end, (unsigned long long)io->dg_nohint);
-            if (!io->probe) return;
+            if (!io->probe) {
+                fprintf(stderr, "[mtg trace] walk: steps by how many steps earlier their record was asked for (0 = never):");
+                for (int b = 0; b < 12; b++) fprintf(stderr, " %d:%llu", b, (unsigned long long)io->probe_hist[0][b]);
+                fprintf(stderr, "\n");
+                return;
+            }
             const char* names[5] = {"record load", "used bits of the target", "used bits of the far node", "used bits of the mirror slot",
                                     "(probe alone, L1 hit)"};
             for (int w = 0; w < 5; w++) {
@@ -701,6 +952,9 @@ void walk_and_break(const WalkInput& in, TailOutput& out, TailScratch& scratch) 
     auto weight_of = [&](u32 q) { return (q & SLOT_BREAK) ? in.k : in.dummy_w[in.slot_edge[q & SLOT_MASK] - E0]; };  // q is a dummy
     auto breaks = [&](u32 q) { return (q & SLOT_BREAK) != 0; };
     u64 steps_total = 0;
+    const bool timing = trace_slow_calls();
+    double ms_runs = 0;
+    const double t_loop = now_ms();
     for (u64 e0 = 0; e0 < E0 && steps_total < E / 2; e0++) {
         if (is_used(in.slot_of_edge[e0])) continue;
         // one closed walk per component, started at the lowest unused edge id (every node owns an original edge, so the
@@ -718,7 +972,14 @@ void walk_and_break(const WalkInput& in, TailOutput& out, TailScratch& scratch) 
             cand.push_back((u32)q_slot.size());  // a walk start is always probed again
             io.q_slot = q_slot.p, io.q_from = q_from.p, io.q_n = q_slot.n;
             io.cand = cand.p, io.cand_n = cand.n;
+            const size_t run_b = io.q_n;
+            const double tr0 = timing ? now_ms() : 0.0;
             run(io, start_slot, start_from);
+            if (timing) ms_runs += now_ms() - tr0;
+            if (replay_env) {
+                replay_runs.push_back({replay_seq.size(), replay_seq.size() + (io.q_n - run_b), start_from});
+                for (size_t i = run_b; i < io.q_n; i++) replay_seq.push_back(q_slot.p[i] & SLOT_MASK);
+            }
             q_slot.n = q_from.n = io.q_n;
             cand.n = io.cand_n;
             if (rooted) children.back().end = (u32)q_slot.size();  // the run just appended belongs to the head's block
@@ -888,6 +1149,9 @@ void walk_and_break(const WalkInput& in, TailOutput& out, TailScratch& scratch) 
     // E. (greedytigs/mod.rs:708-715) every edge pair was walked exactly once, or the graph was not Eulerian after all
     MTG_REQUIRE(steps_total == E / 2, MTG_ERR_INTERNAL, "Failed to make the graph Eulerian (the closed walks do not cover every edge).");
     double tt = now_ms();
+    if (timing && steps_total > 100000)
+        fprintf(stderr, "[mtg trace] walk: set-up %.2f ms, run loops %.2f ms (%.2f ns per step), start scan + re-roots %.2f ms, breaking %.2f ms\n",
+                t_loop - t3, ms_runs, 1e6 * ms_runs / (double)steps_total, tt - t_loop - ms_runs - ms_break, ms_break);
     // slots -> edge ids: independent gathers, spread over the host cores
     if (out.edges_pinned) out.edges_pinned->resize(walk_slots.size());
     else out.walk_edges.resize(walk_slots.size());
@@ -904,6 +1168,34 @@ void walk_and_break(const WalkInput& in, TailOutput& out, TailScratch& scratch) 
         fprintf(stderr, "[mtg trace] breaking: cycle order + cuts + piece emission %.2f ms, slot -> edge gather %.2f ms\n", ms_break, t4 - tt);
     out.ms_break = ms_break + (t4 - tt);
     out.ms_walk = t4 - t3 - out.ms_break;
+    if (replay_env && !replay_seq.empty()) {
+        const size_t n = replay_seq.size();
+        replay_seq.resize(n + 64, replay_seq[0]);
+        std::vector<u32> q2(n + 64), f2(n + 64), c2(n + 64);
+        volatile u32 zero_src = 0;
+        const u32 zero = zero_src;
+        std::string spec = std::string("0:4,") + replay_env;  // the first pass also touches the scratch pages: discarded
+        bool first = true;
+        for (size_t p = 0; p < spec.size();) {
+            size_t q = spec.find(',', p);
+            if (q == std::string::npos) q = spec.size();
+            int mode = 0, depth = 4;
+            sscanf(spec.substr(p, q - p).c_str(), "%d:%d", &mode, &depth);
+            depth = std::max(0, std::min(depth, 63));
+            p = q + 1;
+            memcpy(used, replay_used0.data(), replay_used0.size() * sizeof(u64));
+            u64 wrong = 0;
+            const double ta = now_ms();
+            for (const ReplayRun& r : replay_runs)
+                wrong += (pf_kind == 1 ? walk_replay<1> : walk_replay<0>)(recs, used, replay_seq.data(), r.b, r.e, r.from_h, (u32)depth, mode, zero,
+                                                                          q2.data(), f2.data(), c2.data());
+            const double tb = now_ms();
+            if (!first)
+                fprintf(stderr, "[mtg replay] mode %d depth %2d: %6.2f ns per step (%zu steps, %zu runs, %llu steps off the sequence)\n", mode, depth,
+                        1e6 * (tb - ta) / (double)n, n, replay_runs.size(), (unsigned long long)wrong);
+            first = false;
+        }
+    }
 }
 
 }  // namespace

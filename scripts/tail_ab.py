@@ -21,7 +21,12 @@ ctx.finish_walks()
 print('THP:', open('/sys/kernel/mm/transparent_hugepage/enabled').read().strip(), '| defrag:', open('/sys/kernel/mm/transparent_hugepage/defrag').read().strip(), '|', [l.strip() for l in open('/proc/self/smaps_rollup') if 'AnonHuge' in l or l.startswith('Rss')])
 VARIANTS = (("default", {}), ("memcpy", {"MTG_TAIL_COPY": "memcpy"}), ("spin0", {"MTG_WALK_SPIN": "0"}), ("spin10", {"MTG_WALK_SPIN": "10"}),
             ("spin20", {"MTG_WALK_SPIN": "20"}), ("spin40", {"MTG_WALK_SPIN": "40"}), ("spin80", {"MTG_WALK_SPIN": "80"}), ("sources1", {"MTG_WALK_SOURCES": "1"}), ("fast0", {"MTG_WALK_FAST": "0"}), ("store", {"MTG_WALK_NTSTORE": "0"}),
-            ("t0", {"MTG_WALK_PREFETCH": "t0"}), ("nohint", {"MTG_TAIL_NOHINT": "1"}), ("default", {}), ("probe", {"MTG_WALK_PROBE": "1"}))
+            ("t0", {"MTG_WALK_PREFETCH": "t0"}), ("nohint", {"MTG_TAIL_NOHINT": "1"}), ("default", {}), ("probe", {"MTG_WALK_PROBE": "1"}),
+            ("carried", {"MTG_WALK_CHAIN": "carried"}), ("lean2", {}), ("carried2", {"MTG_WALK_CHAIN": "carried"}), ("lean3", {}),
+            # perfect-lookahead replay of the finished walk: mode (1: address depends on the record in hand, 2: and on the far used
+            # word, 4: no used-bit work, 8: no queue appends) : depth
+            ("replay", {"MTG_WALK_REPLAY": os.environ.get("TAIL_AB_REPLAY", ",".join(f"{m}:{d}" for m in (0, 1, 3) for d in (3, 4, 5, 6, 8, 12)) +
+                                                          ",4:4,4:8,5:4,5:8,8:4,8:8,9:4,9:8,12:4,12:8,13:4,13:8")}))
 only = os.environ.get("TAIL_AB_ONLY")  # comma-separated labels
 for label, env in VARIANTS:
     if only and label not in only.split(","):

@@ -104,7 +104,9 @@ def test_host_tail_threaded_preparation_with_hints(mt):
 
 
 WALK_SWITCHES = [{}, {"MTG_WALK_FAST": "0"}, {"MTG_WALK_SOURCES": "1"}, {"MTG_WALK_SOURCES": "3"}, {"MTG_WALK_NTSTORE": "0"},
-                 {"MTG_WALK_PREFETCH": "t0"}, {"MTG_WALK_PREFETCH": "2"}, {"MTG_WALK_PROBE": "1"}, {"MTG_HOST_THREADS": "3"}]
+                 {"MTG_WALK_PREFETCH": "t0"}, {"MTG_WALK_PREFETCH": "2"}, {"MTG_WALK_PROBE": "1"}, {"MTG_HOST_THREADS": "3"},
+                 {"MTG_WALK_CHAIN": "carried"}, {"MTG_WALK_CHAIN": "carried", "MTG_WALK_SOURCES": "1"}, {"MTG_TRACE": "1"},
+                 {"MTG_WALK_REPLAY": "0:4,19:5,13:2,49:3"}]
 
 
 @pytest.mark.parametrize("seed", range(8))
