@@ -886,9 +886,11 @@ void walk_and_break(const WalkInput& in, TailOutput& out, TailScratch& scratch) 
     const bool nt_store = !(nts_env && nts_env[0] == '0');
     const bool diag = trace_slow_calls() || getenv("MTG_WALK_PROBE") != nullptr || getenv("MTG_WALK_SPIN") != nullptr;
     WalkRunFn run = pick_walk_run(use_hints, pf_kind, nt_store, diag);
+    bool lean_loop = false;
     const char* chain_env = getenv("MTG_WALK_CHAIN");  // A/B: carried = walk_run (also used for the probes), default = walk_run_lean
     const bool probes = getenv("MTG_WALK_PROBE") != nullptr || getenv("MTG_WALK_SPIN") != nullptr;  // only walk_run has them
     if (use_hints && !probes && !(chain_env && chain_env[0] == 'c')) {
+        lean_loop = true;
         if (diag) run = pf_kind == 1 ? walk_run_lean<1, true, true> : walk_run_lean<0, true, true>;
         else if (pf_kind == 1) run = nt_store ? walk_run_lean<1, true, false> : walk_run_lean<1, false, false>;
         else if (pf_kind == 2) run = nt_store ? walk_run_lean<2, true, false> : walk_run_lean<2, false, false>;
@@ -914,10 +916,15 @@ void walk_and_break(const WalkInput& in, TailOutput& out, TailScratch& scratch) 
     io.spin = getenv("MTG_WALK_SPIN") ? (u32)atoi(getenv("MTG_WALK_SPIN")) : 0;
     struct DiagAtExit {
         const RunIO* io;
-        bool on;
+        bool on, lean;
         ~DiagAtExit() {
             if (!on || io->dg_steps < 100000) return;
             const u64* h = io->dg_have;
+            if (lean)
+                fprintf(stderr, "[mtg trace] walk (lean loop): %llu steps, chain complete and regular after %llu of them, %llu steps re-derived all "
+                        "levels from the record in hand (%llu of them at a target with three or four slots)\n", (unsigned long long)io->dg_steps,
+                        (unsigned long long)h[WALK_DEPTH], (unsigned long long)io->dg_reset, (unsigned long long)io->dg_big);
+            else
             fprintf(stderr, "[mtg trace] walk: %llu steps, chain known to level 1/2/3/4/5 after a step: %llu/%llu/%llu/%llu/%llu, unexpected "
                     "next slot %llu, big-node steps %llu, run ends %llu, without hints %llu\n", (unsigned long long)io->dg_steps,
                     (unsigned long long)h[1], (unsigned long long)h[2], (unsigned long long)h[3], (unsigned long long)h[4], (unsigned long long)h[5],
@@ -937,7 +944,7 @@ void walk_and_break(const WalkInput& in, TailOutput& out, TailScratch& scratch) 
                 fprintf(stderr, "\n");
             }
         }
-    } diag_at_exit{&io, diag};
+    } diag_at_exit{&io, diag, lean_loop};
     // Positions whose from-node may still own an unused out-edge, in cycle order from the head.  A position is only
     // recorded if its node had slots left when the walk passed (exhaustion is permanent), which skips about half of
     // the re-root probes.
