@@ -130,6 +130,29 @@ def test_host_tail_with_lookahead_hints_on_small_graphs(mt, seed, monkeypatch):
         assert all(np.array_equal(a, b) for a, b in zip(walks, ow)), env
 
 
+def test_walk_lookahead_reaches_its_depth(mt, monkeypatch, capfd):
+    """The hints never change a result, so a broken lookahead would only show as a slower walk.  MTG_TRACE prints how many
+    steps ahead every record of the walk was asked for; on a chr1-like graph (few nodes with more than two out-edges) the
+    lean run loop must ask for most records a full WALK_DEPTH = 4 steps ahead and for next to none of them too late."""
+    import re
+    text, k, info = tools.config_unitigs("chr1", 0.05)
+    o, args = oracle_inputs(text, k, "fasta", euler_fast=True)
+    monkeypatch.setenv("MTG_TAIL_FORCEHINT", "1")
+    monkeypatch.setenv("MTG_TRACE", "1")
+    capfd.readouterr()
+    walks, _, _ = mt.api.host_tail(k, *args)
+    err = capfd.readouterr().err
+    m = re.search(r"steps by how many steps earlier their record was asked for \(0 = never\):((?: \d+:\d+)+)", err)
+    assert m, err[-2000:]
+    hist = {int(a): int(b) for a, b in (x.split(":") for x in m.group(1).split())}
+    steps = sum(hist.values())
+    assert steps > 100_000
+    assert hist[4] >= 0.70 * steps, hist          # measured: 76 % on this graph, 75.5 % on chr1 x 1.0
+    assert hist[0] + hist[1] <= 0.005 * steps, hist  # run starts and the rare slot used up in between
+    ow = o.walks()
+    assert len(walks) == len(ow) and all(np.array_equal(a, b) for a, b in zip(walks, ow))
+
+
 @pytest.mark.parametrize("seed", range(6))
 def test_host_tail_heavy_matching_dummies_take_the_generic_breaking_path(mt, seed):
     """Behind the GPU matching a matching dummy always weighs less than k, and the tail recognises breaking dummies by edge
