@@ -1,5 +1,6 @@
 """CPU tests of the product's host-side logic (no GPU): the C ABI loads and exports every declared symbol,
 the record reader, and the host-sequential tail against the oracle on the oracle's own graph + triples."""
+import os
 import random
 import re
 from pathlib import Path
@@ -130,27 +131,38 @@ def test_host_tail_with_lookahead_hints_on_small_graphs(mt, seed, monkeypatch):
         assert all(np.array_equal(a, b) for a, b in zip(walks, ow)), env
 
 
-def test_walk_lookahead_reaches_its_depth(mt, monkeypatch, capfd):
+def test_walk_lookahead_reaches_its_depth(mt):
     """The hints never change a result, so a broken lookahead would only show as a slower walk.  MTG_TRACE prints how many
     steps ahead every record of the walk was asked for; on a chr1-like graph (few nodes with more than two out-edges) the
-    lean run loop must ask for most records a full WALK_DEPTH = 4 steps ahead and for next to none of them too late."""
+    lean run loop must ask for most records a full WALK_DEPTH = 4 steps ahead and for next to none of them too late.
+    (Own process: the library reads MTG_TRACE once.)"""
     import re
-    text, k, info = tools.config_unitigs("chr1", 0.05)
-    o, args = oracle_inputs(text, k, "fasta", euler_fast=True)
-    monkeypatch.setenv("MTG_TAIL_FORCEHINT", "1")
-    monkeypatch.setenv("MTG_TRACE", "1")
-    capfd.readouterr()
-    walks, _, _ = mt.api.host_tail(k, *args)
-    err = capfd.readouterr().err
-    m = re.search(r"steps by how many steps earlier their record was asked for \(0 = never\):((?: \d+:\d+)+)", err)
-    assert m, err[-2000:]
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    code = (
+        "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import numpy as np, tools, matchtigs_b200 as mt\n"
+        "from test_host_logic import oracle_inputs\n"
+        "text, k, info = tools.config_unitigs('chr1', 0.05)\n"
+        "o, args = oracle_inputs(text, k, 'fasta', euler_fast=True)\n"
+        "walks, _, _ = mt.api.host_tail(k, *args)\n"
+        "ow = o.walks()\n"
+        "assert len(walks) == len(ow) and all(np.array_equal(a, b) for a, b in zip(walks, ow))\n"
+    ) % (str(root), str(root / "tests"))
+    env = dict(os.environ, MTG_TAIL_FORCEHINT="1", MTG_TRACE="1")
+    for name in ("MTG_WALK_CHAIN", "MTG_WALK_PROBE", "MTG_WALK_SPIN", "MTG_TAIL_NOHINT"):
+        env.pop(name, None)
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    m = re.search(r"steps by how many steps earlier their record was asked for \(0 = never\):((?: \d+:\d+)+)", r.stderr)
+    assert m, r.stderr[-2000:]
     hist = {int(a): int(b) for a, b in (x.split(":") for x in m.group(1).split())}
     steps = sum(hist.values())
     assert steps > 100_000
     assert hist[4] >= 0.70 * steps, hist          # measured: 76 % on this graph, 75.5 % on chr1 x 1.0
     assert hist[0] + hist[1] <= 0.005 * steps, hist  # run starts and the rare slot used up in between
-    ow = o.walks()
-    assert len(walks) == len(ow) and all(np.array_equal(a, b) for a, b in zip(walks, ow))
 
 
 @pytest.mark.parametrize("seed", range(6))
